@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of the sparse-matmul hot path (BASELINE.json):
+
+    SpMM effective HBM GB/s (and GFLOP/s) at 1/2/4/8 B200 vs MKL CPU
+
+Workload (BASELINE.json configs[1]):  CSR(1M x 1M, 50 nnz/row, fp32) x dense(1M x 128),
+`out=` accumulate path (beta = 0.5).  One step = one pass Y := A @ X + 0.5 * Y.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a CUDA)
+    python bench.py --impl reference --steps K --warmup W    # the reference's MKL path on host cores
+
+N > 1 is launched by torch.distributed.run, one rank per GPU: every rank owns
+one 1M-row block of a (N x 1M)-row product (weak scaling), X is replicated, and
+the SpMM epilogue stores each finished row into every rank's full output panel
+over NVLink peer mappings (the fused all-gather of SURVEY.md §8e);
+`--allgather nccl` runs kernel + ncclAllGather instead, `--allgather none` skips
+the exchange.
+
+Prints ONE JSON line (rank 0).  `value` times the kernel with operands resident
+in HBM; `e2e` times the public API call (dot_product_mkl on host arrays, H2D and
+D2H inside); `roofline` uses algorithmic (gather-model) bytes, SURVEY.md §8d;
+`cpu_baseline` is the reference's MKL call sequence on this host's cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_ROWS = 1_000_000
+K_COLS = 1_000_000
+NNZ_PER_ROW = 50
+N_DENSE = 128
+BETA = 0.5
+DTYPE = np.float32
+
+
+# ----------------------------------------------------------------------------- workload
+def make_workload(rows, cols, per_row, n_dense, seed):
+    """BASELINE C2 recipe: exactly `per_row` sorted distinct columns per
+    row, values U[0.5, 1.5) (no cancellation), X and Y uniform random; seeded."""
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, cols, size=(rows, per_row), dtype=np.int32)
+    idx.sort(axis=1)
+    for _ in range(6):  # re-draw duplicates
+        dup = np.zeros(idx.shape, dtype=bool)
+        dup[:, 1:] = idx[:, 1:] == idx[:, :-1]
+        n_dup = int(dup.sum())
+        if n_dup == 0:
+            break
+        idx[dup] = rng.integers(0, cols, size=n_dup, dtype=np.int32)
+        idx.sort(axis=1)
+    indptr = np.arange(0, rows * per_row + 1, per_row, dtype=np.int32)
+    data = rng.random(rows * per_row, dtype=np.float32) + np.float32(0.5)
+    a = sp.csr_matrix((data, idx.ravel(), indptr), shape=(rows, cols))
+    x = np.random.default_rng(seed + 2).random((cols, n_dense), dtype=np.float32)
+    y = np.random.default_rng(seed + 3).random((rows, n_dense), dtype=np.float32)
+    return a, x, y
+
+
+def algorithmic_bytes(rows, nnz, n_dense, beta_nonzero=True, si=4, sv=4):
+    """Gather-model bytes of one SpMM launch:
+    (si+sv) + N*sv per stored entry, N*sv*(1+[beta!=0]) per output row, indptr once."""
+    return nnz * (si + sv) + (rows + 1) * 8 + nnz * n_dense * sv + rows * n_dense * sv * (2 if beta_nonzero else 1)
+
+
+def unique_bytes(rows, cols, nnz, n_dense, beta_nonzero=True, si=4, sv=4):
+    return nnz * (si + sv) + (rows + 1) * 8 + cols * n_dense * sv + rows * n_dense * sv * (2 if beta_nonzero else 1)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, f[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_spmm_runner(a, x, y0, threads=None):
+    """The reference's CPU path for this workload: real oneMKL through the reference's
+    call sequence when reachable (oracle/mkl_ref.py), else the C restatement."""
+    from oracle import mkl_ref
+    from oracle import oracle as orc
+
+    if mkl_ref.available():
+        if threads:
+            mkl_ref.set_threads(threads)
+        cores = threads or mkl_ref.max_threads()
+        h = mkl_ref.Handle(a)
+        y = y0.copy()
+
+        def step():
+            mkl_ref.spmm(a, x, beta=BETA, y=y, handle=h)
+            return y
+
+        kind, what = "reference", f"mkl_sparse_s_mm, {mkl_ref.version_string()} (embedded in libtorch_cpu), " \
+                                  "reference call sequence _common.py:310-319 -> _sparse_dense.py:111-123"
+        return step, kind, cores, what
+    orc.build()
+    cores = threads or orc.max_threads()
+    orc.set_threads(cores)
+    y = y0.copy()
+
+    def step():
+        orc.c_spmm(a, x, beta=BETA, y=y)
+        return y
+
+    return step, "port", cores, "oracle/sdb_oracle.c orc_spmm_f32 (OpenMP)"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    a, x, y0 = make_workload(M_ROWS, K_COLS, NNZ_PER_ROW, N_DENSE, seed=0)
+    step, kind, cores, what = cpu_spmm_runner(a, x, y0)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    g = algorithmic_bytes(M_ROWS, a.nnz, N_DENSE)
+    value = g / dt / 1e9
+    line = {
+        "impl": "reference", "metric": "spmm_effective_hbm_gbs", "value": value, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "gflops": 2.0 * a.nnz * N_DENSE / dt / 1e9,
+        "config": workload_config(1, "none"),
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": kind,
+                         "sample": f"full workload, every step ({what})"},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus, allgather):
+    return {
+        "workload": f"CSR({M_ROWS}x{K_COLS}, {NNZ_PER_ROW} nnz/row, fp32) x dense({K_COLS}x{N_DENSE}) per GPU, "
+                    f"out= accumulate (beta={BETA}); BASELINE.json configs[1]",
+        "rows_per_gpu": M_ROWS, "cols": K_COLS, "nnz_per_row": NNZ_PER_ROW, "n_dense": N_DENSE, "beta": BETA,
+        "parallelism": f"row-sharded x{n_gpus}, X replicated, allgather={allgather}",
+        "cache": "inputs larger than L2 (A 0.4 GB + X 0.5 GB + Y 0.5 GB vs 126 MB L2); no flush needed",
+    }
+
+
+# ----------------------------------------------------------------------------- our arm
+def pinned_like(arr, lib):
+    """Copy `arr` into page-locked host memory (numpy view over sdb_host_alloc)."""
+    p = ctypes.c_void_p()
+    st = lib.sdb_host_alloc(ctypes.byref(p), arr.nbytes)
+    if st != 0:
+        raise RuntimeError("sdb_host_alloc failed")
+    buf = (ctypes.c_char * arr.nbytes).from_address(p.value)
+    out = np.frombuffer(buf, dtype=arr.dtype).reshape(arr.shape)
+    out[...] = arr
+    return out
+
+
+def spot_check(plan, a, x, y0, steps, beta, n_rows=8):
+    """A few rows of what was just timed, recomputed with numpy in float64:
+    after k steps of y <- A x + beta y,  y_k = (1 - beta^k)/(1 - beta) * A x + beta^k * y0."""
+    rows = np.linspace(0, a.shape[0] - 1, n_rows).astype(np.int64)
+    worst = 0.0
+    for r in rows:
+        s, e = a.indptr[r], a.indptr[r + 1]
+        ax = (a.data[s:e].astype(np.float64)[:, None] * x[a.indices[s:e]].astype(np.float64)).sum(axis=0)
+        want = (1.0 - beta ** steps) / (1.0 - beta) * ax + beta ** steps * y0[r].astype(np.float64)
+        got = plan.read_rows(plan.panel_row0 + int(r), 1)[0].astype(np.float64)
+        worst = max(worst, float(np.max(np.abs(got - want) / np.abs(want))))
+    return {"rows_checked": int(n_rows), "max_rel_err": worst, "ok": bool(worst < 1e-5)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import sparse_dot_b200 as sdb
+    from sparse_dot_b200 import _lib
+    from sparse_dot_b200 import sharded
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    lib = _lib.SDB.lib
+    _lib.check(lib.sdb_set_device(local), "sdb_set_device")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mode = args.allgather if world > 1 else "none"
+
+    rows, cols, n = args.rows, K_COLS, N_DENSE
+    a, x, y0 = make_workload(rows, cols, NNZ_PER_ROW, n, seed=rank * 10)
+    x = make_workload(1, cols, 1, n, seed=0)[1] if world > 1 else x  # X is replicated: same on every rank
+    nnz = a.nnz
+
+    # ---- operands resident in HBM
+    plan = sharded.RowShardedSpMM(a, n, world_size=world, rank=rank, allgather=mode,
+                                  group=dist.group.WORLD if world > 1 else None)
+    plan.set_x(x)
+    plan.set_local_y(y0)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        plan.run(alpha=1.0, beta=BETA, stream_ptr=stream.cuda_stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = sdb.kernel_launches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(stream)
+    sync_all()
+    launches = sdb.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+
+    # parity spot check of what was just timed (rank-local rows), against the CPU oracle
+    check = spot_check(plan, a, x, y0, steps=args.warmup + args.steps, beta=BETA)
+
+    # ---- end to end through the public API on host arrays (pinned), rank-local shard
+    e2e = None
+    if not args.no_e2e:
+        xa = pinned_like(x, lib)
+        ya = pinned_like(y0, lib)
+        ap = sp.csr_matrix((pinned_like(a.data, lib), pinned_like(a.indices, lib), pinned_like(a.indptr, lib)),
+                           shape=a.shape)
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        sdb.dot_product_mkl(ap, xa, out=ya, out_scalar=BETA)  # warm-up (allocator pools, pinned ring)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sdb.dot_product_mkl(ap, xa, out=ya, out_scalar=BETA)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item()) / e2e_steps
+        phases = sdb.last_timing_ms()
+        g1 = algorithmic_bytes(rows, nnz, n)
+        e2e = {
+            "value": g1 * world / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3, "steps": e2e_steps,
+            "h2d_bytes_per_step": int(a.data.nbytes + a.indices.nbytes + a.indptr.nbytes + x.nbytes + y0.nbytes),
+            "d2h_bytes_per_step": int(y0.nbytes),
+            "host_memory": "pinned (sdb_host_alloc)",
+            "device_phase_ms": {"h2d": phases[0], "kernels": phases[1], "d2h": phases[2]},
+            "api": "sparse_dot_b200.dot_product_mkl(csr, ndarray, out=, out_scalar=) -> sdb_create_csr + sdb_spmm",
+        }
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    g = algorithmic_bytes(rows, nnz, n)
+    u = unique_bytes(rows, cols, nnz, n)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    k_ms = float(np.mean(kernel_ms))
+    achieved = g / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except ValueError:
+            traffic = None
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): a bounded sample = 3 full-workload steps
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cstep, kind, cores, what = cpu_spmm_runner(a, x, y0)
+        cstep()
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cstep()
+        cdt = (time.perf_counter() - t0) / reps
+        cpu = {"value": g / cdt / 1e9, "unit": "GB/s", "cores": cores, "kind": kind, "ms_per_step": cdt * 1e3,
+               "gflops": 2.0 * nnz * n / cdt / 1e9,
+               "sample": f"{reps} full-workload steps after 1 warm-up ({what})"}
+
+    line = {
+        "metric": "spmm_effective_hbm_gbs", "value": g * world / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "gflops": 2.0 * nnz * n * world / (ms_per_step * 1e-3) / 1e9,
+        "config": workload_config(world, mode),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "spmm_rowmajor_kernel<float,4,32>",
+                     "kernel_ms": k_ms, "algorithmic_bytes": g, "unique_bytes": u,
+                     "frac_of_8TBs_nominal": achieved / 8000.0,
+                     "model": "gather model: (4+4)+128*4 B per nnz, 128*4*2 B per row, 8 B per indptr entry"},
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "parity_spot_check": check,
+        "version": sdb.get_version_string(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--allgather", choices=["fused", "nccl", "none"], default="fused")
+    ap.add_argument("--rows", type=int, default=M_ROWS, help="rows per GPU (default: the BASELINE config)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,241 @@
+/*
+ * sdb200.h — C ABI of libsdb200.so, the B200 (sm_100a) sparse-matmul backend that
+ * sits where Intel MKL's inspector-executor sparse BLAS sits under sparse_dot_mkl.
+ *
+ * Every entry point replaces one (family of) MKL routine(s) the reference binds
+ * through ctypes in sparse_dot_mkl/_mkl_interface/_cfunctions.py; the reference
+ * call site is cited next to each declaration (paths relative to the reference
+ * checkout).  Conventions:
+ *
+ *   - plain C, no C++/torch types; all sizes are explicit-width integers;
+ *   - every routine returns an sdb_status with MKL's sparse_status_t numbering
+ *     (_mkl_interface/_constants.py:2-10), so the reference's
+ *     _check_return_value (_common.py:645-668) works unchanged;
+ *   - sdb_last_error() returns a thread-local human-readable message;
+ *   - calls are synchronous: when a routine returns, its results are in the
+ *     caller's memory (host entry points) or complete on `stream` (the *_dev
+ *     entry points are stream-ordered and do not synchronise);
+ *   - host input buffers are borrowed only for the duration of the call (they
+ *     are copied to HBM); a handle owns its device memory until sdb_destroy;
+ *   - nothing here falls back to the CPU: without a usable GPU the compute
+ *     entry points return SDB_STATUS_EXECUTION_FAILED.
+ */
+#ifndef SDB200_H
+#define SDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_API __attribute__((visibility("default")))
+
+/* ---- status codes: sparse_status_t, _constants.py:2-10 ------------------- */
+typedef int sdb_status;
+#define SDB_STATUS_SUCCESS          0
+#define SDB_STATUS_NOT_INITIALIZED  1
+#define SDB_STATUS_ALLOC_FAILED     2
+#define SDB_STATUS_INVALID_VALUE    3
+#define SDB_STATUS_EXECUTION_FAILED 4
+#define SDB_STATUS_INTERNAL_ERROR   5
+#define SDB_STATUS_NOT_SUPPORTED    6
+
+/* ---- enums shared with the reference: _constants.py:13-19 ----------------- */
+#define SDB_LAYOUT_ROW_MAJOR 101 /* LAYOUT_CODE_C */
+#define SDB_LAYOUT_COL_MAJOR 102 /* LAYOUT_CODE_F */
+#define SDB_OP_NON_TRANSPOSE       10
+#define SDB_OP_TRANSPOSE           11
+#define SDB_OP_CONJUGATE_TRANSPOSE 12
+
+/* value types: the s/d/c/z letter of the MKL routine name */
+#define SDB_F32  0
+#define SDB_F64  1
+#define SDB_C64  2
+#define SDB_C128 3
+
+/* storage formats of a handle */
+#define SDB_FMT_CSR 0
+#define SDB_FMT_CSC 1
+#define SDB_FMT_BSR 2
+
+/* Opaque device-resident sparse matrix: replaces sparse_matrix_t
+ * (_mkl_interface/_structs.py:5-9). */
+typedef struct sdb_mat sdb_mat;
+
+/* ======================= handles ============== */
+
+/* mkl_sparse_?_create_csr / _create_csc (_cfunctions.py:525-536, called at
+ * _common.py:310-319).  indptr has rows+1 (CSR) / cols+1 (CSC) entries — the
+ * reference's rows_start=indptr[:-1], rows_end=indptr[1:] pair collapsed back
+ * into scipy's 3-array form.  index_bits is 32 or 64 and describes BOTH host
+ * index arrays (scipy keeps them the same width).  Zero-based only. */
+SDB_API sdb_status sdb_create_csr(sdb_mat** out, int64_t rows, int64_t cols,
+                                  const void* indptr, const void* indices, int index_bits,
+                                  const void* values, int dtype);
+SDB_API sdb_status sdb_create_csc(sdb_mat** out, int64_t rows, int64_t cols,
+                                  const void* indptr, const void* indices, int index_bits,
+                                  const void* values, int dtype);
+
+/* mkl_sparse_?_create_bsr (_cfunctions.py:538-551, called at _common.py:368-379).
+ * Square blocks; block_layout is SDB_LAYOUT_ROW_MAJOR / _COL_MAJOR for the
+ * elements inside one block. */
+SDB_API sdb_status sdb_create_bsr(sdb_mat** out, int64_t block_rows, int64_t block_cols,
+                                  int64_t block_size, int block_layout,
+                                  const void* indptr, const void* indices, int index_bits,
+                                  const void* values, int dtype);
+
+/* Zero-copy CSR handle over arrays ALREADY in HBM (borrowed; the caller keeps
+ * them alive).  d_indptr is int64[rows+1], d_indices int32[nnz].  This is the
+ * analogue of MKL's zero-copy create for device-resident callers (§8f rank 3)
+ * and what bench.py uses for the HBM-resident `value`. */
+SDB_API sdb_status sdb_create_csr_dev(sdb_mat** out, int64_t rows, int64_t cols, int64_t nnz,
+                                      const int64_t* d_indptr, const int32_t* d_indices,
+                                      const void* d_values, int dtype);
+
+/* mkl_sparse_destroy (_common.py:671-680).  NULL -> SDB_STATUS_NOT_INITIALIZED,
+ * which the reference surfaces as ValueError (tests/test_mkl.py:128-141). */
+SDB_API sdb_status sdb_destroy(sdb_mat* m);
+
+/* Shape query; with sdb_export it replaces mkl_sparse_?_export_csr/csc/bsr
+ * (_cfunctions.py:553-564, called at _common.py:442-451, 542-553).  For BSR
+ * rows/cols are BLOCK counts and nnz counts BLOCKS, as MKL reports them. */
+SDB_API sdb_status sdb_get_info(const sdb_mat* m, int* format, int* dtype,
+                                int64_t* rows, int64_t* cols, int64_t* nnz,
+                                int64_t* block_size, int* block_layout);
+
+/* Copy the three arrays into caller-owned host memory (numpy allocates them, so
+ * the reference's extra copy at _common.py:488-491 disappears).  indptr_bits /
+ * indices_bits select int32 or int64 on the host side; any pointer may be NULL
+ * to skip that array. */
+SDB_API sdb_status sdb_export(const sdb_mat* m, void* indptr, int indptr_bits,
+                              void* indices, int indices_bits, void* values);
+
+/* mkl_sparse_order (_common.py:683-692): ascending column order inside every
+ * row (CSR) / column (CSC) / block row (BSR), values permuted along. */
+SDB_API sdb_status sdb_order(sdb_mat* m);
+
+/* mkl_sparse_convert_csr (_common.py:695-722): CSC or BSR (or CSR) -> new CSR
+ * handle; op must be SDB_OP_NON_TRANSPOSE or SDB_OP_TRANSPOSE. */
+SDB_API sdb_status sdb_convert_csr(const sdb_mat* m, int op, sdb_mat** out);
+
+/* ======================= SpMM ====================== */
+
+/* mkl_sparse_{s,d,c,z}_mm (_cfunctions.py:611-625, called at
+ * _sparse_dense.py:111-123):   Y := alpha * op(A) * X + beta * Y.
+ * alpha/beta point at {re, im} doubles (im ignored for real dtypes) — MKL takes
+ * them by value in the matrix dtype.  X is (k x n), Y is (m x n) with
+ * (m, k) = shape of op(A); `layout` applies to both; ldx/ldy are leading
+ * dimensions in elements.  X and Y are HOST pointers; the copies to and from
+ * HBM happen inside the call (pinned fast path when the memory is page-locked).
+ * beta == 0 means Y is write-only (never read, NaNs in Y do not propagate). */
+SDB_API sdb_status sdb_spmm(int op, const double* alpha, const sdb_mat* A, int layout,
+                            const void* X, int64_t n, int64_t ldx,
+                            const double* beta, void* Y, int64_t ldy);
+
+/* Same operation on DEVICE pointers, stream-ordered on `stream` (a
+ * cudaStream_t passed as void*; NULL = the library's own stream). */
+SDB_API sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, int layout,
+                                const void* dX, int64_t n, int64_t ldx,
+                                const double* beta, void* dY, int64_t ldy, void* stream);
+
+/* Row-sharded SpMM fused with the all-gather of the output panel:
+ * this rank owns rows [row0, row0 + A.rows) of the global product; the kernel's
+ * epilogue stores every finished row once into EACH of the n_peers full-size
+ * row-major output panels (peer-mapped device pointers, ld = ldy, own rank
+ * included), so no second pass over Y and no separate collective is needed.
+ * beta reads the local panel (dY_peers[self]).  Row-major layout, op = N. */
+SDB_API sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A,
+                                          const void* dX, int64_t n, int64_t ldx,
+                                          const double* beta, void* const* dY_peers,
+                                          int n_peers, int self, int64_t row0, int64_t ldy,
+                                          void* stream);
+
+/* ======================= SpGEMM ==================== */
+
+/* mkl_sparse_spmm (_cfunctions.py:376-382, called at _sparse_sparse.py:35-40):
+ * C := op(A) * B as a NEW handle in the format of A (CSR x CSR -> CSR,
+ * CSC x CSC -> CSC, BSR x BSR -> BSR); structural nonzeros are kept (numeric
+ * cancellation does not drop an entry), columns inside a row are NOT sorted
+ * until sdb_order is called. */
+SDB_API sdb_status sdb_spgemm(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C);
+
+/* mkl_sparse_?_spmmd (_cfunctions.py:600-609, called at _sparse_sparse.py:94-101):
+ * dense C := op(A) * B, OVERWRITING the host array C (no beta). */
+SDB_API sdb_status sdb_spgemm_dense(int op, const sdb_mat* A, const sdb_mat* B,
+                                    int layout, void* C, int64_t ldc);
+SDB_API sdb_status sdb_spgemm_dense_dev(int op, const sdb_mat* A, const sdb_mat* B,
+                                        int layout, void* dC, int64_t ldc, void* stream);
+
+/* ======================= SYRK ===================== */
+
+/* mkl_sparse_syrk (_cfunctions.py:456-461, called at _gram_matrix.py:70-74):
+ * upper triangle of  A^T*A (op = SDB_OP_TRANSPOSE)  or  A*A^T
+ * (op = SDB_OP_NON_TRANSPOSE)  as a new CSR handle. */
+SDB_API sdb_status sdb_syrk(int op, const sdb_mat* A, sdb_mat** C);
+
+/* mkl_sparse_?_syrkd (_cfunctions.py:639-649, called at _gram_matrix.py:149-157):
+ * dense C := alpha * op-product + beta * C on the UPPER triangle of the host
+ * array C; the strict lower triangle is left untouched. */
+SDB_API sdb_status sdb_syrkd(int op, const sdb_mat* A, const double* alpha, const double* beta,
+                             void* C, int layout, int64_t ldc);
+/* Same product into a FRESH host array (the reference's out=None case,
+ * _gram_matrix.py:136-139 + the lower-triangle clean-up at :168-169): upper
+ * triangle = alpha * product, strict lower triangle = 0, nothing is uploaded. */
+SDB_API sdb_status sdb_syrkd_new(int op, const sdb_mat* A, const double* alpha, void* C, int layout,
+                                 int64_t ldc);
+SDB_API sdb_status sdb_syrkd_dev(int op, const sdb_mat* A, const double* alpha,
+                                 const double* beta, void* dC, int layout, int64_t ldc,
+                                 void* stream);
+
+/* ======================= host-side helpers ================================= */
+
+/* nnz-balanced contiguous row blocks for the multi-GPU path:
+ * bounds[0] = 0 <= bounds[1] <= ... <= bounds[parts] = rows.  Pure host code. */
+SDB_API sdb_status sdb_partition_rows(const void* indptr, int index_bits, int64_t rows,
+                                      int parts, int64_t* bounds);
+
+/* Page-locked host buffers for callers who want the DMA fast path. */
+SDB_API sdb_status sdb_host_alloc(void** p, size_t bytes);
+SDB_API sdb_status sdb_host_free(void* p);
+
+/* Plain device memory (cudaMalloc, so it can be shared across processes) and
+ * synchronous copies, for device-resident callers that do not bring their own
+ * allocator.  kind: 1 = host->device, 2 = device->host, 3 = device->device. */
+SDB_API sdb_status sdb_dev_alloc(void** p, size_t bytes);
+SDB_API sdb_status sdb_dev_free(void* p);
+SDB_API sdb_status sdb_memcpy(void* dst, const void* src, size_t bytes, int kind);
+SDB_API sdb_status sdb_device_synchronize(void);
+
+/* Peer mapping of an sdb_dev_alloc buffer into another process on the same
+ * node (one process per GPU, NVLink/NVSwitch underneath): the owner exports a
+ * 64-byte token, every peer opens it and gets a device pointer it can hand to
+ * sdb_spmm_dev_allgather.  sdb_ipc_close unmaps (peers only; the owner frees). */
+#define SDB_IPC_TOKEN_BYTES 64
+SDB_API sdb_status sdb_ipc_export(const void* d_ptr, char token[SDB_IPC_TOKEN_BYTES]);
+SDB_API sdb_status sdb_ipc_open(const char token[SDB_IPC_TOKEN_BYTES], void** d_ptr);
+SDB_API sdb_status sdb_ipc_close(void* d_ptr);
+
+/* Device selection / introspection (the analogue of mkl_get_max_threads and
+ * mkl_get_version_string, _cfunctions.py:738-767). */
+SDB_API sdb_status sdb_device_count(int* n);
+SDB_API sdb_status sdb_set_device(int device);
+SDB_API sdb_status sdb_get_device(int* device);
+SDB_API sdb_status sdb_version_string(char* buf, int len);
+SDB_API int        sdb_last_error(char* buf, int len);
+
+/* Number of CUDA kernels this library has launched in this process (all
+ * threads); bench.py reports the delta over the timed region. */
+SDB_API int64_t sdb_kernel_launches(void);
+
+/* Device time (ms, CUDA events on the launch stream) the most recent
+ * host-pointer entry point on this thread spent in: [0] host->device copies,
+ * [1] kernels, [2] device->host copies.  The reference's debug_timer
+ * (_common.py:138-155) prints the same phases. */
+SDB_API sdb_status sdb_last_timing(double ms[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H */

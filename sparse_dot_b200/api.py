@@ -1,0 +1,96 @@
+"""
+Public surface — the same names, arguments and return types as
+sparse_dot_mkl/sparse_dot.py:18-253 (dot_product_mkl, gram_matrix_mkl,
+dot_product_transpose_mkl) and the service functions re-exported at
+sparse_dot_mkl/__init__.py:4-29 (set_debug_mode, get_version_string).
+Dispatch only; the work happens in _ops (one libsdb200 call per product).
+"""
+import warnings as _warnings
+
+import numpy as _np
+import scipy.sparse as _sps
+
+from . import _lib
+from . import _ops
+from ._validate import is_dense_vector as _is_vec
+
+
+def set_debug_mode(debug_bool):
+    """Print library status, return codes and per-phase timings on every call."""
+    _lib.SDB.DEBUG = bool(debug_bool)
+
+
+def get_version_string():
+    """Library, CUDA runtime/driver and GPU description (the analogue of
+    mkl_get_version_string)."""
+    return _lib.version_string()
+
+
+def _print_debug():
+    if not _lib.SDB.DEBUG:
+        return
+    print(get_version_string())
+    print(f"libsdb200 linked: {_lib.library_path()}")
+    print(f"CUDA devices visible: {_lib.device_count()}")
+    print("Index interface: int32 or int64 host indices; int64 row offsets + int32 columns in HBM")
+
+
+def _warn_debug_flag(debug):
+    if debug:
+        _warnings.warn("Set debug mode with sparse_dot_b200.set_debug_mode(True)", DeprecationWarning)
+
+
+def dot_product_mkl(matrix_a, matrix_b, cast=False, copy=True, reorder_output=False, dense=False,
+                    debug=False, out=None, out_scalar=None):
+    """
+    A @ B on the GPU for any mix of scipy CSR / CSC / BSR matrices and numpy
+    arrays with at least one sparse operand.
+
+    :param cast: convert unsupported / mismatched dtypes (to float64, or
+        complex128) instead of raising ValueError
+    :param copy: deprecated, ignored (kept for signature compatibility)
+    :param reorder_output: sort the column indices of a sparse result
+    :param dense: sparse @ sparse only — return a dense array
+    :param debug: deprecated; use set_debug_mode(True)
+    :param out: dense results only — accumulate into this array
+        (out = A @ B + out_scalar * out; out_scalar defaults to 1)
+    :return: sparse matrix in the container of ``matrix_a`` or a numpy array
+    """
+    _warn_debug_flag(debug)
+    _print_debug()
+    n_sparse = int(_sps.issparse(matrix_a)) + int(_sps.issparse(matrix_b))
+
+    if n_sparse == 2:
+        return _ops.dot_sparse_sparse(matrix_a, matrix_b, cast=cast, reorder_output=reorder_output,
+                                      dense=dense, out=out)
+    if n_sparse == 1:
+        a_is_row_vec = _is_vec(matrix_a) and (matrix_a.ndim == 1 or matrix_a.shape[0] == 1)
+        b_is_col_vec = _is_vec(matrix_b) and (matrix_b.ndim == 1 or matrix_b.shape[1] == 1)
+        if a_is_row_vec or b_is_col_vec:
+            return _ops.dot_sparse_vector(matrix_a, matrix_b, cast=cast, out=out, out_scalar=out_scalar)
+        return _ops.dot_sparse_dense(matrix_a, matrix_b, cast=cast, out=out, out_scalar=out_scalar)
+    raise NotImplementedError(
+        "dot_product_mkl with two dense operands is a dense GEMM, outside the sparse hot path this "
+        "backend covers (SURVEY.md §2 row 7); use numpy / torch for it"
+    )
+
+
+def gram_matrix_mkl(matrix, transpose=False, cast=False, dense=False, debug=False, reorder_output=False,
+                    out=None, out_scalar=None):
+    """
+    Upper triangle of the gram matrix A^T A (``transpose=False``) or A A^T
+    (``transpose=True``) of a CSR matrix (CSC with ``cast=True``).
+
+    :param dense: return a dense row-major array instead of a csr_matrix
+    :param reorder_output: sort the column indices of the sparse result
+    :param out: dense only — accumulate: out = gram + out_scalar * out on the
+        upper triangle; the strict lower triangle of ``out`` is left as is
+    """
+    _warn_debug_flag(debug)
+    _print_debug()
+    return _ops.gram(matrix, transpose=transpose, cast=cast, dense=dense, reorder_output=reorder_output,
+                     out=out, out_scalar=out_scalar)
+
+
+# backwards-compatible alias, as in the reference (sparse_dot.py:252)
+dot_product_transpose_mkl = gram_matrix_mkl

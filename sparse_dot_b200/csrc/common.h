@@ -1,0 +1,200 @@
+// common.h — shared plumbing of libsdb200: status/error convention, the opaque
+// handle, the per-thread execution context (stream, pinned staging ring, phase
+// timers) and small RAII helpers.  Host-side C++17; included by every .cu file.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/sdb200.h"
+
+namespace sdb {
+
+// ---------------------------------------------------------------- errors
+// The ABI never throws: every internal routine returns an sdb_status and leaves
+// a message in a thread-local buffer (sdb_last_error).
+void set_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+sdb_status cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define SDB_CUDA(expr)                                                     \
+    do {                                                                   \
+        cudaError_t _e = (expr);                                           \
+        if (_e != cudaSuccess) return ::sdb::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define SDB_TRY(expr)                                 \
+    do {                                              \
+        sdb_status _s = (expr);                       \
+        if (_s != SDB_STATUS_SUCCESS) return _s;      \
+    } while (0)
+
+#define SDB_REQUIRE(cond, status, ...)     \
+    do {                                   \
+        if (!(cond)) {                     \
+            ::sdb::set_error(__VA_ARGS__); \
+            return (status);               \
+        }                                  \
+    } while (0)
+
+// Every kernel launch goes through this so sdb_kernel_launches() is exact.
+extern std::atomic<int64_t> g_launches;
+#define SDB_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+    do {                                                                   \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);        \
+        ::sdb::g_launches.fetch_add(1, std::memory_order_relaxed);         \
+        SDB_CUDA(cudaGetLastError());                                      \
+    } while (0)
+
+// ---------------------------------------------------------------- dtypes
+inline size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case SDB_F32: return 4;
+        case SDB_F64: return 8;
+        case SDB_C64: return 8;
+        case SDB_C128: return 16;
+        default: return 0;
+    }
+}
+
+// ---------------------------------------------------------------- context
+// One per host thread and device: a non-blocking stream, a ring of pinned
+// staging chunks for pageable<->HBM copies, and CUDA-event phase timers.
+struct Context {
+    int device = -1;
+    cudaStream_t stream = nullptr;   // compute + H2D
+    cudaStream_t d2h_stream = nullptr;
+    int sm_count = 0;
+    size_t l2_bytes = 0;
+    // pinned staging ring
+    static constexpr int kChunks = 4;
+    static constexpr size_t kChunkBytes = size_t(32) << 20;
+    void* chunk[kChunks] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t chunk_free[kChunks] = {nullptr, nullptr, nullptr, nullptr};
+    int next_chunk = 0;
+    // phase timing of the last host-pointer entry point (ms)
+    double last_ms[3] = {0, 0, 0};
+};
+
+sdb_status get_context(Context** out);
+
+// Stream-ordered device allocation from the device's default memory pool (the
+// pool keeps freed blocks, so repeated calls do not hit cudaMalloc).
+sdb_status dev_alloc(void** p, size_t bytes, cudaStream_t s);
+void dev_free(void* p, cudaStream_t s);
+
+// RAII temp buffer; freed stream-ordered on destruction.
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { reset(); }
+    sdb_status alloc(size_t bytes, cudaStream_t stream) {
+        reset();
+        s = stream;
+        return dev_alloc(&p, bytes ? bytes : 16, stream);
+    }
+    void reset() {
+        if (p) dev_free(p, s);
+        p = nullptr;
+    }
+    void* release() {
+        void* r = p;
+        p = nullptr;
+        return r;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Host <-> HBM copies that DMA straight from/to page-locked memory and stage
+// pageable memory through the context's pinned ring.  Both are stream-ordered
+// on ctx->stream; h2d returns once the host buffer may be reused, d2h returns
+// once the bytes are in `dst`.  2-D variants copy `rows` rows of `row_bytes`
+// with independent pitches (dense panels with ld != n).
+sdb_status h2d(Context* ctx, void* d_dst, const void* h_src, size_t bytes);
+sdb_status d2h(Context* ctx, void* h_dst, const void* d_src, size_t bytes);
+sdb_status h2d_2d(Context* ctx, void* d_dst, size_t d_pitch, const void* h_src, size_t h_pitch,
+                  size_t row_bytes, size_t rows);
+sdb_status d2h_2d(Context* ctx, void* h_dst, size_t h_pitch, const void* d_src, size_t d_pitch,
+                  size_t row_bytes, size_t rows);
+
+// CUDA-event stopwatch for the H2D / kernel / D2H phases.
+struct PhaseTimer {
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t s = nullptr;
+    sdb_status init(cudaStream_t stream);
+    sdb_status mark(int i);  // 0: start, 1: after H2D, 2: after kernels, 3: after D2H
+    void finish(Context* ctx);
+    ~PhaseTimer();
+};
+
+}  // namespace sdb
+
+// ---------------------------------------------------------------- the handle
+// Device-resident sparse matrix.  indptr is always int64 and indices int32 in
+// HBM whatever the host handed us (SURVEY §8b "Index width").  For BSR, rows /
+// cols / nnz count BLOCKS and `values` holds nnz * block * block elements.
+struct sdb_mat {
+    uint32_t magic;
+    int format;        // SDB_FMT_*
+    int dtype;         // SDB_F32 ...
+    int64_t rows, cols;
+    int64_t nnz;
+    int64_t block;     // 1 for CSR/CSC
+    int block_layout;  // SDB_LAYOUT_* (BSR only)
+    int64_t* indptr;
+    int32_t* indices;
+    void* values;
+    bool owns;         // false for sdb_create_csr_dev (borrowed HBM arrays)
+    int device;
+    // Lazily built companion holding the transposed compressed form (CSR of
+    // A^T); invalidated by sdb_order.  Lets op=T and CSC inputs reuse the
+    // gather kernel instead of a scatter/atomic path.
+    sdb_mat* transposed;
+    // Lazily built CSR expansion of a BSR handle (every stored block becomes
+    // block*block explicit entries); lets BSR reuse the CSR kernels.
+    sdb_mat* expanded;
+};
+
+namespace sdb {
+constexpr uint32_t kMagic = 0x5db200a5u;
+inline bool valid(const sdb_mat* m) { return m != nullptr && m->magic == kMagic; }
+
+// major dimension of the compressed arrays (rows for CSR/BSR, cols for CSC)
+inline int64_t major_dim(const sdb_mat* m) { return m->format == SDB_FMT_CSC ? m->cols : m->rows; }
+inline int64_t minor_dim(const sdb_mat* m) { return m->format == SDB_FMT_CSC ? m->rows : m->cols; }
+
+sdb_status new_handle(sdb_mat** out, int format, int dtype, int64_t rows, int64_t cols,
+                      int64_t nnz, int64_t block, int block_layout, cudaStream_t s);
+void free_handle(sdb_mat* m);
+
+// Internal device-level operations shared between translation units -------------
+// CSR(A) -> CSR(A^T) as a new owned handle (rows/cols swapped), rows sorted.
+sdb_status transpose_compressed(Context* ctx, const sdb_mat* a, sdb_mat** out);
+// The CSR view of `m` for op(A): returns arrays such that row r lists op(A)[r,:].
+struct CsrView {
+    int64_t rows, cols, nnz;
+    const int64_t* indptr;
+    const int32_t* indices;
+    const void* values;
+};
+sdb_status csr_view(Context* ctx, const sdb_mat* m, bool transpose, CsrView* v);
+sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indptr, int32_t* indices,
+                     void* values, int64_t elems_per_entry);
+sdb_status expand_bsr(Context* ctx, const sdb_mat* bsr, sdb_mat** out_csr);
+// True when every row's column indices are non-decreasing (device reduction + sync).
+sdb_status rows_sorted(Context* ctx, int64_t rows, const int64_t* indptr, const int32_t* indices,
+                       bool* sorted);
+// SpGEMM core on CSR views: C = L * R (optionally only entries with col >= row).
+sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int dtype, bool upper,
+                         sdb_mat** out);
+
+sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a, const double* alpha,
+                       const double* beta, int layout, const void* dX, int64_t n, int64_t ldx,
+                       void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy);
+}  // namespace sdb

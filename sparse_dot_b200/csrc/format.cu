@@ -1,0 +1,504 @@
+// format.cu — structure-changing operations on a device-resident sparse matrix:
+//   * per-row column sort        (mkl_sparse_order,        _common.py:683-692)
+//   * compressed-axis transpose  (mkl_sparse_convert_csr on a CSC handle, and
+//                                 op = TRANSPOSE for every kernel; _common.py:695-722)
+//   * BSR -> CSR expansion       (mkl_sparse_convert_csr on a BSR handle;
+//                                 tests/test_mkl.py:251-268)
+// All integer/byte work: HBM-bound, coalesced streams, no tensor cores.
+#include "common.h"
+#include "prims.h"
+
+namespace sdb {
+
+// ============================================================ row sorting
+// Rows are binned by length: <= 32 entries sort inside one warp's registers,
+// <= kSmemSortMax inside one CTA's shared memory, longer rows by one CTA
+// working in global memory (L2 resident) with the small strides of every merge
+// stage done tile by tile in shared memory.  All three run the same
+// ascending-only bitonic network (first step of a merge stage pairs i with
+// i ^ (2k-1), the rest are half-cleaners i ^ j), which sorts any length n
+// without padding because a virtual +inf tail never has to move.
+// The sort key is (column, original position): unique, so the result is the
+// stable order whatever the network does.
+
+constexpr int kSmemSortMax = 4096;  // entries per CTA-sorted row (32 KB of keys)
+constexpr int kSortThreads = 256;
+
+__global__ void __launch_bounds__(256) classify_rows_kernel(int64_t rows, const int64_t* __restrict__ indptr,
+                                                            const int32_t* __restrict__ indices,
+                                                            int32_t* __restrict__ med_rows,
+                                                            int32_t* __restrict__ long_rows,
+                                                            unsigned* __restrict__ counters /*[3]: med, long, unsorted*/) {
+    int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int64_t b = indptr[r], e = indptr[r + 1];
+    const int64_t len = e - b;
+    bool unsorted = false;
+    for (int64_t p = b + 1; p < e; ++p)
+        if (indices[p] < indices[p - 1]) {
+            unsorted = true;
+            break;
+        }
+    if (!unsorted) return;
+    atomicAdd(&counters[2], 1u);
+    if (len > kSmemSortMax) long_rows[atomicAdd(&counters[1], 1u)] = int32_t(r);
+    else if (len > 32) med_rows[atomicAdd(&counters[0], 1u)] = int32_t(r);
+}
+
+// one warp per row of <= 32 entries; writes sorted columns in place and the
+// source position of every output entry into perm
+__global__ void __launch_bounds__(256) sort_rows_warp_kernel(int64_t rows, const int64_t* __restrict__ indptr,
+                                                             int32_t* __restrict__ indices,
+                                                             int32_t* __restrict__ perm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const int64_t b = indptr[r];
+    const int len = int(min(int64_t(33), indptr[r + 1] - b));
+    if (len > 32 || len == 0) return;  // warp-uniform
+    uint64_t key = lane < len ? (uint64_t(uint32_t(indices[b + lane])) << 32) | uint32_t(lane) : ~uint64_t(0);
+    // full 32-wide bitonic network (padding keys are +inf and end up at the top)
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int partner = (j == (k >> 1)) ? (lane ^ (k - 1)) : (lane ^ j);
+            const uint64_t other = __shfl_sync(0xffffffffu, key, partner);
+            const bool keep_min = lane < partner;
+            key = keep_min ? (key < other ? key : other) : (key < other ? other : key);
+        }
+    }
+    if (lane < len) {
+        indices[b + lane] = int32_t(key >> 32);
+        perm[b + lane] = int32_t(uint32_t(key));
+    }
+}
+
+// one CTA per listed row of <= kSmemSortMax entries
+__global__ void __launch_bounds__(kSortThreads) sort_rows_cta_kernel(const int32_t* __restrict__ row_list,
+                                                                     const int64_t* __restrict__ indptr,
+                                                                     int32_t* __restrict__ indices,
+                                                                     int32_t* __restrict__ perm) {
+    __shared__ uint64_t keys[kSmemSortMax];
+    const int64_t r = row_list[blockIdx.x];
+    const int64_t b = indptr[r];
+    const int n = int(indptr[r + 1] - b);
+    for (int i = threadIdx.x; i < n; i += kSortThreads)
+        keys[i] = (uint64_t(uint32_t(indices[b + i])) << 32) | uint32_t(i);
+    __syncthreads();
+    int p2 = 1;
+    while (p2 < n) p2 <<= 1;
+    for (int k = 2; k <= p2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool flip = j == (k >> 1);
+            for (int t = threadIdx.x; t < (p2 >> 1); t += kSortThreads) {
+                // t enumerates the lower element of every pair at stride j
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = flip ? (lo ^ (k - 1)) : (lo | j);
+                if (hi < n) {
+                    const uint64_t a = keys[lo], c = keys[hi];
+                    if (a > c) {
+                        keys[lo] = c;
+                        keys[hi] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += kSortThreads) {
+        indices[b + i] = int32_t(keys[i] >> 32);
+        perm[b + i] = int32_t(uint32_t(keys[i]));
+    }
+}
+
+// one CTA per listed long row; keys live in a global scratch array (row-aligned
+// with indices), strides < kSmemSortMax are finished tile by tile in shared memory
+__global__ void __launch_bounds__(1024) sort_rows_global_kernel(const int32_t* __restrict__ row_list,
+                                                                const int64_t* __restrict__ indptr,
+                                                                int32_t* __restrict__ indices,
+                                                                int32_t* __restrict__ perm,
+                                                                uint64_t* __restrict__ scratch) {
+    __shared__ uint64_t tile[kSmemSortMax];
+    const int64_t r = row_list[blockIdx.x];
+    const int64_t b = indptr[r];
+    const int64_t n = indptr[r + 1] - b;
+    uint64_t* keys = scratch + b;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+        keys[i] = (uint64_t(uint32_t(indices[b + i])) << 32) | uint32_t(i);
+    __syncthreads();
+    int64_t p2 = 1;
+    while (p2 < n) p2 <<= 1;
+    // stages k <= kSmemSortMax never leave an aligned tile: run them all per tile load
+    for (int64_t t0 = 0; t0 < n; t0 += kSmemSortMax) {
+        const int len = int(min(int64_t(kSmemSortMax), n - t0));
+        for (int i = threadIdx.x; i < len; i += blockDim.x) tile[i] = keys[t0 + i];
+        __syncthreads();
+        for (int k = 2; k <= kSmemSortMax; k <<= 1) {
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                const bool flip = jj == (k >> 1);
+                for (int t = threadIdx.x; t < (kSmemSortMax >> 1); t += blockDim.x) {
+                    const int lo = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+                    const int hi = flip ? (lo ^ (k - 1)) : (lo | jj);
+                    if (hi < len) {
+                        const uint64_t a = tile[lo], c = tile[hi];
+                        if (a > c) {
+                            tile[lo] = c;
+                            tile[hi] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = threadIdx.x; i < len; i += blockDim.x) keys[t0 + i] = tile[i];
+        __syncthreads();
+    }
+    for (int64_t k = int64_t(kSmemSortMax) << 1; k <= p2; k <<= 1) {
+        int64_t j = k >> 1;
+        // large strides: straight in global memory
+        for (; j >= kSmemSortMax; j >>= 1) {
+            const bool flip = j == (k >> 1);
+            for (int64_t t = threadIdx.x; t < (p2 >> 1); t += blockDim.x) {
+                const int64_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int64_t hi = flip ? (lo ^ (k - 1)) : (lo | j);
+                if (hi < n) {
+                    const uint64_t a = keys[lo], c = keys[hi];
+                    if (a > c) {
+                        keys[lo] = c;
+                        keys[hi] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // remaining half-cleaner strides j < kSmemSortMax stay inside aligned tiles
+        for (int64_t t0 = 0; t0 < n; t0 += kSmemSortMax) {
+            const int len = int(min(int64_t(kSmemSortMax), n - t0));
+            for (int i = threadIdx.x; i < len; i += blockDim.x) tile[i] = keys[t0 + i];
+            __syncthreads();
+            for (int jj = int(j); jj > 0; jj >>= 1) {
+                for (int t = threadIdx.x; t < (kSmemSortMax >> 1); t += blockDim.x) {
+                    const int lo = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+                    const int hi = lo | jj;
+                    if (hi < len) {
+                        const uint64_t a = tile[lo], c = tile[hi];
+                        if (a > c) {
+                            tile[lo] = c;
+                            tile[hi] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            for (int i = threadIdx.x; i < len; i += blockDim.x) keys[t0 + i] = tile[i];
+            __syncthreads();
+        }
+    }
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        indices[b + i] = int32_t(keys[i] >> 32);
+        perm[b + i] = int32_t(uint32_t(keys[i]));
+    }
+}
+
+// identity permutation (rows that were already sorted keep perm[p] = p - row start)
+__global__ void __launch_bounds__(256) perm_identity_kernel(int64_t rows, const int64_t* __restrict__ indptr,
+                                                            int32_t* __restrict__ perm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const int64_t b = indptr[r], e = indptr[r + 1];
+    for (int64_t p = b + lane; p < e; p += 32) perm[p] = int32_t(p - b);
+}
+
+// dst entry p of row r = src entry (row start + perm[p]); one entry is `epe`
+// 4-byte words (values are moved as raw words so every dtype / block shares this)
+__global__ void __launch_bounds__(256) permute_values_kernel(int64_t rows, const int64_t* __restrict__ indptr,
+                                                             const int32_t* __restrict__ perm,
+                                                             const uint32_t* __restrict__ src,
+                                                             uint32_t* __restrict__ dst, int64_t words_per_entry) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const int64_t b = indptr[r], e = indptr[r + 1];
+    if (words_per_entry == 1) {
+        for (int64_t p = b + lane; p < e; p += 32) dst[p] = src[b + perm[p]];
+    } else if (words_per_entry <= 4) {
+        for (int64_t p = b + lane; p < e; p += 32) {
+            const int64_t s = (b + perm[p]) * words_per_entry, d = p * words_per_entry;
+            for (int64_t w = 0; w < words_per_entry; ++w) dst[d + w] = src[s + w];
+        }
+    } else {  // blocks: the whole warp moves one entry at a time
+        for (int64_t p = b; p < e; ++p) {
+            const int64_t s = (b + perm[p]) * words_per_entry, d = p * words_per_entry;
+            for (int64_t w = lane; w < words_per_entry; w += 32) dst[d + w] = src[s + w];
+        }
+    }
+}
+
+static unsigned blocks_for(int64_t n, int per_block) { return unsigned((n + per_block - 1) / per_block); }
+
+sdb_status rows_sorted(Context* ctx, int64_t rows, const int64_t* indptr, const int32_t* indices, bool* sorted) {
+    *sorted = true;
+    if (rows <= 0) return SDB_STATUS_SUCCESS;
+    cudaStream_t s = ctx->stream;
+    DevBuf counters, dummy;
+    SDB_TRY(counters.alloc(3 * sizeof(unsigned), s));
+    SDB_TRY(dummy.alloc(size_t(rows) * sizeof(int32_t), s));
+    SDB_CUDA(cudaMemsetAsync(counters.p, 0, 3 * sizeof(unsigned), s));
+    SDB_LAUNCH(classify_rows_kernel, blocks_for(rows, 256), 256, 0, s, rows, indptr, indices, dummy.as<int32_t>(),
+               dummy.as<int32_t>(), counters.as<unsigned>());
+    unsigned h[3];
+    SDB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    SDB_CUDA(cudaStreamSynchronize(s));
+    *sorted = h[2] == 0;
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indptr, int32_t* indices,
+                     void* values, int64_t elems_per_entry) {
+    if (rows <= 0) return SDB_STATUS_SUCCESS;
+    cudaStream_t s = ctx->stream;
+    SDB_REQUIRE(rows < (int64_t(1) << 31), SDB_STATUS_NOT_SUPPORTED, "sort_rows: too many rows");
+    DevBuf counters, med, lng;
+    SDB_TRY(counters.alloc(3 * sizeof(unsigned), s));
+    SDB_TRY(med.alloc(size_t(rows) * sizeof(int32_t), s));
+    SDB_TRY(lng.alloc(size_t(rows) * sizeof(int32_t), s));
+    SDB_CUDA(cudaMemsetAsync(counters.p, 0, 3 * sizeof(unsigned), s));
+    SDB_LAUNCH(classify_rows_kernel, blocks_for(rows, 256), 256, 0, s, rows, indptr, indices, med.as<int32_t>(),
+               lng.as<int32_t>(), counters.as<unsigned>());
+    unsigned h[3];
+    int64_t nnz = 0;
+    SDB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    SDB_CUDA(cudaMemcpyAsync(&nnz, indptr + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SDB_CUDA(cudaStreamSynchronize(s));
+    if (h[2] == 0 || nnz == 0) return SDB_STATUS_SUCCESS;  // already in order: nothing moves
+
+    DevBuf perm, tmp;
+    SDB_TRY(perm.alloc(size_t(nnz) * sizeof(int32_t), s));
+    SDB_LAUNCH(perm_identity_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, perm.as<int32_t>());
+    SDB_LAUNCH(sort_rows_warp_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, indices,
+               perm.as<int32_t>());
+    if (h[0] > 0)
+        SDB_LAUNCH(sort_rows_cta_kernel, h[0], kSortThreads, 0, s, med.as<int32_t>(), indptr, indices,
+                   perm.as<int32_t>());
+    if (h[1] > 0) {
+        DevBuf scratch;
+        SDB_TRY(scratch.alloc(size_t(nnz) * sizeof(uint64_t), s));
+        SDB_LAUNCH(sort_rows_global_kernel, h[1], 1024, 0, s, lng.as<int32_t>(), indptr, indices,
+                   perm.as<int32_t>(), scratch.as<uint64_t>());
+    }
+    if (values != nullptr) {
+        const size_t entry_bytes = dtype_size(dtype) * size_t(elems_per_entry);
+        SDB_TRY(tmp.alloc(size_t(nnz) * entry_bytes, s));
+        SDB_LAUNCH(permute_values_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, perm.as<int32_t>(),
+                   static_cast<const uint32_t*>(values), tmp.as<uint32_t>(), int64_t(entry_bytes / 4));
+        SDB_CUDA(cudaMemcpyAsync(values, tmp.p, size_t(nnz) * entry_bytes, cudaMemcpyDeviceToDevice, s));
+    }
+    return SDB_STATUS_SUCCESS;
+}
+
+// ============================================================ transpose
+// CSR(A) -> CSR(A^T): column histogram, prefix sum, scatter through per-column
+// cursors, then the row sort above puts every output row in ascending order
+// (the scatter order is whatever the atomics gave; the sort key includes the
+// source position only within a row, so sort on the source ROW id instead:
+// the scattered "column" of A^T *is* the source row, unique per output row when
+// A has no duplicate entries, and stable enough otherwise).
+__global__ void __launch_bounds__(256) count_columns_kernel(int64_t nnz, const int32_t* __restrict__ indices,
+                                                            int32_t* __restrict__ counts) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (; i < nnz; i += stride) atomicAdd(&counts[indices[i]], 1);
+}
+
+__global__ void __launch_bounds__(256) scatter_transpose_kernel(int64_t rows, const int64_t* __restrict__ indptr,
+                                                                const int32_t* __restrict__ indices,
+                                                                const uint32_t* __restrict__ values,
+                                                                int words_per_entry,
+                                                                unsigned long long* __restrict__ cursor,
+                                                                int32_t* __restrict__ t_indices,
+                                                                uint32_t* __restrict__ t_values) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const int64_t b = indptr[r], e = indptr[r + 1];
+    for (int64_t p = b + lane; p < e; p += 32) {
+        const unsigned long long q = atomicAdd(&cursor[indices[p]], 1ull);
+        t_indices[q] = int32_t(r);
+        for (int w = 0; w < words_per_entry; ++w) t_values[q * words_per_entry + w] = values[p * words_per_entry + w];
+    }
+}
+
+sdb_status transpose_compressed(Context* ctx, const sdb_mat* a, sdb_mat** out) {
+    // `a` is read as a compressed matrix with major_dim(a) lines over minor_dim(a) indices
+    cudaStream_t s = ctx->stream;
+    const int64_t major = major_dim(a), minor = minor_dim(a);
+    SDB_REQUIRE(a->block == 1, SDB_STATUS_NOT_SUPPORTED, "transpose: BSR must be expanded first");
+    sdb_mat* t;
+    // the result has `minor` lines; describe it as a CSR (minor x major) matrix
+    SDB_TRY(new_handle(&t, SDB_FMT_CSR, a->dtype, minor, major, a->nnz, 1, SDB_LAYOUT_ROW_MAJOR, s));
+    sdb_status st = [&]() -> sdb_status {
+        DevBuf counts, cursor;
+        SDB_TRY(counts.alloc(size_t(minor + 1) * sizeof(int32_t), s));
+        SDB_CUDA(cudaMemsetAsync(counts.p, 0, size_t(minor + 1) * sizeof(int32_t), s));
+        if (a->nnz > 0) {
+            unsigned g = unsigned(std::min<int64_t>((a->nnz + 255) / 256, int64_t(ctx->sm_count) * 16));
+            SDB_LAUNCH(count_columns_kernel, g, 256, 0, s, a->nnz, a->indices, counts.as<int32_t>());
+        }
+        SDB_TRY(exclusive_scan_i32_to_i64(s, counts.as<int32_t>(), t->indptr, minor));
+        if (a->nnz == 0) return SDB_STATUS_SUCCESS;
+        SDB_TRY(cursor.alloc(size_t(minor) * sizeof(int64_t), s));
+        SDB_CUDA(cudaMemcpyAsync(cursor.p, t->indptr, size_t(minor) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+        SDB_LAUNCH(scatter_transpose_kernel, blocks_for(major * 32, 256), 256, 0, s, major, a->indptr, a->indices,
+                   static_cast<const uint32_t*>(a->values), int(dtype_size(a->dtype) / 4),
+                   cursor.as<unsigned long long>(), t->indices, static_cast<uint32_t*>(t->values));
+        return sort_rows(ctx, t->dtype, minor, t->indptr, t->indices, t->values, 1);
+    }();
+    if (st != SDB_STATUS_SUCCESS) {
+        free_handle(t);
+        return st;
+    }
+    *out = t;
+    return SDB_STATUS_SUCCESS;
+}
+
+// ============================================================ BSR -> CSR
+// Row (I*b + r) of the expansion lists, for every stored block q of block row
+// I in order, the b columns bidx[q]*b .. +b-1.  One warp per output row.
+__global__ void __launch_bounds__(256) expand_bsr_kernel(int64_t block_rows, int b, int col_major_blocks,
+                                                         const int64_t* __restrict__ bptr,
+                                                         const int32_t* __restrict__ bidx,
+                                                         const uint32_t* __restrict__ bval, int words,
+                                                         int64_t* __restrict__ indptr, int32_t* __restrict__ indices,
+                                                         uint32_t* __restrict__ values) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= block_rows * b) return;
+    const int64_t I = row / b;
+    const int r = int(row - I * b);
+    const int64_t qb = bptr[I], nb = bptr[I + 1] - qb;
+    const int64_t o0 = qb * b * b + int64_t(r) * nb * b;
+    if (lane == 0) {
+        indptr[row + 1] = o0 + nb * b;
+        if (row == 0) indptr[0] = 0;
+    }
+    for (int64_t e = lane; e < nb * b; e += 32) {
+        const int64_t q = qb + e / b;
+        const int c = int(e % b);
+        indices[o0 + e] = int32_t(int64_t(bidx[q]) * b + c);
+        const int64_t src = q * b * b + (col_major_blocks ? int64_t(c) * b + r : int64_t(r) * b + c);
+        for (int w = 0; w < words; ++w) values[(o0 + e) * words + w] = bval[src * words + w];
+    }
+}
+
+sdb_status expand_bsr(Context* ctx, const sdb_mat* m, sdb_mat** out_csr) {
+    cudaStream_t s = ctx->stream;
+    const int64_t b = m->block;
+    sdb_mat* c;
+    SDB_TRY(new_handle(&c, SDB_FMT_CSR, m->dtype, m->rows * b, m->cols * b, m->nnz * b * b, 1,
+                       SDB_LAYOUT_ROW_MAJOR, s));
+    if (c->rows == 0) {
+        cudaMemsetAsync(c->indptr, 0, sizeof(int64_t), s);
+    } else {
+        expand_bsr_kernel<<<blocks_for(c->rows * 32, 256), 256, 0, s>>>(
+            m->rows, int(b), m->block_layout == SDB_LAYOUT_COL_MAJOR, m->indptr, m->indices,
+            static_cast<const uint32_t*>(m->values), int(dtype_size(m->dtype) / 4), c->indptr, c->indices,
+            static_cast<uint32_t*>(c->values));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            free_handle(c);
+            return cuda_fail(e, "expand_bsr_kernel", __FILE__, __LINE__);
+        }
+    }
+    *out_csr = c;
+    return SDB_STATUS_SUCCESS;
+}
+
+// ============================================================ CSR view of op(A)
+sdb_status csr_view(Context* ctx, const sdb_mat* m_in, bool transpose, CsrView* v) {
+    sdb_mat* m = const_cast<sdb_mat*>(m_in);  // companions are a cache, not a logical mutation
+    if (m->format == SDB_FMT_BSR) {
+        if (!m->expanded) SDB_TRY(expand_bsr(ctx, m, &m->expanded));
+        m = m->expanded;
+    }
+    // the stored arrays list lines of A (CSR) or of A^T (CSC)
+    const bool stored_is_transposed = m->format == SDB_FMT_CSC;
+    if (stored_is_transposed == transpose) {
+        v->rows = major_dim(m);
+        v->cols = minor_dim(m);
+        v->nnz = m->nnz;
+        v->indptr = m->indptr;
+        v->indices = m->indices;
+        v->values = m->values;
+        return SDB_STATUS_SUCCESS;
+    }
+    if (!m->transposed) SDB_TRY(transpose_compressed(ctx, m, &m->transposed));
+    const sdb_mat* t = m->transposed;
+    v->rows = t->rows;
+    v->cols = t->cols;
+    v->nnz = t->nnz;
+    v->indptr = t->indptr;
+    v->indices = t->indices;
+    v->values = t->values;
+    return SDB_STATUS_SUCCESS;
+}
+
+}  // namespace sdb
+
+using namespace sdb;
+
+extern "C" {
+
+sdb_status sdb_order(sdb_mat* m) {
+    SDB_REQUIRE(m != nullptr, SDB_STATUS_NOT_INITIALIZED, "order: null handle");
+    SDB_REQUIRE(valid(m), SDB_STATUS_INVALID_VALUE, "order: not a live sdb_mat handle");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    SDB_TRY(sort_rows(ctx, m->dtype, major_dim(m), m->indptr, m->indices, m->values, m->block * m->block));
+    // companions were derived from the old entry order; they stay valid as
+    // matrices (same entries) but drop them so exports of derived handles are
+    // reproducible from the ordered arrays
+    if (m->transposed) {
+        free_handle(m->transposed);
+        m->transposed = nullptr;
+    }
+    if (m->expanded) {
+        free_handle(m->expanded);
+        m->expanded = nullptr;
+    }
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_convert_csr(const sdb_mat* m, int op, sdb_mat** out) {
+    SDB_REQUIRE(out != nullptr, SDB_STATUS_INVALID_VALUE, "convert_csr: null output handle");
+    *out = nullptr;
+    SDB_REQUIRE(m != nullptr, SDB_STATUS_NOT_INITIALIZED, "convert_csr: null handle");
+    SDB_REQUIRE(valid(m), SDB_STATUS_INVALID_VALUE, "convert_csr: not a live sdb_mat handle");
+    SDB_REQUIRE(op == SDB_OP_NON_TRANSPOSE || op == SDB_OP_TRANSPOSE, SDB_STATUS_NOT_SUPPORTED,
+                "convert_csr: op %d not supported", op);
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    cudaStream_t s = ctx->stream;
+    CsrView v;
+    SDB_TRY(csr_view(ctx, m, op == SDB_OP_TRANSPOSE, &v));
+    // hand back an independent copy: the caller destroys both handles separately
+    sdb_mat* c;
+    SDB_TRY(new_handle(&c, SDB_FMT_CSR, m->dtype, v.rows, v.cols, v.nnz, 1, SDB_LAYOUT_ROW_MAJOR, s));
+    cudaError_t e = cudaMemcpyAsync(c->indptr, v.indptr, size_t(v.rows + 1) * 8, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && v.nnz > 0)
+        e = cudaMemcpyAsync(c->indices, v.indices, size_t(v.nnz) * 4, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && v.nnz > 0)
+        e = cudaMemcpyAsync(c->values, v.values, size_t(v.nnz) * dtype_size(m->dtype), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        free_handle(c);
+        return cuda_fail(e, "convert_csr copy", __FILE__, __LINE__);
+    }
+    *out = c;
+    return SDB_STATUS_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+// runtime.cu — host runtime of libsdb200: error plumbing, per-thread context,
+// stream-ordered memory, pinned staging copies, phase timers and the small
+// host-only ABI entry points (version string, device selection, row partitioner).
+#include <cstdarg>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "common.h"
+
+namespace sdb {
+
+std::atomic<int64_t> g_launches{0};
+
+static thread_local char t_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+sdb_status cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    const char* base = strrchr(file, '/');
+    set_error("CUDA error %d (%s) in %s at %s:%d", int(e), cudaGetErrorString(e), what,
+              base ? base + 1 : file, line);
+    cudaGetLastError();  // clear the sticky-free error state
+    return e == cudaErrorMemoryAllocation ? SDB_STATUS_ALLOC_FAILED : SDB_STATUS_EXECUTION_FAILED;
+}
+
+// ---------------------------------------------------------------- context
+static thread_local Context t_ctx[16];
+
+sdb_status get_context(Context** out) {
+    int dev = 0;
+    SDB_CUDA(cudaGetDevice(&dev));
+    SDB_REQUIRE(dev >= 0 && dev < 16, SDB_STATUS_NOT_SUPPORTED, "device index %d out of range", dev);
+    Context* c = &t_ctx[dev];
+    if (c->device < 0) {
+        SDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SDB_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        cudaDeviceProp prop;
+        SDB_CUDA(cudaGetDeviceProperties(&prop, dev));
+        c->sm_count = prop.multiProcessorCount;
+        c->l2_bytes = size_t(prop.l2CacheSize);
+        // keep freed blocks in the pool: repeated calls reuse them
+        cudaMemPool_t pool;
+        SDB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;
+        SDB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        c->device = dev;
+    }
+    *out = c;
+    return SDB_STATUS_SUCCESS;
+}
+
+static sdb_status ensure_staging(Context* c) {
+    if (c->chunk[0]) return SDB_STATUS_SUCCESS;
+    for (int i = 0; i < Context::kChunks; ++i) {
+        SDB_CUDA(cudaHostAlloc(&c->chunk[i], Context::kChunkBytes, cudaHostAllocDefault));
+        SDB_CUDA(cudaEventCreateWithFlags(&c->chunk_free[i], cudaEventDisableTiming));
+    }
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status dev_alloc(void** p, size_t bytes, cudaStream_t s) {
+    *p = nullptr;
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, s);
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return cuda_fail(e, "cudaMallocAsync", __FILE__, __LINE__);
+    }
+    return SDB_STATUS_SUCCESS;
+}
+
+void dev_free(void* p, cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
+}
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// memcpy split over a few host threads: one core moves ~10 GB/s, PCIe 5 wants ~55.
+static void fast_memcpy(void* dst, const void* src, size_t bytes) {
+    constexpr size_t kMin = size_t(4) << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = int(bytes / kMin);
+    if (nt > 8) nt = 8;
+    if (hw && nt > int(hw)) nt = int(hw);
+    if (nt <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    size_t per = (bytes / nt + 63) & ~size_t(63);
+    for (int t = 0; t < nt; ++t) {
+        size_t off = size_t(t) * per;
+        if (off >= bytes) break;
+        size_t len = bytes - off < per ? bytes - off : per;
+        th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    }
+    for (auto& x : th) x.join();
+}
+
+sdb_status h2d(Context* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    if (bytes == 0) return SDB_STATUS_SUCCESS;
+    if (is_pinned(h_src)) {
+        SDB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return SDB_STATUS_SUCCESS;
+    }
+    SDB_TRY(ensure_staging(ctx));
+    size_t off = 0;
+    while (off < bytes) {
+        int k = ctx->next_chunk;
+        ctx->next_chunk = (k + 1) % Context::kChunks;
+        SDB_CUDA(cudaEventSynchronize(ctx->chunk_free[k]));
+        size_t len = bytes - off < Context::kChunkBytes ? bytes - off : Context::kChunkBytes;
+        fast_memcpy(ctx->chunk[k], (const char*)h_src + off, len);
+        SDB_CUDA(cudaMemcpyAsync((char*)d_dst + off, ctx->chunk[k], len, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+        SDB_CUDA(cudaEventRecord(ctx->chunk_free[k], ctx->stream));
+        off += len;
+    }
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status d2h(Context* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    if (bytes == 0) return SDB_STATUS_SUCCESS;
+    if (is_pinned(h_dst)) {
+        SDB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SDB_STATUS_SUCCESS;
+    }
+    SDB_TRY(ensure_staging(ctx));
+    // software pipeline: DMA chunk i+1 while the host copies chunk i out of the ring
+    struct Pending { int k; size_t off, len; };
+    Pending pend[Context::kChunks];
+    int head = 0, tail = 0, inflight = 0;
+    size_t off = 0;
+    while (off < bytes || inflight > 0) {
+        while (off < bytes && inflight < Context::kChunks - 1) {
+            int k = ctx->next_chunk;
+            ctx->next_chunk = (k + 1) % Context::kChunks;
+            SDB_CUDA(cudaEventSynchronize(ctx->chunk_free[k]));
+            size_t len = bytes - off < Context::kChunkBytes ? bytes - off : Context::kChunkBytes;
+            SDB_CUDA(cudaMemcpyAsync(ctx->chunk[k], (const char*)d_src + off, len,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+            SDB_CUDA(cudaEventRecord(ctx->chunk_free[k], ctx->stream));
+            pend[tail] = {k, off, len};
+            tail = (tail + 1) % Context::kChunks;
+            ++inflight;
+            off += len;
+        }
+        Pending p = pend[head];
+        head = (head + 1) % Context::kChunks;
+        --inflight;
+        SDB_CUDA(cudaEventSynchronize(ctx->chunk_free[p.k]));
+        fast_memcpy((char*)h_dst + p.off, ctx->chunk[p.k], p.len);
+    }
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status h2d_2d(Context* ctx, void* d_dst, size_t d_pitch, const void* h_src, size_t h_pitch,
+                  size_t row_bytes, size_t rows) {
+    if (rows == 0 || row_bytes == 0) return SDB_STATUS_SUCCESS;
+    if (d_pitch == row_bytes && h_pitch == row_bytes) return h2d(ctx, d_dst, h_src, row_bytes * rows);
+    // strided panels are rare (ld != n): let the driver do the 2-D copy
+    SDB_CUDA(cudaMemcpy2DAsync(d_dst, d_pitch, h_src, h_pitch, row_bytes, rows,
+                               cudaMemcpyHostToDevice, ctx->stream));
+    if (!is_pinned(h_src)) SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status d2h_2d(Context* ctx, void* h_dst, size_t h_pitch, const void* d_src, size_t d_pitch,
+                  size_t row_bytes, size_t rows) {
+    if (rows == 0 || row_bytes == 0) return SDB_STATUS_SUCCESS;
+    if (d_pitch == row_bytes && h_pitch == row_bytes) return d2h(ctx, h_dst, d_src, row_bytes * rows);
+    SDB_CUDA(cudaMemcpy2DAsync(h_dst, h_pitch, d_src, d_pitch, row_bytes, rows,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SDB_STATUS_SUCCESS;
+}
+
+// ---------------------------------------------------------------- timers
+sdb_status PhaseTimer::init(cudaStream_t stream) {
+    s = stream;
+    for (auto& e : ev) SDB_CUDA(cudaEventCreate(&e));
+    return SDB_STATUS_SUCCESS;
+}
+sdb_status PhaseTimer::mark(int i) {
+    SDB_CUDA(cudaEventRecord(ev[i], s));
+    return SDB_STATUS_SUCCESS;
+}
+void PhaseTimer::finish(Context* ctx) {
+    if (!ev[3]) return;
+    if (cudaEventSynchronize(ev[3]) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    for (int i = 0; i < 3; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) != cudaSuccess) {
+            cudaGetLastError();
+            ms = 0.f;
+        }
+        ctx->last_ms[i] = ms;
+    }
+}
+PhaseTimer::~PhaseTimer() {
+    for (auto& e : ev)
+        if (e) cudaEventDestroy(e);
+}
+
+}  // namespace sdb
+
+// =============================================================== ABI: misc
+using namespace sdb;
+
+extern "C" {
+
+int sdb_last_error(char* buf, int len) {
+    if (buf && len > 0) {
+        strncpy(buf, t_err, size_t(len) - 1);
+        buf[len - 1] = '\0';
+    }
+    return int(strlen(t_err));
+}
+
+int64_t sdb_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+sdb_status sdb_last_timing(double ms[3]) {
+    SDB_REQUIRE(ms != nullptr, SDB_STATUS_INVALID_VALUE, "sdb_last_timing: null output");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    for (int i = 0; i < 3; ++i) ms[i] = ctx->last_ms[i];
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_device_count(int* n) {
+    SDB_REQUIRE(n != nullptr, SDB_STATUS_INVALID_VALUE, "sdb_device_count: null output");
+    *n = 0;
+    SDB_CUDA(cudaGetDeviceCount(n));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_set_device(int device) {
+    SDB_CUDA(cudaSetDevice(device));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_get_device(int* device) {
+    SDB_REQUIRE(device != nullptr, SDB_STATUS_INVALID_VALUE, "sdb_get_device: null output");
+    SDB_CUDA(cudaGetDevice(device));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_version_string(char* buf, int len) {
+    SDB_REQUIRE(buf != nullptr && len > 0, SDB_STATUS_INVALID_VALUE, "sdb_version_string: bad buffer");
+    int rt = 0, drv = 0, ndev = 0, dev = 0;
+    cudaRuntimeGetVersion(&rt);
+    cudaDriverGetVersion(&drv);
+    char gpu[160] = "no CUDA device visible";
+    if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0 && cudaGetDevice(&dev) == cudaSuccess) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) == cudaSuccess)
+            snprintf(gpu, sizeof(gpu), "%s sm_%d%d, %d SMs, %.0f GiB, L2 %d MiB (device %d of %d)", p.name,
+                     p.major, p.minor, p.multiProcessorCount, double(p.totalGlobalMem) / double(1 << 30),
+                     p.l2CacheSize >> 20, dev, ndev);
+    } else {
+        cudaGetLastError();
+    }
+    snprintf(buf, size_t(len), "sparse_dot_b200 libsdb200 0.1.0 (sm_100a) | CUDA runtime %d.%d, driver %d.%d | %s",
+             rt / 1000, (rt % 1000) / 10, drv / 1000, (drv % 1000) / 10, gpu);
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_host_alloc(void** p, size_t bytes) {
+    SDB_REQUIRE(p != nullptr, SDB_STATUS_INVALID_VALUE, "sdb_host_alloc: null output");
+    *p = nullptr;
+    SDB_CUDA(cudaHostAlloc(p, bytes ? bytes : 16, cudaHostAllocDefault));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_host_free(void* p) {
+    if (p) SDB_CUDA(cudaFreeHost(p));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_dev_alloc(void** p, size_t bytes) {
+    SDB_REQUIRE(p != nullptr, SDB_STATUS_INVALID_VALUE, "sdb_dev_alloc: null output");
+    *p = nullptr;
+    SDB_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_dev_free(void* p) {
+    if (p) SDB_CUDA(cudaFree(p));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_memcpy(void* dst, const void* src, size_t bytes, int kind) {
+    SDB_REQUIRE(kind >= 1 && kind <= 3, SDB_STATUS_INVALID_VALUE, "sdb_memcpy: kind must be 1, 2 or 3");
+    if (bytes == 0) return SDB_STATUS_SUCCESS;
+    SDB_REQUIRE(dst && src, SDB_STATUS_INVALID_VALUE, "sdb_memcpy: null pointer");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    if (kind == 1) {
+        SDB_TRY(h2d(ctx, dst, src, bytes));
+    } else if (kind == 2) {
+        SDB_TRY(d2h(ctx, dst, src, bytes));
+    } else {
+        SDB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_device_synchronize(void) {
+    SDB_CUDA(cudaDeviceSynchronize());
+    return SDB_STATUS_SUCCESS;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == SDB_IPC_TOKEN_BYTES, "IPC token size");
+
+sdb_status sdb_ipc_export(const void* d_ptr, char* token) {
+    SDB_REQUIRE(d_ptr && token, SDB_STATUS_INVALID_VALUE, "sdb_ipc_export: null argument");
+    cudaIpcMemHandle_t h;
+    SDB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    memcpy(token, &h, sizeof(h));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_ipc_open(const char* token, void** d_ptr) {
+    SDB_REQUIRE(d_ptr && token, SDB_STATUS_INVALID_VALUE, "sdb_ipc_open: null argument");
+    *d_ptr = nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, token, sizeof(h));
+    SDB_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_ipc_close(void* d_ptr) {
+    if (d_ptr) SDB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return SDB_STATUS_SUCCESS;
+}
+
+// nnz-balanced contiguous row blocks (SURVEY §8e "Partitioning"): bounds[p] is
+// the first row whose cumulative nnz reaches p/parts of the total.
+sdb_status sdb_partition_rows(const void* indptr, int index_bits, int64_t rows, int parts,
+                              int64_t* bounds) {
+    SDB_REQUIRE(indptr && bounds && parts > 0 && rows >= 0, SDB_STATUS_INVALID_VALUE,
+                "sdb_partition_rows: bad arguments");
+    SDB_REQUIRE(index_bits == 32 || index_bits == 64, SDB_STATUS_INVALID_VALUE,
+                "sdb_partition_rows: index_bits must be 32 or 64");
+    auto at = [&](int64_t i) -> int64_t {
+        return index_bits == 32 ? int64_t(static_cast<const int32_t*>(indptr)[i])
+                                : static_cast<const int64_t*>(indptr)[i];
+    };
+    const int64_t base = at(0), total = at(rows) - base;
+    bounds[0] = 0;
+    for (int p = 1; p < parts; ++p) {
+        if (total == 0) {  // no nonzeros: split rows evenly
+            bounds[p] = rows * p / parts;
+            continue;
+        }
+        // smallest row r with indptr[r] - base >= total * p / parts
+        const int64_t want = base + (total / parts) * p + (total % parts) * p / parts;
+        int64_t lo = bounds[p - 1], hi = rows;
+        while (lo < hi) {
+            int64_t mid = lo + (hi - lo) / 2;
+            if (at(mid) >= want) hi = mid;
+            else lo = mid + 1;
+        }
+        bounds[p] = lo;
+    }
+    bounds[parts] = rows;
+    return SDB_STATUS_SUCCESS;
+}
+
+}  // extern "C"

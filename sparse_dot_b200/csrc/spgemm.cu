@@ -1,0 +1,673 @@
+// spgemm.cu — sparse x sparse products:
+//   sdb_spgemm        C = op(A) * B, sparse result   (mkl_sparse_spmm,     _sparse_sparse.py:21-44)
+//   sdb_spgemm_dense  dense C = op(A) * B, overwrite (mkl_sparse_?_spmmd,  _sparse_sparse.py:56-106)
+//   sdb_syrk          upper(A^T A) / upper(A A^T)    (mkl_sparse_syrk,     _gram_matrix.py:43-92)
+//   sdb_syrkd         dense upper, alpha/beta        (mkl_sparse_?_syrkd,  _gram_matrix.py:104-171)
+//
+// Sparse result: Gustavson row-by-row in two passes (symbolic count, numeric
+// fill) so the result is allocated exactly once between them.  Rows are binned
+// by an upper bound of their work (symbolic) / by their exact length (numeric):
+//   warp bin   per-warp hash table in shared memory (kWarpSlots slots)
+//   CTA bin    one CTA, one shared-memory hash table (kCtaSlots slots)
+//   wide bin   one CTA, dense accumulator + bitmap in global memory (L2
+//              resident), emitted in ascending column order
+// MKL's structural convention is kept: an entry exists for every structural
+// product even if the values cancel to 0.0 (SURVEY §8c parity hazard 2), and
+// columns inside a row are unordered until sdb_order.
+// sdb_syrk is the same two passes on (A^T, A) or (A, A^T) with a col >= row
+// filter.  Dense results accumulate one output row (column tile) per CTA in
+// shared memory and write it once.  HBM/L2-bound integer + FMA work.
+#include "common.h"
+#include "prims.h"
+#include "types.cuh"
+
+namespace sdb {
+
+constexpr int kWarpSlots = 512, kWarpSlotsLog2 = 9, kWarpMax = 256;
+constexpr int kCtaSlots = 8192, kCtaSlotsLog2 = 13, kCtaMax = 4096;
+constexpr int kHashWarps = 8;  // warps per CTA in the warp-bin kernels
+constexpr int kCtaThreads = 512;
+constexpr int32_t kEmpty = -1;
+
+__device__ __forceinline__ uint32_t hash_slot(int32_t col, int log2size) {
+    return (uint32_t(col) * 0x9E3779B1u) >> (32 - log2size);
+}
+
+// returns 1 when `col` was not in the table yet; *slot = where it lives
+template <int SLOTS, int LOG2>
+__device__ __forceinline__ int hash_insert(int32_t* keys, int32_t col, uint32_t* slot) {
+    uint32_t h = hash_slot(col, LOG2);
+    while (true) {
+        int32_t cur = *reinterpret_cast<volatile int32_t*>(keys + h);
+        if (cur == kEmpty) cur = atomicCAS(keys + h, kEmpty, col);
+        if (cur == kEmpty) {
+            *slot = h;
+            return 1;
+        }
+        if (cur == col) {
+            *slot = h;
+            return 0;
+        }
+        h = (h + 1) & (SLOTS - 1);
+    }
+}
+
+// ------------------------------------------------------------ work estimate
+// ub[i] = sum over entries (i,k) of L of len(R[k]), clamped to INT32_MAX
+__global__ void __launch_bounds__(256) row_products_kernel(int64_t rows, const int64_t* __restrict__ l_ptr,
+                                                           const int32_t* __restrict__ l_idx,
+                                                           const int64_t* __restrict__ r_ptr,
+                                                           int32_t* __restrict__ ub) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (i >= rows) return;
+    int64_t acc = 0;
+    for (int64_t p = l_ptr[i] + lane; p < l_ptr[i + 1]; p += 32) {
+        const int32_t k = l_idx[p];
+        acc += r_ptr[k + 1] - r_ptr[k];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) ub[i] = int32_t(min(acc, int64_t(INT32_MAX)));
+}
+
+// rows with size 0 get c_len = 0 here; the others go to one of three lists
+__global__ void __launch_bounds__(256) bin_rows_kernel(int64_t rows, const int32_t* __restrict__ size,
+                                                       int32_t* __restrict__ zero_len, int32_t* __restrict__ list_w,
+                                                       int32_t* __restrict__ list_c, int32_t* __restrict__ list_g,
+                                                       unsigned* __restrict__ counters) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int bin = -1;
+    if (i < rows) {
+        const int32_t v = size[i];
+        if (v == 0) {
+            if (zero_len) zero_len[i] = 0;
+        } else {
+            bin = v <= kWarpMax ? 0 : (v <= kCtaMax ? 1 : 2);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {  // warp-aggregated append
+        const unsigned m = __ballot_sync(0xffffffffu, bin == b);
+        if (m == 0) continue;
+        unsigned base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(&counters[b], unsigned(__popc(m)));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (bin == b) {
+            int32_t* list = b == 0 ? list_w : (b == 1 ? list_c : list_g);
+            list[base + __popc(m & ((1u << lane) - 1))] = int32_t(i);
+        }
+    }
+}
+
+// ------------------------------------------------------------ hash passes
+// One pass over the products of row i; NUMERIC adds values, else only counts.
+// `team` = 32 for a warp-owned table, blockDim.x for a CTA-owned one.
+template <typename T, bool NUMERIC, int SLOTS, int LOG2>
+__device__ __forceinline__ int hash_row(int64_t i, int tid, int team, const int64_t* __restrict__ l_ptr,
+                                        const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
+                                        const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
+                                        const T* __restrict__ r_val, bool upper, int32_t* keys, T* vals) {
+    int added = 0;
+    const int lane = tid & 31;
+    const int nwarps = team >> 5, warp = tid >> 5;
+    // every warp of the team takes L entries in turn; its lanes stride the R row
+    for (int64_t p0 = l_ptr[i] + int64_t(warp) * 32; p0 < l_ptr[i + 1]; p0 += int64_t(nwarps) * 32) {
+        const int64_t mine = p0 + lane;
+        int64_t rb = 0, re = 0;
+        T a = Num<T>::zero();
+        if (mine < l_ptr[i + 1]) {
+            const int32_t k = l_idx[mine];
+            rb = r_ptr[k];
+            re = r_ptr[k + 1];
+            if (NUMERIC) a = l_val[mine];
+        }
+        const int cnt = int(min(int64_t(32), l_ptr[i + 1] - p0));
+        for (int j = 0; j < cnt; ++j) {
+            const int64_t qb = __shfl_sync(0xffffffffu, rb, j), qe = __shfl_sync(0xffffffffu, re, j);
+            T aj = Num<T>::zero();
+            if (NUMERIC) aj = shfl(0xffffffffu, a, j, 32);
+            for (int64_t q = qb + lane; q < qe; q += 32) {
+                const int32_t col = r_idx[q];
+                if (upper && int64_t(col) < i) continue;
+                uint32_t slot;
+                added += hash_insert<SLOTS, LOG2>(keys, col, &slot);
+                if (NUMERIC) atomic_add(vals + slot, mul(aj, r_val[q]));
+            }
+        }
+    }
+    return added;
+}
+
+template <typename T, bool NUMERIC>
+__global__ void __launch_bounds__(kHashWarps * 32)
+    spgemm_warp_kernel(const int32_t* __restrict__ list, unsigned n_list, const int64_t* __restrict__ l_ptr,
+                       const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
+                       const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
+                       const T* __restrict__ r_val, bool upper, int32_t* __restrict__ c_len,
+                       const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* all_keys = reinterpret_cast<int32_t*>(smem_raw);
+    T* all_vals = reinterpret_cast<T*>(smem_raw + sizeof(int32_t) * kWarpSlots * kHashWarps);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned w = blockIdx.x * kHashWarps + warp;
+    if (w >= n_list) return;
+    const int64_t i = list[w];
+    int32_t* keys = all_keys + warp * kWarpSlots;
+    T* vals = all_vals + warp * kWarpSlots;
+    for (int s = lane; s < kWarpSlots; s += 32) {
+        keys[s] = kEmpty;
+        if (NUMERIC) vals[s] = Num<T>::zero();
+    }
+    __syncwarp();
+    int added = hash_row<T, NUMERIC, kWarpSlots, kWarpSlotsLog2>(i, lane, 32, l_ptr, l_idx, l_val, r_ptr, r_idx,
+                                                                r_val, upper, keys, vals);
+    __syncwarp();
+    if (!NUMERIC) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) added += __shfl_xor_sync(0xffffffffu, added, d);
+        if (lane == 0) c_len[i] = added;
+        return;
+    }
+    int64_t out = c_ptr[i];
+    for (int s = lane; s < kWarpSlots; s += 32) {
+        const int32_t k = keys[s];
+        const unsigned m = __ballot_sync(0xffffffffu, k != kEmpty);
+        if (k != kEmpty) {
+            const int64_t o = out + __popc(m & ((1u << lane) - 1));
+            c_idx[o] = k;
+            c_val[o] = vals[s];
+        }
+        out += __popc(m);
+    }
+}
+
+template <typename T, bool NUMERIC>
+__global__ void __launch_bounds__(kCtaThreads)
+    spgemm_cta_kernel(const int32_t* __restrict__ list, const int64_t* __restrict__ l_ptr,
+                      const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
+                      const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
+                      const T* __restrict__ r_val, bool upper, int32_t* __restrict__ c_len,
+                      const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int32_t* keys = reinterpret_cast<int32_t*>(smem_raw);
+    T* vals = reinterpret_cast<T*>(smem_raw + sizeof(int32_t) * kCtaSlots);
+    __shared__ int total;
+    const int64_t i = list[blockIdx.x];
+    for (int s = threadIdx.x; s < kCtaSlots; s += kCtaThreads) {
+        keys[s] = kEmpty;
+        if (NUMERIC) vals[s] = Num<T>::zero();
+    }
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    int added = hash_row<T, NUMERIC, kCtaSlots, kCtaSlotsLog2>(i, threadIdx.x, kCtaThreads, l_ptr, l_idx, l_val,
+                                                               r_ptr, r_idx, r_val, upper, keys, vals);
+    if (!NUMERIC) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) added += __shfl_xor_sync(0xffffffffu, added, d);
+        if ((threadIdx.x & 31) == 0 && added) atomicAdd(&total, added);
+        __syncthreads();
+        if (threadIdx.x == 0) c_len[i] = total;
+        return;
+    }
+    __syncthreads();
+    const int64_t out = c_ptr[i];
+    const int lane = threadIdx.x & 31;
+    for (int s = threadIdx.x; s < kCtaSlots; s += kCtaThreads) {
+        const int32_t k = keys[s];
+        const unsigned m = __ballot_sync(0xffffffffu, k != kEmpty);
+        int base = 0;
+        if (lane == 0 && m) base = atomicAdd(&total, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (k != kEmpty) {
+            const int64_t o = out + base + __popc(m & ((1u << lane) - 1));
+            c_idx[o] = k;
+            c_val[o] = vals[s];
+        }
+    }
+}
+
+// Wide rows: bitmap (and dense values) of the whole column range per resident
+// CTA, in global memory.  Grid-stride over the listed rows.
+template <typename T, bool NUMERIC>
+__global__ void __launch_bounds__(1024)
+    spgemm_wide_kernel(const int32_t* __restrict__ list, unsigned n_list, int64_t n_cols,
+                       const int64_t* __restrict__ l_ptr, const int32_t* __restrict__ l_idx,
+                       const T* __restrict__ l_val, const int64_t* __restrict__ r_ptr,
+                       const int32_t* __restrict__ r_idx, const T* __restrict__ r_val, bool upper,
+                       unsigned* __restrict__ bitmaps, T* __restrict__ dense, int32_t* __restrict__ c_len,
+                       const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
+    __shared__ int warp_tot[32];
+    __shared__ int64_t running;
+    const int64_t words = (n_cols + 31) >> 5;
+    unsigned* bm = bitmaps + int64_t(blockIdx.x) * words;
+    T* acc = NUMERIC ? dense + int64_t(blockIdx.x) * n_cols : nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (unsigned li = blockIdx.x; li < n_list; li += gridDim.x) {
+        const int64_t i = list[li];
+        // scatter
+        for (int64_t p = l_ptr[i] + warp; p < l_ptr[i + 1]; p += nwarps) {
+            const int32_t k = l_idx[p];
+            T a = Num<T>::zero();
+            if (NUMERIC) a = l_val[p];
+            for (int64_t q = r_ptr[k] + lane; q < r_ptr[k + 1]; q += 32) {
+                const int32_t col = r_idx[q];
+                if (upper && int64_t(col) < i) continue;
+                atomicOr(&bm[col >> 5], 1u << (col & 31));
+                if (NUMERIC) atomic_add(acc + col, mul(a, r_val[q]));
+            }
+        }
+        if (threadIdx.x == 0) running = 0;
+        __syncthreads();
+        // ordered emission / count, one bitmap word per thread per sweep
+        for (int64_t w0 = 0; w0 < words; w0 += blockDim.x) {
+            const int64_t w = w0 + threadIdx.x;
+            unsigned bits = w < words ? __ldcg(bm + w) : 0u;
+            int cnt = __popc(bits);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) warp_tot[warp] = incl;
+            __syncthreads();
+            int before = 0, sweep = 0;
+            for (int x = 0; x < nwarps; ++x) {
+                const int t = warp_tot[x];
+                if (x < warp) before += t;
+                sweep += t;
+            }
+            const int64_t base = running;
+            if (NUMERIC && bits) {
+                int64_t o = c_ptr[i] + base + before + incl - cnt;
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int64_t col = (w << 5) + b;
+                    c_idx[o] = int32_t(col);
+                    c_val[o] = ldcg(acc + col);
+                    acc[col] = Num<T>::zero();
+                    ++o;
+                }
+            }
+            if (w < words && cnt) bm[w] = 0u;
+            __syncthreads();
+            if (threadIdx.x == 0) running = base + sweep;
+            __syncthreads();
+        }
+        if (!NUMERIC && threadIdx.x == 0) c_len[i] = int32_t(running);
+        __syncthreads();
+    }
+}
+
+template <typename T, bool NUMERIC>
+static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, bool upper, const int32_t* sizes,
+                           int32_t* c_len, const int64_t* c_ptr, int32_t* c_idx, T* c_val) {
+    cudaStream_t s = ctx->stream;
+    const int64_t rows = l.rows;
+    DevBuf lw, lc, lg, counters;
+    SDB_TRY(lw.alloc(size_t(rows) * 4, s));
+    SDB_TRY(lc.alloc(size_t(rows) * 4, s));
+    SDB_TRY(lg.alloc(size_t(rows) * 4, s));
+    SDB_TRY(counters.alloc(3 * sizeof(unsigned), s));
+    SDB_CUDA(cudaMemsetAsync(counters.p, 0, 3 * sizeof(unsigned), s));
+    SDB_LAUNCH(bin_rows_kernel, unsigned((rows + 255) / 256), 256, 0, s, rows, sizes, NUMERIC ? nullptr : c_len,
+               lw.as<int32_t>(), lc.as<int32_t>(), lg.as<int32_t>(), counters.as<unsigned>());
+    unsigned h[3];
+    SDB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    SDB_CUDA(cudaStreamSynchronize(s));
+    const int64_t* lp = l.indptr;
+    const int32_t* li = l.indices;
+    const T* lv = static_cast<const T*>(l.values);
+    const int64_t* rp = r.indptr;
+    const int32_t* ri = r.indices;
+    const T* rv = static_cast<const T*>(r.values);
+    if (h[0] > 0) {
+        const size_t smem = size_t(kHashWarps) * kWarpSlots * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0));
+        SDB_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel<T, NUMERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(smem)));
+        SDB_LAUNCH((spgemm_warp_kernel<T, NUMERIC>), (h[0] + kHashWarps - 1) / kHashWarps, kHashWarps * 32, smem, s,
+                   lw.as<int32_t>(), h[0], lp, li, lv, rp, ri, rv, upper, c_len, c_ptr, c_idx, c_val);
+    }
+    if (h[1] > 0) {
+        const size_t smem = size_t(kCtaSlots) * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0));
+        SDB_CUDA(cudaFuncSetAttribute(spgemm_cta_kernel<T, NUMERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(smem)));
+        SDB_LAUNCH((spgemm_cta_kernel<T, NUMERIC>), h[1], kCtaThreads, smem, s, lc.as<int32_t>(), lp, li, lv, rp, ri,
+                   rv, upper, c_len, c_ptr, c_idx, c_val);
+    }
+    if (h[2] > 0) {
+        const int64_t n_cols = r.cols;
+        const int64_t words = (n_cols + 31) >> 5;
+        // resident CTAs: bounded by the list, the SM count and ~2 GiB of scratch
+        const int64_t per_cta = words * 4 + (NUMERIC ? n_cols * int64_t(sizeof(T)) : 0);
+        int64_t ctas = std::min<int64_t>(h[2], ctx->sm_count);
+        ctas = std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t(2) << 30) / std::max<int64_t>(per_cta, 1)));
+        DevBuf bm, dense;
+        SDB_TRY(bm.alloc(size_t(ctas * words) * 4, s));
+        SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(ctas * words) * 4, s));
+        if (NUMERIC) {
+            SDB_TRY(dense.alloc(size_t(ctas * n_cols) * sizeof(T), s));
+            SDB_CUDA(cudaMemsetAsync(dense.p, 0, size_t(ctas * n_cols) * sizeof(T), s));
+        }
+        SDB_LAUNCH((spgemm_wide_kernel<T, NUMERIC>), unsigned(ctas), 1024, 0, s, lg.as<int32_t>(), h[2], n_cols, lp,
+                   li, lv, rp, ri, rv, upper, bm.as<unsigned>(), dense.as<T>(), c_len, c_ptr, c_idx, c_val);
+    }
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int dtype, bool upper, sdb_mat** out) {
+    cudaStream_t s = ctx->stream;
+    SDB_REQUIRE(l.cols == r.rows, SDB_STATUS_INVALID_VALUE, "spgemm: inner dimensions %lld and %lld differ",
+                (long long)l.cols, (long long)r.rows);
+    const int64_t rows = l.rows;
+    DevBuf ub, c_len;
+    SDB_TRY(ub.alloc(size_t(rows + 1) * 4, s));
+    SDB_TRY(c_len.alloc(size_t(rows + 1) * 4, s));
+    sdb_mat* c = nullptr;
+    if (rows > 0) {
+        SDB_LAUNCH(row_products_kernel, unsigned((rows * 32 + 255) / 256), 256, 0, s, rows, l.indptr, l.indices,
+                   r.indptr, ub.as<int32_t>());
+        SDB_TRY(SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
+            return run_pass<T, false>(ctx, l, r, upper, ub.as<int32_t>(), c_len.as<int32_t>(), nullptr, nullptr,
+                                      nullptr);
+        }));
+    }
+    // row offsets of C, then its size
+    DevBuf c_ptr;
+    SDB_TRY(c_ptr.alloc(size_t(rows + 1) * 8, s));
+    SDB_TRY(exclusive_scan_i32_to_i64(s, c_len.as<int32_t>(), c_ptr.as<int64_t>(), rows));
+    int64_t nnz = 0;
+    SDB_CUDA(cudaMemcpyAsync(&nnz, c_ptr.as<int64_t>() + rows, 8, cudaMemcpyDeviceToHost, s));
+    SDB_CUDA(cudaStreamSynchronize(s));
+    SDB_TRY(new_handle(&c, SDB_FMT_CSR, dtype, rows, r.cols, nnz, 1, SDB_LAYOUT_ROW_MAJOR, s));
+    sdb_status st = [&]() -> sdb_status {
+        SDB_CUDA(cudaMemcpyAsync(c->indptr, c_ptr.p, size_t(rows + 1) * 8, cudaMemcpyDeviceToDevice, s));
+        if (nnz == 0) return SDB_STATUS_SUCCESS;
+        return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
+            return run_pass<T, true>(ctx, l, r, upper, c_len.as<int32_t>(), nullptr, c->indptr, c->indices,
+                                     static_cast<T*>(c->values));
+        });
+    }();
+    if (st != SDB_STATUS_SUCCESS) {
+        free_handle(c);
+        return st;
+    }
+    *out = c;
+    return SDB_STATUS_SUCCESS;
+}
+
+// ============================================================ dense results
+// C[i, j0:j1) = alpha * sum_k L[i,k] * R[k, j0:j1) + beta * C[i, j0:j1), with an
+// optional col >= row restriction.  One CTA per (row, column tile); the tile
+// accumulates in shared memory (shared-memory atomics, every R entry lands
+// once) and is written to HBM once, coalesced.
+constexpr int kDenseThreads = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(kDenseThreads)
+    spgemm_dense_kernel(int64_t n_cols, int tile_cols, const int64_t* __restrict__ l_ptr,
+                        const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
+                        const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
+                        const T* __restrict__ r_val, bool upper, bool zero_lower, T alpha, T beta,
+                        T* __restrict__ C, int64_t ldc, bool col_major) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* acc = reinterpret_cast<T*>(smem_raw);
+    const int64_t i = blockIdx.x;
+    const int64_t j0 = int64_t(blockIdx.y) * tile_cols;
+    const int64_t j1 = min(n_cols, j0 + tile_cols);
+    const int64_t lo = upper ? max(j0, i) : j0;  // first column this CTA owns
+    if (upper && zero_lower)  // fresh result: the strict lower triangle is defined to be zero
+        for (int64_t j = j0 + threadIdx.x; j < min(lo, j1); j += kDenseThreads)
+            *(col_major ? C + j * ldc + i : C + i * ldc + j) = Num<T>::zero();
+    if (lo >= j1) return;
+    for (int64_t j = lo - j0 + threadIdx.x; j < j1 - j0; j += kDenseThreads) acc[j] = Num<T>::zero();
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kDenseThreads / 32;
+    for (int64_t p = l_ptr[i] + warp; p < l_ptr[i + 1]; p += kWarps) {
+        const int32_t k = l_idx[p];
+        const T a = l_val[p];
+        for (int64_t q = r_ptr[k] + lane; q < r_ptr[k + 1]; q += 32) {
+            const int64_t col = r_idx[q];
+            if (col >= lo && col < j1) atomic_add(acc + (col - j0), mul(a, r_val[q]));
+        }
+    }
+    __syncthreads();
+    const bool beta_zero = Num<T>::is_zero(beta);
+    for (int64_t j = lo + threadIdx.x; j < j1; j += kDenseThreads) {
+        T* c = col_major ? C + j * ldc + i : C + i * ldc + j;
+        const T v = mul(alpha, acc[j - j0]);
+        *c = beta_zero ? v : madd(beta, *c, v);
+    }
+}
+
+sdb_status spgemm_dense_device(Context* ctx, cudaStream_t s, const CsrView& l, const CsrView& r, int dtype,
+                               bool upper, bool zero_lower, const double* alpha, const double* beta, int layout,
+                               void* dC, int64_t ldc) {
+    (void)ctx;
+    SDB_REQUIRE(l.cols == r.rows, SDB_STATUS_INVALID_VALUE, "dense product: inner dimensions %lld and %lld differ",
+                (long long)l.cols, (long long)r.rows);
+    const int64_t m = l.rows, n = r.cols;
+    if (m == 0 || n == 0) return SDB_STATUS_SUCCESS;
+    SDB_REQUIRE(m < (int64_t(1) << 31), SDB_STATUS_NOT_SUPPORTED, "dense product: too many rows");
+    const bool col_major = layout == SDB_LAYOUT_COL_MAJOR;
+    SDB_REQUIRE(ldc >= (col_major ? m : n), SDB_STATUS_INVALID_VALUE, "dense product: ldc too small");
+    return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
+        const int64_t max_tile = (192 * 1024) / int64_t(sizeof(T));
+        const int64_t tiles = (n + max_tile - 1) / max_tile;
+        const int64_t tile = std::min<int64_t>(max_tile, ((n + tiles - 1) / tiles + 31) / 32 * 32);
+        const size_t smem = size_t(tile) * sizeof(T);
+        SDB_REQUIRE(tiles < 65536, SDB_STATUS_NOT_SUPPORTED, "dense product: too many column tiles");
+        SDB_CUDA(cudaFuncSetAttribute(spgemm_dense_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(std::max<size_t>(smem, 48 * 1024))));
+        SDB_LAUNCH(spgemm_dense_kernel<T>, dim3(unsigned(m), unsigned(tiles)), kDenseThreads, smem, s, n, int(tile),
+                   l.indptr, l.indices, static_cast<const T*>(l.values), r.indptr, r.indices,
+                   static_cast<const T*>(r.values), upper, zero_lower, Num<T>::make(alpha[0], alpha[1]),
+                   Num<T>::make(beta[0], beta[1]), static_cast<T*>(dC), ldc, col_major);
+        return SDB_STATUS_SUCCESS;
+    });
+}
+
+}  // namespace sdb
+
+using namespace sdb;
+
+static sdb_status check_pair(const char* who, const sdb_mat* A, const sdb_mat* B) {
+    SDB_REQUIRE(A != nullptr && B != nullptr, SDB_STATUS_NOT_INITIALIZED, "%s: null handle", who);
+    SDB_REQUIRE(valid(A) && valid(B), SDB_STATUS_INVALID_VALUE, "%s: not a live sdb_mat handle", who);
+    SDB_REQUIRE(A->dtype == B->dtype, SDB_STATUS_INVALID_VALUE, "%s: operand dtypes differ", who);
+    return SDB_STATUS_SUCCESS;
+}
+
+static int64_t logical_rows(const sdb_mat* m) { return m->rows * m->block; }
+static int64_t logical_cols(const sdb_mat* m) { return m->cols * m->block; }
+
+extern "C" {
+
+sdb_status sdb_spgemm(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C) {
+    SDB_REQUIRE(C != nullptr, SDB_STATUS_INVALID_VALUE, "spgemm: null output handle");
+    *C = nullptr;
+    SDB_TRY(check_pair("spgemm", A, B));
+    SDB_REQUIRE(op == SDB_OP_NON_TRANSPOSE || op == SDB_OP_TRANSPOSE, SDB_STATUS_NOT_SUPPORTED,
+                "spgemm: op %d not supported", op);
+    SDB_REQUIRE(A->format != SDB_FMT_BSR && B->format != SDB_FMT_BSR, SDB_STATUS_NOT_SUPPORTED,
+                "spgemm: BSR operands are not supported for a sparse result");
+    const bool ta = op == SDB_OP_TRANSPOSE;
+    const int64_t inner_a = ta ? logical_rows(A) : logical_cols(A);
+    SDB_REQUIRE(inner_a == logical_rows(B), SDB_STATUS_INVALID_VALUE, "spgemm: inner dimensions differ");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    CsrView l, r;
+    sdb_mat* c = nullptr;
+    if (A->format == SDB_FMT_CSC) {
+        // result in A's format: CSC(C) = CSR(C^T) = CSR(B^T) * CSR(op(A)^T)
+        SDB_TRY(csr_view(ctx, B, true, &l));
+        SDB_TRY(csr_view(ctx, A, !ta, &r));
+        SDB_TRY(spgemm_device(ctx, l, r, A->dtype, false, &c));
+        c->format = SDB_FMT_CSC;
+        std::swap(c->rows, c->cols);
+    } else {
+        SDB_TRY(csr_view(ctx, A, ta, &l));
+        SDB_TRY(csr_view(ctx, B, false, &r));
+        SDB_TRY(spgemm_device(ctx, l, r, A->dtype, false, &c));
+    }
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *C = c;
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_syrk(int op, const sdb_mat* A, sdb_mat** C) {
+    SDB_REQUIRE(C != nullptr, SDB_STATUS_INVALID_VALUE, "syrk: null output handle");
+    *C = nullptr;
+    SDB_REQUIRE(A != nullptr, SDB_STATUS_NOT_INITIALIZED, "syrk: null handle");
+    SDB_REQUIRE(valid(A), SDB_STATUS_INVALID_VALUE, "syrk: not a live sdb_mat handle");
+    SDB_REQUIRE(op == SDB_OP_NON_TRANSPOSE || op == SDB_OP_TRANSPOSE, SDB_STATUS_NOT_SUPPORTED,
+                "syrk: op %d not supported", op);
+    SDB_REQUIRE(A->format != SDB_FMT_BSR, SDB_STATUS_NOT_SUPPORTED, "syrk: BSR is not supported");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    CsrView a, at;
+    SDB_TRY(csr_view(ctx, A, false, &a));
+    SDB_TRY(csr_view(ctx, A, true, &at));
+    // op = TRANSPOSE: A^T A = (A^T) * A;  op = NON_TRANSPOSE: A A^T = A * (A^T)
+    sdb_mat* c = nullptr;
+    if (op == SDB_OP_TRANSPOSE) SDB_TRY(spgemm_device(ctx, at, a, A->dtype, true, &c));
+    else SDB_TRY(spgemm_device(ctx, a, at, A->dtype, true, &c));
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *C = c;
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_spgemm_dense_dev(int op, const sdb_mat* A, const sdb_mat* B, int layout, void* dC, int64_t ldc,
+                                void* stream) {
+    SDB_TRY(check_pair("spgemm_dense", A, B));
+    SDB_REQUIRE(dC != nullptr, SDB_STATUS_INVALID_VALUE, "spgemm_dense: null output");
+    SDB_REQUIRE(op == SDB_OP_NON_TRANSPOSE || op == SDB_OP_TRANSPOSE, SDB_STATUS_NOT_SUPPORTED,
+                "spgemm_dense: op %d not supported", op);
+    SDB_REQUIRE(layout == SDB_LAYOUT_ROW_MAJOR || layout == SDB_LAYOUT_COL_MAJOR, SDB_STATUS_INVALID_VALUE,
+                "spgemm_dense: bad layout %d", layout);
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    CsrView l, r;
+    SDB_TRY(csr_view(ctx, A, op == SDB_OP_TRANSPOSE, &l));
+    SDB_TRY(csr_view(ctx, B, false, &r));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    if (s != ctx->stream) SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double one[2] = {1.0, 0.0}, zero[2] = {0.0, 0.0};
+    return spgemm_dense_device(ctx, s, l, r, A->dtype, false, false, one, zero, layout, dC, ldc);
+}
+
+sdb_status sdb_spgemm_dense(int op, const sdb_mat* A, const sdb_mat* B, int layout, void* C, int64_t ldc) {
+    SDB_TRY(check_pair("spgemm_dense", A, B));
+    SDB_REQUIRE(C != nullptr, SDB_STATUS_INVALID_VALUE, "spgemm_dense: null output");
+    SDB_REQUIRE(layout == SDB_LAYOUT_ROW_MAJOR || layout == SDB_LAYOUT_COL_MAJOR, SDB_STATUS_INVALID_VALUE,
+                "spgemm_dense: bad layout %d", layout);
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    const int64_t m = op == SDB_OP_TRANSPOSE ? logical_cols(A) : logical_rows(A), n = logical_cols(B);
+    const size_t es = dtype_size(A->dtype);
+    const bool row_major = layout == SDB_LAYOUT_ROW_MAJOR;
+    const int64_t lines = row_major ? m : n, run = row_major ? n : m;
+    SDB_REQUIRE(ldc >= run, SDB_STATUS_INVALID_VALUE, "spgemm_dense: ldc too small");
+    PhaseTimer timer;
+    SDB_TRY(timer.init(ctx->stream));
+    SDB_TRY(timer.mark(0));
+    SDB_TRY(timer.mark(1));
+    DevBuf dc;
+    SDB_TRY(dc.alloc(size_t(lines) * size_t(run) * es, ctx->stream));
+    SDB_TRY(sdb_spgemm_dense_dev(op, A, B, layout, dc.p, run, nullptr));
+    SDB_TRY(timer.mark(2));
+    SDB_TRY(d2h_2d(ctx, C, size_t(ldc) * es, dc.p, size_t(run) * es, size_t(run) * es, size_t(lines)));
+    SDB_TRY(timer.mark(3));
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    timer.finish(ctx);
+    return SDB_STATUS_SUCCESS;
+}
+
+static sdb_status syrkd_dev_impl(int op, const sdb_mat* A, const double* alpha, const double* beta, void* dC,
+                                 int layout, int64_t ldc, void* stream, bool zero_lower) {
+    SDB_REQUIRE(A != nullptr, SDB_STATUS_NOT_INITIALIZED, "syrkd: null handle");
+    SDB_REQUIRE(valid(A), SDB_STATUS_INVALID_VALUE, "syrkd: not a live sdb_mat handle");
+    SDB_REQUIRE(alpha && beta && dC, SDB_STATUS_INVALID_VALUE, "syrkd: null argument");
+    SDB_REQUIRE(op == SDB_OP_NON_TRANSPOSE || op == SDB_OP_TRANSPOSE, SDB_STATUS_NOT_SUPPORTED,
+                "syrkd: op %d not supported", op);
+    SDB_REQUIRE(layout == SDB_LAYOUT_ROW_MAJOR || layout == SDB_LAYOUT_COL_MAJOR, SDB_STATUS_INVALID_VALUE,
+                "syrkd: bad layout %d", layout);
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    CsrView a, at;
+    SDB_TRY(csr_view(ctx, A, false, &a));
+    SDB_TRY(csr_view(ctx, A, true, &at));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    if (s != ctx->stream) SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (op == SDB_OP_TRANSPOSE)
+        return spgemm_dense_device(ctx, s, at, a, A->dtype, true, zero_lower, alpha, beta, layout, dC, ldc);
+    return spgemm_dense_device(ctx, s, a, at, A->dtype, true, zero_lower, alpha, beta, layout, dC, ldc);
+}
+
+sdb_status sdb_syrkd_dev(int op, const sdb_mat* A, const double* alpha, const double* beta, void* dC, int layout,
+                         int64_t ldc, void* stream) {
+    return syrkd_dev_impl(op, A, alpha, beta, dC, layout, ldc, stream, false);
+}
+
+sdb_status sdb_syrkd_new(int op, const sdb_mat* A, const double* alpha, void* C, int layout, int64_t ldc) {
+    SDB_REQUIRE(A != nullptr, SDB_STATUS_NOT_INITIALIZED, "syrkd: null handle");
+    SDB_REQUIRE(valid(A), SDB_STATUS_INVALID_VALUE, "syrkd: not a live sdb_mat handle");
+    SDB_REQUIRE(alpha && C, SDB_STATUS_INVALID_VALUE, "syrkd: null argument");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    const int64_t n = op == SDB_OP_TRANSPOSE ? logical_cols(A) : logical_rows(A);
+    SDB_REQUIRE(ldc >= n, SDB_STATUS_INVALID_VALUE, "syrkd: ldc too small");
+    const size_t es = dtype_size(A->dtype);
+    PhaseTimer timer;
+    SDB_TRY(timer.init(ctx->stream));
+    SDB_TRY(timer.mark(0));
+    SDB_TRY(timer.mark(1));
+    DevBuf dc;
+    SDB_TRY(dc.alloc(size_t(n) * size_t(n) * es, ctx->stream));
+    const double zero[2] = {0.0, 0.0};
+    SDB_TRY(syrkd_dev_impl(op, A, alpha, zero, dc.p, layout, n, nullptr, true));
+    SDB_TRY(timer.mark(2));
+    SDB_TRY(d2h_2d(ctx, C, size_t(ldc) * es, dc.p, size_t(n) * es, size_t(n) * es, size_t(n)));
+    SDB_TRY(timer.mark(3));
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    timer.finish(ctx);
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_syrkd(int op, const sdb_mat* A, const double* alpha, const double* beta, void* C, int layout,
+                     int64_t ldc) {
+    SDB_REQUIRE(A != nullptr, SDB_STATUS_NOT_INITIALIZED, "syrkd: null handle");
+    SDB_REQUIRE(valid(A), SDB_STATUS_INVALID_VALUE, "syrkd: not a live sdb_mat handle");
+    SDB_REQUIRE(alpha && beta && C, SDB_STATUS_INVALID_VALUE, "syrkd: null argument");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    const int64_t n = op == SDB_OP_TRANSPOSE ? logical_cols(A) : logical_rows(A);
+    SDB_REQUIRE(ldc >= n, SDB_STATUS_INVALID_VALUE, "syrkd: ldc too small");
+    const size_t es = dtype_size(A->dtype);
+    const bool beta_zero = beta[0] == 0.0 && beta[1] == 0.0;
+    PhaseTimer timer;
+    SDB_TRY(timer.init(ctx->stream));
+    SDB_TRY(timer.mark(0));
+    DevBuf dc;
+    SDB_TRY(dc.alloc(size_t(n) * size_t(n) * es, ctx->stream));
+    // The strict lower triangle is never written by the kernel and the caller's
+    // values there must survive the whole-panel copy back, so the panel always
+    // goes up (sdb_syrkd_new is the no-upload variant for a fresh result).
+    (void)beta_zero;
+    SDB_TRY(h2d_2d(ctx, dc.p, size_t(n) * es, C, size_t(ldc) * es, size_t(n) * es, size_t(n)));
+    SDB_TRY(timer.mark(1));
+    SDB_TRY(sdb_syrkd_dev(op, A, alpha, beta, dc.p, layout, n, nullptr));
+    SDB_TRY(timer.mark(2));
+    SDB_TRY(d2h_2d(ctx, C, size_t(ldc) * es, dc.p, size_t(n) * es, size_t(n) * es, size_t(n)));
+    SDB_TRY(timer.mark(3));
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    timer.finish(ctx);
+    return SDB_STATUS_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,352 @@
+// spmm.cu — Y := alpha * op(A) * X + beta * Y with A sparse (CSR view) and X, Y
+// dense.  Replaces mkl_sparse_{s,d,c,z}_mm as _sparse_dense_matmul drives it
+// (sparse_dot_mkl/_sparse_dense.py:34-132, the call itself at :111-123).
+//
+// Roofline: HBM.  Every stored entry of A gathers one n-wide row of X, so the
+// algorithmic traffic per entry is (4 + sizeof(T)) + n*sizeof(T) bytes, plus
+// n*sizeof(T)*(1 + [beta != 0]) per output row (gather model).
+// Arithmetic intensity is ~0.5 FLOP/B: no tensor cores, the job is to keep
+// enough 16-byte gathers in flight.
+//
+// Mapping (row-major X / Y): a group of LANES lanes owns one output row and a
+// (LANES * VEC)-column chunk of it; each lane keeps VEC consecutive columns in
+// registers.  The group reads LANES (column, value) pairs of the CSR row with
+// one coalesced load each, then every pair is broadcast by shuffle and each
+// lane issues ONE 16-byte load of its slice of X[column, :] — the group's
+// loads cover a contiguous LANES*16 bytes of that X row, i.e. whole 128-byte
+// lines.  kUnroll gathers are issued back to back before the first FMA so each
+// warp keeps kUnroll * 512 B in flight.  The alpha/beta epilogue is fused and
+// the finished row slice is stored once to every peer panel (n_peers = 1
+// normally; > 1 is the fused all-gather over NVLink peer mappings, §8e).
+#include "common.h"
+#include "prims.h"
+#include "types.cuh"
+
+namespace sdb {
+
+constexpr int kMaxPeers = 8;
+constexpr int kSpmmWarps = 8;  // warps per CTA
+constexpr int kUnroll = 8;
+
+template <typename T> struct PeerPanels {
+    T* y[kMaxPeers];
+};
+
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) Pack {
+    T v[VEC];
+};
+
+// read-only path; sizeof(Pack) is 4, 8 or 16 -> LDG.32 / .64 / .128
+template <typename T, int VEC> __device__ __forceinline__ Pack<T, VEC> load_pack(const T* p);
+template <> __device__ __forceinline__ Pack<float, 4> load_pack<float, 4>(const float* p) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    Pack<float, 4> r;
+    r.v[0] = q.x, r.v[1] = q.y, r.v[2] = q.z, r.v[3] = q.w;
+    return r;
+}
+template <> __device__ __forceinline__ Pack<double, 2> load_pack<double, 2>(const double* p) {
+    const double2 q = __ldg(reinterpret_cast<const double2*>(p));
+    Pack<double, 2> r;
+    r.v[0] = q.x, r.v[1] = q.y;
+    return r;
+}
+template <> __device__ __forceinline__ Pack<cf32, 2> load_pack<cf32, 2>(const cf32* p) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    Pack<cf32, 2> r;
+    r.v[0] = cf32{q.x, q.y}, r.v[1] = cf32{q.z, q.w};
+    return r;
+}
+template <> __device__ __forceinline__ Pack<cf64, 1> load_pack<cf64, 1>(const cf64* p) {
+    const double2 q = __ldg(reinterpret_cast<const double2*>(p));
+    Pack<cf64, 1> r;
+    r.v[0] = cf64{q.x, q.y};
+    return r;
+}
+template <> __device__ __forceinline__ Pack<float, 1> load_pack<float, 1>(const float* p) {
+    Pack<float, 1> r;
+    r.v[0] = __ldg(p);
+    return r;
+}
+template <> __device__ __forceinline__ Pack<double, 1> load_pack<double, 1>(const double* p) {
+    Pack<double, 1> r;
+    r.v[0] = __ldg(p);
+    return r;
+}
+template <> __device__ __forceinline__ Pack<cf32, 1> load_pack<cf32, 1>(const cf32* p) {
+    const float2 q = __ldg(reinterpret_cast<const float2*>(p));
+    Pack<cf32, 1> r;
+    r.v[0] = cf32{q.x, q.y};
+    return r;
+}
+
+template <typename T, int VEC> __device__ __forceinline__ void store_pack(T* p, const Pack<T, VEC>& a) {
+    *reinterpret_cast<Pack<T, VEC>*>(p) = a;
+}
+
+template <typename T, int VEC, int LANES>
+__global__ void __launch_bounds__(kSpmmWarps * 32)
+    spmm_rowmajor_kernel(int64_t rows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                         const T* __restrict__ values, bool conj_a, const T* __restrict__ X, int64_t ldx, int64_t n,
+                         T alpha, T beta, T* __restrict__ y_self, PeerPanels<T> out, int n_peers, int self, int64_t row0,
+                         int64_t ldy) {
+    constexpr int kRowsPerWarp = 32 / LANES;
+    constexpr unsigned kFull = 0xffffffffu;
+    constexpr int kU = LANES < kUnroll ? LANES : kUnroll;  // gathers in flight per lane
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LANES;  // position inside the row group
+    const int64_t warp = int64_t(blockIdx.x) * kSpmmWarps + (threadIdx.x >> 5);
+    const int64_t row = warp * kRowsPerWarp + lane / LANES;
+    const int64_t col0 = (int64_t(blockIdx.y) * LANES + sub) * VEC;
+    const bool row_ok = row < rows;
+    const bool col_ok = col0 < n;  // n % VEC == 0 on the vector path, VEC == 1 otherwise
+
+    int64_t p = 0, end = 0;
+    if (row_ok) {
+        p = indptr[row];
+        end = indptr[row + 1];
+    }
+    // the warp iterates together: shuffles need every lane, groups may differ in length
+    int64_t len = end - p;
+    if (LANES < 32) {
+#pragma unroll
+        for (int d = 16; d >= LANES; d >>= 1) len = max(len, __shfl_xor_sync(kFull, len, d));
+    }
+
+    Pack<T, VEC> acc;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc.v[i] = Num<T>::zero();
+
+    const T* xcol = X + col0;
+    for (int64_t done = 0; done < len; done += LANES, p += LANES) {
+        const int64_t mine = p + sub;
+        int32_t c = 0;
+        T v = Num<T>::zero();
+        if (mine < end) {
+            c = __ldg(indices + mine);
+            v = ldg(values + mine);
+            if (conj_a) v = conj_(v);
+        }
+        const int batch = int(min(int64_t(LANES), len - done));  // warp-uniform
+        for (int j0 = 0; j0 < batch; j0 += kU) {
+            Pack<T, VEC> x[kU];
+            T a[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int j = j0 + u;  // may run past LANES: shuffles wrap, the predicate masks it
+                const int32_t cj = __shfl_sync(kFull, c, j, LANES);
+                a[u] = shfl(kFull, v, j, LANES);
+                const bool live = col_ok && j < LANES && (p + j) < end;
+                if (live) {
+                    x[u] = load_pack<T, VEC>(xcol + int64_t(cj) * ldx);
+                } else {
+                    a[u] = Num<T>::zero();
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) x[u].v[i] = Num<T>::zero();
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc.v[i] = madd(a[u], x[u].v[i], acc.v[i]);
+        }
+    }
+
+    if (!(row_ok && col_ok)) return;
+    const int64_t off = (row0 + row) * ldy + col0;
+    Pack<T, VEC> y;
+    if (Num<T>::is_zero(beta)) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) y.v[i] = mul(alpha, acc.v[i]);
+    } else {
+        const Pack<T, VEC> old = *reinterpret_cast<const Pack<T, VEC>*>(y_self + off);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) y.v[i] = madd(alpha, acc.v[i], mul(beta, old.v[i]));
+    }
+    store_pack<T, VEC>(y_self + off, y);
+    if (n_peers > 1) {
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)  // static indices keep the pointers in the constant bank
+            if (q < n_peers && q != self) store_pack<T, VEC>(out.y[q] + off, y);
+    }
+}
+
+template <typename T, int VEC, int LANES>
+static sdb_status launch_rowmajor(cudaStream_t s, const CsrView& a, bool conj_a, const T* X, int64_t ldx, int64_t n,
+                                  T alpha, T beta, const PeerPanels<T>& out, int n_peers, int self, int64_t row0,
+                                  int64_t ldy) {
+    constexpr int kRowsPerCta = kSpmmWarps * (32 / LANES);
+    const int64_t gx = (a.rows + kRowsPerCta - 1) / kRowsPerCta;
+    const int64_t gy = (n + int64_t(LANES) * VEC - 1) / (int64_t(LANES) * VEC);
+    SDB_REQUIRE(gx < (int64_t(1) << 31) && gy < 65536, SDB_STATUS_NOT_SUPPORTED, "spmm: grid too large");
+    SDB_LAUNCH((spmm_rowmajor_kernel<T, VEC, LANES>), dim3(unsigned(gx), unsigned(gy)), kSpmmWarps * 32, 0, s, a.rows,
+               a.indptr, a.indices, static_cast<const T*>(a.values), conj_a, X, ldx, n, alpha, beta, out.y[self], out,
+               n_peers, self, row0, ldy);
+    return SDB_STATUS_SUCCESS;
+}
+
+template <typename T, int VEC>
+static sdb_status pick_lanes(cudaStream_t s, const CsrView& a, bool conj_a, const T* X, int64_t ldx, int64_t n,
+                             T alpha, T beta, const PeerPanels<T>& out, int n_peers, int self, int64_t row0,
+                             int64_t ldy) {
+    const int64_t packs = (n + VEC - 1) / VEC;
+#define SDB_GO(L) return launch_rowmajor<T, VEC, L>(s, a, conj_a, X, ldx, n, alpha, beta, out, n_peers, self, row0, ldy)
+    if (packs > 16) SDB_GO(32);
+    if (packs > 8) SDB_GO(16);
+    if (packs > 4) SDB_GO(8);
+    if (packs > 2) SDB_GO(4);
+    if (packs > 1) SDB_GO(2);
+    SDB_GO(1);
+#undef SDB_GO
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+static sdb_status spmm_rowmajor(cudaStream_t s, const CsrView& a, bool conj_a, const double* alpha_d,
+                                const double* beta_d, const void* dX, int64_t n, int64_t ldx, void* const* dY_peers,
+                                int n_peers, int self, int64_t row0, int64_t ldy) {
+    const T alpha = Num<T>::make(alpha_d[0], alpha_d[1]);
+    const T beta = Num<T>::make(beta_d[0], beta_d[1]);
+    PeerPanels<T> out;
+    bool vec_ok = aligned16(dX);
+    for (int q = 0; q < kMaxPeers; ++q) {
+        out.y[q] = q < n_peers ? static_cast<T*>(dY_peers[q]) : nullptr;
+        if (q < n_peers) vec_ok = vec_ok && aligned16(dY_peers[q]);
+    }
+    constexpr int kVec = 16 / int(sizeof(T));
+    vec_ok = vec_ok && (n % kVec == 0) && (ldx % kVec == 0) && (ldy % kVec == 0);
+    if (kVec > 1 && vec_ok)
+        return pick_lanes<T, kVec>(s, a, conj_a, static_cast<const T*>(dX), ldx, n, alpha, beta, out, n_peers, self,
+                                   row0, ldy);
+    return pick_lanes<T, 1>(s, a, conj_a, static_cast<const T*>(dX), ldx, n, alpha, beta, out, n_peers, self, row0,
+                            ldy);
+}
+
+// Y (m x n), X (k x n), both in `layout`.  Column-major panels are turned
+// row-major on the device (tiled transposes, coalesced both ways), run through
+// the same gather kernel and turned back: the gather wants X rows contiguous.
+sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a, const double* alpha,
+                       const double* beta, int layout, const void* dX, int64_t n, int64_t ldx,
+                       void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy) {
+    (void)ctx;
+    SDB_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && self >= 0 && self < n_peers, SDB_STATUS_INVALID_VALUE,
+                "spmm: bad peer configuration (%d peers, self %d)", n_peers, self);
+    if (a.rows == 0 || n == 0) return SDB_STATUS_SUCCESS;
+    if (layout == SDB_LAYOUT_ROW_MAJOR) {
+        SDB_REQUIRE(ldx >= n && ldy >= n, SDB_STATUS_INVALID_VALUE, "spmm: leading dimension smaller than n");
+        return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
+            return spmm_rowmajor<T>(s, a, conj_a, alpha, beta, dX, n, ldx, dY_peers, n_peers, self, row0, ldy);
+        });
+    }
+    SDB_REQUIRE(layout == SDB_LAYOUT_COL_MAJOR, SDB_STATUS_INVALID_VALUE, "spmm: bad layout %d", layout);
+    SDB_REQUIRE(n_peers == 1 && row0 == 0, SDB_STATUS_NOT_SUPPORTED, "spmm: peer panels must be row-major");
+    SDB_REQUIRE(ldx >= a.cols && ldy >= a.rows, SDB_STATUS_INVALID_VALUE,
+                "spmm: leading dimension smaller than the column length");
+    const int es = int(dtype_size(dtype));
+    const bool beta_zero = beta[0] == 0.0 && beta[1] == 0.0;
+    DevBuf xr, yr;
+    SDB_TRY(xr.alloc(size_t(a.cols) * size_t(n) * es, s));
+    SDB_TRY(yr.alloc(size_t(a.rows) * size_t(n) * es, s));
+    // X col-major (k x n, ld) is a row-major (n x k, ld) array: transpose it to (k x n, n)
+    SDB_TRY(transpose_dense(s, dX, ldx, xr.p, n, n, a.cols, es));
+    if (!beta_zero) SDB_TRY(transpose_dense(s, dY_peers[0], ldy, yr.p, n, n, a.rows, es));
+    void* yp[1] = {yr.p};
+    SDB_TRY(SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
+        return spmm_rowmajor<T>(s, a, conj_a, alpha, beta, xr.p, n, n, yp, 1, 0, 0, n);
+    }));
+    return transpose_dense(s, yr.p, n, dY_peers[0], ldy, a.rows, n, es);
+}
+
+}  // namespace sdb
+
+using namespace sdb;
+
+static sdb_status check_spmm_args(int op, const double* alpha, const sdb_mat* A, int layout, const void* X,
+                                  const double* beta, const void* Y) {
+    SDB_REQUIRE(A != nullptr, SDB_STATUS_NOT_INITIALIZED, "spmm: null handle");
+    SDB_REQUIRE(valid(A), SDB_STATUS_INVALID_VALUE, "spmm: not a live sdb_mat handle");
+    SDB_REQUIRE(op == SDB_OP_NON_TRANSPOSE || op == SDB_OP_TRANSPOSE || op == SDB_OP_CONJUGATE_TRANSPOSE,
+                SDB_STATUS_INVALID_VALUE, "spmm: bad operation %d", op);
+    SDB_REQUIRE(layout == SDB_LAYOUT_ROW_MAJOR || layout == SDB_LAYOUT_COL_MAJOR, SDB_STATUS_INVALID_VALUE,
+                "spmm: bad layout %d", layout);
+    SDB_REQUIRE(alpha && beta && X && Y, SDB_STATUS_INVALID_VALUE, "spmm: null argument");
+    return SDB_STATUS_SUCCESS;
+}
+
+extern "C" {
+
+sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, int layout, const void* dX, int64_t n,
+                        int64_t ldx, const double* beta, void* dY, int64_t ldy, void* stream) {
+    SDB_TRY(check_spmm_args(op, alpha, A, layout, dX, beta, dY));
+    SDB_REQUIRE(n >= 0, SDB_STATUS_INVALID_VALUE, "spmm: negative n");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    CsrView v;
+    SDB_TRY(csr_view(ctx, A, op != SDB_OP_NON_TRANSPOSE, &v));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    if (s != ctx->stream) {
+        // companions (transpose / expansion) are built on the library stream
+        SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    const bool conj_a = op == SDB_OP_CONJUGATE_TRANSPOSE;
+    void* yp[1] = {dY};
+    return spmm_device(ctx, s, v, A->dtype, conj_a, alpha, beta, layout, dX, n, ldx, yp, 1, 0, 0, ldy);
+}
+
+sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A, const void* dX, int64_t n, int64_t ldx,
+                                  const double* beta, void* const* dY_peers, int n_peers, int self, int64_t row0,
+                                  int64_t ldy, void* stream) {
+    SDB_REQUIRE(dY_peers != nullptr && n_peers >= 1 && n_peers <= kMaxPeers && self >= 0 && self < n_peers,
+                SDB_STATUS_INVALID_VALUE, "spmm_allgather: bad peer list");
+    SDB_TRY(check_spmm_args(SDB_OP_NON_TRANSPOSE, alpha, A, SDB_LAYOUT_ROW_MAJOR, dX, beta, dY_peers[self]));
+    for (int q = 0; q < n_peers; ++q)
+        SDB_REQUIRE(dY_peers[q] != nullptr, SDB_STATUS_INVALID_VALUE, "spmm_allgather: null peer panel %d", q);
+    SDB_REQUIRE(n >= 0 && row0 >= 0, SDB_STATUS_INVALID_VALUE, "spmm_allgather: negative size");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    CsrView v;
+    SDB_TRY(csr_view(ctx, A, false, &v));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    if (s != ctx->stream) SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return spmm_device(ctx, s, v, A->dtype, false, alpha, beta, SDB_LAYOUT_ROW_MAJOR, dX, n, ldx, dY_peers, n_peers,
+                       self, row0, ldy);
+}
+
+sdb_status sdb_spmm(int op, const double* alpha, const sdb_mat* A, int layout, const void* X, int64_t n, int64_t ldx,
+                    const double* beta, void* Y, int64_t ldy) {
+    SDB_TRY(check_spmm_args(op, alpha, A, layout, X, beta, Y));
+    SDB_REQUIRE(n >= 0, SDB_STATUS_INVALID_VALUE, "spmm: negative n");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    cudaStream_t s = ctx->stream;
+    PhaseTimer timer;
+    SDB_TRY(timer.init(s));
+    SDB_TRY(timer.mark(0));
+    CsrView v;
+    SDB_TRY(csr_view(ctx, A, op != SDB_OP_NON_TRANSPOSE, &v));
+    const size_t es = dtype_size(A->dtype);
+    const bool row_major = layout == SDB_LAYOUT_ROW_MAJOR;
+    const bool beta_zero = beta[0] == 0.0 && beta[1] == 0.0;
+    // host panels: `lines` contiguous runs of `run` elements, pitch ld
+    const int64_t x_lines = row_major ? v.cols : n, x_run = row_major ? n : v.cols;
+    const int64_t y_lines = row_major ? v.rows : n, y_run = row_major ? n : v.rows;
+    SDB_REQUIRE(ldx >= x_run && ldy >= y_run, SDB_STATUS_INVALID_VALUE, "spmm: leading dimension too small");
+    DevBuf dx, dy;
+    SDB_TRY(dx.alloc(size_t(x_lines) * size_t(x_run) * es, s));
+    SDB_TRY(dy.alloc(size_t(y_lines) * size_t(y_run) * es, s));
+    SDB_TRY(h2d_2d(ctx, dx.p, size_t(x_run) * es, X, size_t(ldx) * es, size_t(x_run) * es, size_t(x_lines)));
+    if (!beta_zero)
+        SDB_TRY(h2d_2d(ctx, dy.p, size_t(y_run) * es, Y, size_t(ldy) * es, size_t(y_run) * es, size_t(y_lines)));
+    SDB_TRY(timer.mark(1));
+    void* yp[1] = {dy.p};
+    SDB_TRY(spmm_device(ctx, s, v, A->dtype, op == SDB_OP_CONJUGATE_TRANSPOSE, alpha, beta, layout, dx.p, n, x_run,
+                        yp, 1, 0, 0, y_run));
+    SDB_TRY(timer.mark(2));
+    SDB_TRY(d2h_2d(ctx, Y, size_t(ldy) * es, dy.p, size_t(y_run) * es, size_t(y_run) * es, size_t(y_lines)));
+    SDB_TRY(timer.mark(3));
+    SDB_CUDA(cudaStreamSynchronize(s));
+    timer.finish(ctx);
+    return SDB_STATUS_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+"""
+Row-sharded SpMM across the GPUs of one node (BASELINE configs[4]).
+
+One process per GPU.  Rank r owns a contiguous block of rows of A (and of Y);
+X is replicated; Y = A @ X needs no reduction, only an all-gather of the dense
+output panel so that every GPU ends up with all of Y.  Three exchange modes:
+
+  fused  the SpMM epilogue stores each finished row once into EVERY rank's full
+         panel through NVLink peer mappings (sdb_spmm_dev_allgather): transfer
+         overlaps the gathers, Y is never re-read.  Peer pointers come from
+         CUDA IPC tokens exchanged over torch.distributed.
+  nccl   kernel into the local block, then ncclAllGather (all_gather_into_tensor)
+         — the baseline the fused kernel is compared with.
+  none   no exchange (independent shards).
+
+torch is used here for the process group only (rendezvous, token exchange, the
+NCCL baseline); memory and kernels are libsdb200's.  The reference has no
+multi-device path at all — this is new surface.
+"""
+import ctypes as _ct
+
+import numpy as np
+
+from . import _handles as _h
+from . import _lib
+from ._lib import SDB, check, scalar_pair
+
+
+def partition_rows(indptr, parts):
+    """nnz-balanced contiguous row blocks: bounds[0]=0 <= ... <= bounds[parts]=rows
+    (host code in the library: sdb_partition_rows)."""
+    indptr = np.ascontiguousarray(indptr)
+    if indptr.dtype not in (np.dtype(np.int32), np.dtype(np.int64)):
+        indptr = indptr.astype(np.int64)
+    bounds = (_ct.c_int64 * (parts + 1))()
+    check(
+        SDB.lib.sdb_partition_rows(indptr.ctypes.data_as(_ct.c_void_p), indptr.itemsize * 8,
+                                   indptr.shape[0] - 1, parts, bounds),
+        "sdb_partition_rows",
+    )
+    return np.array(bounds[:], dtype=np.int64)
+
+
+def row_block(a_csr, lo, hi):
+    """Rows [lo, hi) of a CSR matrix as a CSR matrix with rebased offsets (views
+    of the index/value arrays, a fresh indptr)."""
+    import scipy.sparse as sps
+
+    s, e = int(a_csr.indptr[lo]), int(a_csr.indptr[hi])
+    indptr = (a_csr.indptr[lo:hi + 1] - a_csr.indptr[lo]).astype(a_csr.indptr.dtype, copy=False)
+    return sps.csr_matrix((a_csr.data[s:e], a_csr.indices[s:e], indptr), shape=(hi - lo, a_csr.shape[1]))
+
+
+class _DevBuf:
+    def __init__(self, nbytes):
+        self.ptr = _ct.c_void_p()
+        self.nbytes = int(nbytes)
+        check(SDB.lib.sdb_dev_alloc(_ct.byref(self.ptr), self.nbytes), "sdb_dev_alloc")
+
+    def free(self):
+        if self.ptr:
+            check(SDB.lib.sdb_dev_free(self.ptr), "sdb_dev_free")
+            self.ptr = _ct.c_void_p()
+
+    def at(self, byte_offset):
+        return _ct.c_void_p(self.ptr.value + int(byte_offset))
+
+
+class _CudaView:
+    """__cuda_array_interface__ over a raw device pointer (so torch can wrap the
+    panel for the NCCL baseline without copying)."""
+
+    def __init__(self, ptr, shape, dtype):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": np.dtype(dtype).str, "data": (int(ptr), False), "version": 3,
+            "strides": None,
+        }
+
+
+class RowShardedSpMM:
+    """Y_panel[row0 : row0 + rows_local, :] = alpha * A_local @ X + beta * (same rows),
+    with the panel replicated on every rank according to ``allgather``."""
+
+    def __init__(self, a_local, n_dense, world_size=1, rank=0, allgather="fused", group=None):
+        if allgather not in ("fused", "nccl", "none"):
+            raise ValueError("allgather must be 'fused', 'nccl' or 'none'")
+        self.world, self.rank, self.group = int(world_size), int(rank), group
+        self.mode = allgather if self.world > 1 else "none"
+        self.n = int(n_dense)
+        self.dtype = np.dtype(a_local.dtype)
+        self.es = self.dtype.itemsize
+        self.rows_local, self.cols = a_local.shape
+        self.handle, _, _ = _h.create(a_local)
+        self._peers_opened = []
+        # every rank's block position inside the global panel
+        counts = self._all_gather_obj(self.rows_local)
+        self.row_counts = [int(c) for c in counts]
+        self.row0 = int(sum(self.row_counts[: self.rank]))
+        self.rows_total = int(sum(self.row_counts))
+        panel_rows = self.rows_total if self.mode != "none" else self.rows_local
+        self.panel_row0 = self.row0 if self.mode != "none" else 0
+        self.x = _DevBuf(self.cols * self.n * self.es)
+        self.panel = _DevBuf(panel_rows * self.n * self.es)
+        self.panel_rows = panel_rows
+        self.peer_ptrs = [self.panel.ptr.value]
+        if self.mode == "fused":
+            token = _ct.create_string_buffer(64)
+            check(SDB.lib.sdb_ipc_export(self.panel.ptr, token), "sdb_ipc_export")
+            tokens = self._all_gather_obj(token.raw)
+            self.peer_ptrs = []
+            for q, tok in enumerate(tokens):
+                if q == self.rank:
+                    self.peer_ptrs.append(self.panel.ptr.value)
+                    continue
+                p = _ct.c_void_p()
+                check(SDB.lib.sdb_ipc_open(_ct.create_string_buffer(tok, 64), _ct.byref(p)), "sdb_ipc_open")
+                self._peers_opened.append(p)
+                self.peer_ptrs.append(p.value)
+        self._torch_panel = None
+        if self.mode == "nccl":
+            if len(set(self.row_counts)) != 1:
+                raise ValueError("allgather='nccl' needs equal row counts per rank (ncclAllGather)")
+            import torch
+
+            self._torch_panel = torch.as_tensor(
+                _CudaView(self.panel.ptr.value, (self.panel_rows, self.n), self.dtype), device="cuda")
+
+    # ------------------------------------------------------------------ plumbing
+    def _all_gather_obj(self, obj):
+        if self.world == 1:
+            return [obj]
+        import torch.distributed as dist
+
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def set_x(self, x_host):
+        x_host = np.ascontiguousarray(x_host, dtype=self.dtype)
+        if x_host.shape != (self.cols, self.n):
+            raise ValueError(f"X must be {(self.cols, self.n)}, got {x_host.shape}")
+        check(SDB.lib.sdb_memcpy(self.x.ptr, x_host.ctypes.data_as(_ct.c_void_p), x_host.nbytes, 1), "sdb_memcpy")
+
+    def _local_ptr(self):
+        return self.panel.at(self.panel_row0 * self.n * self.es)
+
+    def set_local_y(self, y_host):
+        y_host = np.ascontiguousarray(y_host, dtype=self.dtype)
+        if y_host.shape != (self.rows_local, self.n):
+            raise ValueError(f"local Y must be {(self.rows_local, self.n)}, got {y_host.shape}")
+        check(SDB.lib.sdb_memcpy(self._local_ptr(), y_host.ctypes.data_as(_ct.c_void_p), y_host.nbytes, 1),
+              "sdb_memcpy")
+
+    # ------------------------------------------------------------------ compute
+    def run(self, alpha=1.0, beta=0.0, stream_ptr=None):
+        """One sharded SpMM step, stream-ordered on ``stream_ptr`` (a cudaStream_t
+        as int; None = the library's stream).  Does not synchronise."""
+        stream = _ct.c_void_p(stream_ptr) if stream_ptr else None
+        a, b = scalar_pair(alpha), scalar_pair(beta)
+        if self.mode == "fused":
+            ptrs = (_ct.c_void_p * self.world)(*self.peer_ptrs)
+            check(
+                SDB.lib.sdb_spmm_dev_allgather(a, self.handle.ref, self.x.ptr, self.n, self.n, b, ptrs, self.world,
+                                               self.rank, self.row0, self.n, stream),
+                "sdb_spmm_dev_allgather",
+            )
+            return
+        check(
+            SDB.lib.sdb_spmm_dev(_lib.OP_N, a, self.handle.ref, _lib.LAYOUT_C, self.x.ptr, self.n, self.n, b,
+                                 self._local_ptr(), self.n, stream),
+            "sdb_spmm_dev",
+        )
+        if self.mode == "nccl":
+            import torch.distributed as dist
+
+            if stream is None:  # NCCL orders after torch's current stream, not the library's
+                check(SDB.lib.sdb_device_synchronize(), "sdb_device_synchronize")
+            local = self._torch_panel[self.row0:self.row0 + self.rows_local]
+            dist.all_gather_into_tensor(self._torch_panel, local, group=self.group)
+
+    def synchronize(self):
+        check(SDB.lib.sdb_device_synchronize(), "sdb_device_synchronize")
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)
+
+    # ------------------------------------------------------------------ results
+    def read_rows(self, first, count):
+        """Rows [first, first+count) of this rank's copy of the panel -> numpy."""
+        out = np.empty((count, self.n), dtype=self.dtype)
+        check(SDB.lib.sdb_memcpy(out.ctypes.data_as(_ct.c_void_p), self.panel.at(first * self.n * self.es),
+                                 out.nbytes, 2), "sdb_memcpy")
+        return out
+
+    def read_panel(self):
+        return self.read_rows(0, self.panel_rows)
+
+    def close(self):
+        for p in self._peers_opened:
+            SDB.lib.sdb_ipc_close(p)
+        if self._peers_opened and self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)  # every peer has unmapped before any owner frees
+        self._peers_opened = []
+        self._torch_panel = None
+        self.x.free()
+        self.panel.free()
+        if self.handle:
+            self.handle.destroy()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+def spmm_sharded(a_csr, x, world_size, rank, allgather="fused", group=None, out=None, out_scalar=None):
+    """Convenience wrapper: every rank passes the SAME global CSR matrix and X;
+    rows are split nnz-balanced, each rank computes its block and the full
+    product comes back on every rank (``allgather`` != 'none') as a numpy array."""
+    bounds = partition_rows(a_csr.indptr, world_size)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    with RowShardedSpMM(row_block(a_csr, lo, hi), x.shape[1], world_size, rank, allgather, group) as plan:
+        plan.set_x(x)
+        beta = 0.0
+        if out is not None:
+            plan.set_local_y(out[lo:hi])
+            beta = 1.0 if out_scalar is None else out_scalar
+        plan.run(alpha=1.0, beta=beta)
+        plan.synchronize()
+        result = plan.read_panel()
+    return result

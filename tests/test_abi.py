@@ -1,0 +1,88 @@
+"""
+The C-ABI boundary without a GPU: libsdb200.so loads, exports every symbol that
+include/sdb200.h declares, the ctypes table covers exactly that set, host-only
+entry points work, and compute entry points fail LOUDLY (status != 0 ->
+ValueError) instead of falling back to the CPU.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import sparse_dot_b200 as sdb
+from sparse_dot_b200 import _handles, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sdb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    names = declared_symbols()
+    assert len(names) >= 30
+    lib = ctypes.CDLL(_lib.library_path())
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in sdb200.h but not exported"
+    assert sorted(_lib.PROTOTYPES) == names, "ctypes table and header disagree"
+
+
+def test_no_oracle_or_cpu_fallback_in_product():
+    pkg = os.path.join(ROOT, "sparse_dot_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+                assert "import torch" not in src or f in ("sharded.py",), f"{f} imports torch"
+
+
+def test_version_string_and_status_names():
+    s = sdb.get_version_string()
+    assert "libsdb200" in s and "sm_100a" in s
+    assert _lib.STATUS_NAMES[4] == "SPARSE_STATUS_EXECUTION_FAILED"
+
+
+def test_null_handles_are_value_errors():
+    with pytest.raises(ValueError, match="sdb_destroy returned 1"):
+        _handles.Handle(ctypes.c_void_p(), np.float64).destroy()
+    with pytest.raises(ValueError, match="sdb_order returned 1"):
+        _handles.order(_handles.Handle(ctypes.c_void_p(), np.float64))
+
+
+def test_partition_rows_balances_nnz():
+    rng = np.random.default_rng(0)
+    lens = rng.integers(0, 50, size=10_000)
+    for it in (np.int32, np.int64):
+        indptr = np.concatenate([[0], np.cumsum(lens)]).astype(it)
+        for parts in (1, 2, 3, 8):
+            bounds = (ctypes.c_int64 * (parts + 1))()
+            st = _lib.SDB.lib.sdb_partition_rows(indptr.ctypes.data_as(ctypes.c_void_p), indptr.itemsize * 8,
+                                                 len(lens), parts, bounds)
+            assert st == 0
+            b = np.array(bounds[:])
+            assert b[0] == 0 and b[-1] == len(lens) and np.all(np.diff(b) >= 0)
+            per = np.diff(indptr[b])
+            assert per.sum() == indptr[-1]
+            assert per.max() - per.min() <= 2 * lens.max()
+    empty = np.zeros(11, dtype=np.int64)
+    bounds = (ctypes.c_int64 * 5)()
+    assert _lib.SDB.lib.sdb_partition_rows(empty.ctypes.data_as(ctypes.c_void_p), 64, 10, 4, bounds) == 0
+    assert list(bounds) == [0, 2, 5, 7, 10]
+    assert _lib.SDB.lib.sdb_partition_rows(None, 64, 10, 4, bounds) == 3
+
+
+@pytest.mark.skipif(sdb.device_count() > 0, reason="only meaningful without a GPU")
+def test_compute_fails_loudly_without_gpu():
+    a = sp.random(20, 30, density=0.2, format="csr", dtype=np.float64, random_state=0)
+    b = np.ones((30, 4))
+    with pytest.raises(ValueError, match="SPARSE_STATUS_EXECUTION_FAILED"):
+        sdb.dot_product_mkl(a, b)
+    with pytest.raises(ValueError):
+        sdb.gram_matrix_mkl(a)
