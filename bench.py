@@ -256,10 +256,11 @@ def run_ours(args):
                                   group=dist.group.WORLD if world > 1 else None)
     plan.set_x(x)
     plan.set_local_y(y0)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-default) stream: kernels, events and NCCL all order on it
 
     def step():
-        plan.run(alpha=1.0, beta=BETA, stream_ptr=stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            plan.run(alpha=1.0, beta=BETA, stream_ptr=stream.cuda_stream)
 
     def sync_all():
         torch.cuda.synchronize()

@@ -68,6 +68,8 @@ def sparse_times_dense(a_sparse, b_dense, scalar=1.0, transpose=False, out=None,
 
 def dot_sparse_dense(a, b, cast=False, scalar=1.0, out=None, out_scalar=None):
     """One sparse and one dense operand, either side."""
+    if not _v.is_supported_sparse(a) or not _v.is_supported_sparse(b):
+        raise ValueError("Only CSR, CSC, and BSR-type sparse matrices are supported; COO is not")
     _v.check_shapes(a, b)
     if _v.product_is_empty(a, b):
         _v.debug_print("Skipping multiplication because A (dot) B must yield empty matrix")
@@ -77,8 +79,6 @@ def dot_sparse_dense(a, b, cast=False, scalar=1.0, out=None, out_scalar=None):
     n_sparse = int(sps.issparse(a)) + int(sps.issparse(b))
     if n_sparse != 1:
         raise ValueError("_sparse_dot_dense takes one sparse and one dense array")
-    if not _v.is_supported_sparse(a) or not _v.is_supported_sparse(b):
-        raise ValueError("Only CSR, CSC, and BSR-type sparse matrices are supported")
     if sps.issparse(a):
         return sparse_times_dense(a, b, scalar=scalar, out=out, out_scalar=out_scalar)
     # dense @ sparse = (sparse^T @ dense^T)^T, all as views
@@ -111,10 +111,10 @@ def sparse_times_vector(a_sparse, vec, scalar=1.0, transpose=False, out=None, ou
 
 
 def dot_sparse_vector(a, b, cast=False, scalar=1.0, out=None, out_scalar=None):
-    _v.check_shapes(a, b, allow_vector=True)
-    a, b = _v.unify_dtypes(a, b, cast=cast)
     if not _v.is_supported_sparse(a) or not _v.is_supported_sparse(b):
         raise ValueError("Only CSR, CSC, and BSR-type sparse matrices are supported")
+    _v.check_shapes(a, b, allow_vector=True)
+    a, b = _v.unify_dtypes(a, b, cast=cast)
     if _v.is_dense_vector(b):
         return sparse_times_vector(a, b, scalar=scalar, out=out, out_scalar=out_scalar)
     if _v.is_dense_vector(a):

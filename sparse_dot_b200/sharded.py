@@ -51,6 +51,33 @@ def row_block(a_csr, lo, hi):
     return sps.csr_matrix((a_csr.data[s:e], a_csr.indices[s:e], indptr), shape=(hi - lo, a_csr.shape[1]))
 
 
+def _all_gather_obj(obj, world, group):
+    if world == 1:
+        return [obj]
+    import torch.distributed as dist
+
+    out = [None] * world
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+class ShardLayout:
+    """Where this rank's row block sits in the global output panel (pure host
+    logic; one all-gather of the local row counts)."""
+
+    def __init__(self, rows_local, world_size=1, rank=0, group=None):
+        self.world, self.rank, self.group = int(world_size), int(rank), group
+        self.rows_local = int(rows_local)
+        self.row_counts = [int(c) for c in _all_gather_obj(self.rows_local, self.world, group)]
+        self.row0 = int(sum(self.row_counts[: self.rank]))
+        self.rows_total = int(sum(self.row_counts))
+        self.uniform = len(set(self.row_counts)) == 1
+
+    def block(self, q):
+        """(first row, row count) of rank q's block."""
+        return int(sum(self.row_counts[:q])), self.row_counts[q]
+
+
 class _DevBuf:
     def __init__(self, nbytes):
         self.ptr = _ct.c_void_p()
@@ -93,10 +120,10 @@ class RowShardedSpMM:
         self.handle, _, _ = _h.create(a_local)
         self._peers_opened = []
         # every rank's block position inside the global panel
-        counts = self._all_gather_obj(self.rows_local)
-        self.row_counts = [int(c) for c in counts]
-        self.row0 = int(sum(self.row_counts[: self.rank]))
-        self.rows_total = int(sum(self.row_counts))
+        self.layout = ShardLayout(self.rows_local, self.world, self.rank, group)
+        self.row_counts = self.layout.row_counts
+        self.row0 = self.layout.row0
+        self.rows_total = self.layout.rows_total
         panel_rows = self.rows_total if self.mode != "none" else self.rows_local
         self.panel_row0 = self.row0 if self.mode != "none" else 0
         self.x = _DevBuf(self.cols * self.n * self.es)
@@ -118,7 +145,7 @@ class RowShardedSpMM:
                 self.peer_ptrs.append(p.value)
         self._torch_panel = None
         if self.mode == "nccl":
-            if len(set(self.row_counts)) != 1:
+            if not self.layout.uniform:
                 raise ValueError("allgather='nccl' needs equal row counts per rank (ncclAllGather)")
             import torch
 
@@ -127,13 +154,7 @@ class RowShardedSpMM:
 
     # ------------------------------------------------------------------ plumbing
     def _all_gather_obj(self, obj):
-        if self.world == 1:
-            return [obj]
-        import torch.distributed as dist
-
-        out = [None] * self.world
-        dist.all_gather_object(out, obj, group=self.group)
-        return out
+        return _all_gather_obj(obj, self.world, self.group)
 
     def set_x(self, x_host):
         x_host = np.ascontiguousarray(x_host, dtype=self.dtype)

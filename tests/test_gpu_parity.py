@@ -32,15 +32,15 @@ def _pair(dtype):
     return m1.astype(dtype), m2.astype(dtype)
 
 
-def _close(got, a, b, dtype, want=None):
-    """got ~= a @ b within the dtype's tolerance, relative to |a| @ |b|."""
+def _close(got, a, b, dtype, want=None, offset=0.0):
+    """got ~= a @ b (+ offset) within the dtype's tolerance, relative to |a| @ |b| (+ |offset|)."""
     a64 = a.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64)
     b64 = b.astype(a64.dtype)
     if want is None:
         want = a64 @ b64
-    want = want.toarray() if sp.issparse(want) else np.asarray(want)
+    want = (want.toarray() if sp.issparse(want) else np.asarray(want)) + offset
     bound = abs(a64) @ abs(b64)
-    bound = bound.toarray() if sp.issparse(bound) else np.asarray(bound)
+    bound = (bound.toarray() if sp.issparse(bound) else np.asarray(bound)) + abs(offset)
     got = got.toarray() if sp.issparse(got) else np.asarray(got)
     assert got.shape == want.shape
     err = cs.rel_err(got, want, bound)
@@ -171,16 +171,16 @@ def test_sparse_dense_out_and_scalar(dtype, order):
     out = np.ones((200, 100), dtype=dtype, order=order)
     got = sdb.dot_product_mkl(m1, b, out=out, out_scalar=3.0)
     assert got is out
-    _close(got - 3.0, m1, b, dtype, want=want)
+    _close(got, m1, b, dtype, want=want, offset=3.0)
     out = np.ones((200, 100), dtype=dtype, order=order)
     got = sdb.dot_product_mkl(m1, b, out=out)  # beta defaults to 1
-    _close(got - 1.0, m1, b, dtype, want=want)
+    _close(got, m1, b, dtype, want=want, offset=1.0)
     # dense @ sparse with out
     d1 = np.asarray(m1.toarray(), order=order)
     out = np.ones((200, 100), dtype=dtype, order=order)
     got = sdb.dot_product_mkl(d1, m2, out=out, out_scalar=0.5)
     assert got is out
-    _close(got - 0.5, d1, m2, dtype, want=want)
+    _close(got, d1, m2, dtype, want=want, offset=0.5)
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 7, 8, 31, 33, 64, 100, 128, 130, 256, 300])
@@ -290,7 +290,7 @@ def test_sparse_vector(dtype, fmt):
     out = np.ones(200, dtype=dtype)
     got = sdb.dot_product_mkl(a, v, out=out, out_scalar=2.0)
     assert got is out
-    _close((got - 2.0).reshape(-1, 1), m1, v.reshape(-1, 1), dtype)
+    _close(got.reshape(-1, 1), m1, v.reshape(-1, 1), dtype, offset=2.0)
 
 
 # =============================================================== sparse x sparse
