@@ -320,8 +320,9 @@ def run_ours(args):
             "h2d_bytes_per_step": int(a.data.nbytes + a.indices.nbytes + a.indptr.nbytes + x.nbytes + y0.nbytes),
             "d2h_bytes_per_step": int(y0.nbytes),
             "host_memory": "pinned (sdb_host_alloc)",
-            "device_phase_ms": {"h2d": phases[0], "kernels": phases[1], "d2h": phases[2]},
-            "api": "sparse_dot_b200.dot_product_mkl(csr, ndarray, out=, out_scalar=) -> sdb_create_csr + sdb_spmm",
+            "device_spans_ms": {"start_to_last_upload": phases[0], "kernel_sum": phases[1], "whole_call": phases[2]},
+            "api": "sparse_dot_b200.dot_product_mkl(csr, ndarray, out=, out_scalar=) -> sdb_spmm_csr_host "
+                   "(3-stream row-chunk pipeline: upload / kernel / download overlap)",
         }
 
     if rank != 0:

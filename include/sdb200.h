@@ -134,6 +134,19 @@ SDB_API sdb_status sdb_spmm(int op, const double* alpha, const sdb_mat* A, int l
                             const void* X, int64_t n, int64_t ldx,
                             const double* beta, void* Y, int64_t ldy);
 
+/* The reference's create -> mm -> destroy triple (_sparse_dense.py:34-132) as
+ * ONE call for the common case op = N, A CSR, X / Y row-major: all arrays are
+ * HOST pointers.  With page-locked buffers (sdb_host_alloc or any
+ * cudaHostAlloc'ed memory) the uploads, the kernels and the download run as a
+ * row-chunk pipeline on three streams; otherwise it is exactly
+ * sdb_create_csr + sdb_spmm + sdb_destroy.  After a pipelined call
+ * sdb_last_timing reports overlapping spans: [0] start -> last upload landed,
+ * [1] sum of kernel times, [2] the whole call. */
+SDB_API sdb_status sdb_spmm_csr_host(int64_t rows, int64_t cols, const void* indptr, const void* indices,
+                                     int index_bits, const void* values, int dtype, const double* alpha,
+                                     const void* X, int64_t n, int64_t ldx, const double* beta, void* Y,
+                                     int64_t ldy);
+
 /* Same operation on DEVICE pointers, stream-ordered on `stream` (a
  * cudaStream_t passed as void*; NULL = the library's own stream). */
 SDB_API sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, int layout,

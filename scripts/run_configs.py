@@ -1,0 +1,245 @@
+#!/usr/bin/env python
+"""
+run_configs.py — the BASELINE.json parity-test configurations at (or near) full
+size on one B200, each timed on the device and checked with size-independent
+properties (linearity checksums, sampled entries, triangle rules) plus a full
+oracle comparison where the CPU can finish in seconds.  Not a bench line: the
+output (one JSON object per config) feeds DESIGN.md / profiles.
+
+    python scripts/run_configs.py [c1] [c3] [c4] [c5bsr] [--scale 22 --ef 1]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import sparse_dot_b200 as sdb  # noqa: E402
+from sparse_dot_b200 import _handles as H  # noqa: E402
+from sparse_dot_b200 import _lib  # noqa: E402
+from tests import _cases as cs  # noqa: E402
+
+lib = _lib.SDB.lib
+
+
+def sync():
+    _lib.check(lib.sdb_device_synchronize(), "sync")
+
+
+def timed(fn, reps=1):
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = fn()
+    sync()
+    return (time.perf_counter() - t0) / reps * 1e3, out
+
+
+def run_c1():
+    """configs[0]: CSR 10k x 10k d=1e-3 fp64 x dense 10k x 64."""
+    from oracle import oracle as orc
+
+    a = sp.random(10_000, 10_000, density=1e-3, format="csr", dtype=np.float64, random_state=86)
+    x = np.random.default_rng(88).random((10_000, 64))
+    ms, y = timed(lambda: sdb.dot_product_mkl(a, x), reps=5)
+    want = orc.c_spmm(a, x)
+    t0 = time.perf_counter()
+    orc.c_spmm(a, x)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    return {"config": "c1", "e2e_ms": ms, "oracle_cpu_ms": cpu_ms, "max_rel_err": cs.rel_err(y, want),
+            "kernel_ms": sdb.last_timing_ms()[1]}
+
+
+def run_c3(scale, ef, full_check):
+    """configs[2]: CSR x CSR SpGEMM, two R-MAT fp32 matrices, reorder_output=True."""
+    a = cs.rmat_csr(scale, ef, np.float32, seed=1)
+    b = cs.rmat_csr(scale, ef, np.float32, seed=2)
+    res = {"config": "c3", "scale": scale, "edge_factor": ef, "nnz_a": int(a.nnz), "nnz_b": int(b.nnz),
+           "max_row_a": int(np.diff(a.indptr).max())}
+    products = int(np.dot(np.bincount(a.indices, minlength=a.shape[1]).astype(np.int64),
+                          np.diff(b.indptr).astype(np.int64)))
+    res["products"] = products
+    ha, _, _ = H.create(a)
+    hb, _, _ = H.create(b)
+    with ha, hb:
+        def mult():
+            ref = C.c_void_p()
+            _lib.check(lib.sdb_spgemm(_lib.OP_N, ha.ref, hb.ref, C.byref(ref)), "sdb_spgemm")
+            return H.Handle(ref, np.float32)
+
+        ms, hc = timed(mult)
+        with hc:
+            res["spgemm_ms"] = ms
+            ms2, _ = timed(lambda: H.order(hc))
+            res["order_ms"] = ms2
+            info = H.info(hc)
+            res["nnz_c"] = int(info["nnz"])
+            res["compression"] = products / max(1, info["nnz"])
+            res["gbytes_model"] = (a.nnz * 8 + products * (8 + 4) + info["nnz"] * 8) / 1e9
+            # checksum of checksums: 1^T (A B) 1 = sum_k colsum_A(k) * rowsum_B(k)
+            t0 = time.perf_counter()
+            c = H.export(hc)
+            res["export_ms"] = (time.perf_counter() - t0) * 1e3
+            colsum_a = np.bincount(a.indices, weights=a.data.astype(np.float64), minlength=a.shape[1])
+            rowsum_b = np.asarray(b.astype(np.float64).sum(axis=1)).ravel()
+            want_total = float(np.dot(colsum_a, rowsum_b))
+            got_total = float(c.data.astype(np.float64).sum())
+            res["total_rel_err"] = abs(got_total - want_total) / want_total
+            # per-row linearity: C 1 = A (B 1)
+            rows_c = np.asarray(c.astype(np.float64).sum(axis=1)).ravel()
+            want_rows = a.astype(np.float64) @ rowsum_b
+            res["rowsum_max_rel_err"] = float(np.max(np.abs(rows_c - want_rows) / np.maximum(want_rows, 1e-300)))
+            srt = True
+            idx = c.indices
+            ptr = c.indptr
+            # sortedness: a decrease may only happen at a row boundary
+            dec = np.flatnonzero(np.diff(idx.astype(np.int64)) < 0) + 1
+            srt = bool(np.all(np.isin(dec, ptr)))
+            res["sorted"] = srt
+            if full_check:
+                t0 = time.perf_counter()
+                want = (a @ b).tocsr()
+                want.sort_indices()
+                res["scipy_ms"] = (time.perf_counter() - t0) * 1e3
+                res["indptr_equal"] = bool(np.array_equal(c.indptr, want.indptr))
+                res["indices_equal"] = bool(np.array_equal(c.indices, want.indices))
+                res["values_max_rel_err"] = float(np.max(np.abs(c.data - want.data) / np.abs(want.data)))
+    return res
+
+
+def run_c4(m, n, per_row):
+    """configs[3]: gram_matrix_mkl A^T A, CSR(m x n, per_row nnz/row, fp32), dense upper-triangular output,
+    device-resident (the 40 GB result stays in HBM; sampled rows come back for the checks)."""
+    a = cs.uniform_rows_csr(m, n, per_row, np.float32, seed=4)
+    res = {"config": "c4", "m": m, "n": n, "nnz": int(a.nnz)}
+    ha, _, _ = H.create(a)
+    with ha:
+        d_c = C.c_void_p()
+        _lib.check(lib.sdb_dev_alloc(C.byref(d_c), n * n * 4), "sdb_dev_alloc")
+        one, zero = _lib.scalar_pair(1.0), _lib.scalar_pair(0.0)
+        try:
+            # first call builds the transposed companion; time it separately
+            ms0, _ = timed(lambda: _lib.check(
+                lib.sdb_syrkd_dev(_lib.OP_T, ha.ref, one, zero, d_c, _lib.LAYOUT_C, n, None), "sdb_syrkd_dev"))
+            ms, _ = timed(lambda: _lib.check(
+                lib.sdb_syrkd_dev(_lib.OP_T, ha.ref, one, zero, d_c, _lib.LAYOUT_C, n, None), "sdb_syrkd_dev"))
+            res["first_call_ms"] = ms0
+            res["syrkd_ms"] = ms
+            macs = float(per_row * (per_row + 1) / 2 * m)
+            res["gflops"] = 2 * macs / (ms * 1e-3) / 1e9
+            res["out_gbytes_upper"] = n * (n + 1) / 2 * 4 / 1e9
+            # sampled rows: recompute C[i, i:] = A[:, i]^T A[:, i:] on the host
+            csc = a.tocsc()
+            rng = np.random.default_rng(0)
+            worst = 0.0
+            for i in rng.choice(n, size=6, replace=False):
+                row = np.empty(n, dtype=np.float32)
+                _lib.check(lib.sdb_memcpy(row.ctypes.data_as(C.c_void_p), C.c_void_p(d_c.value + int(i) * n * 4),
+                                          n * 4, 2), "sdb_memcpy")
+                col_i = csc[:, [int(i)]].astype(np.float64)
+                want = np.asarray((a.astype(np.float64).T @ col_i).todense()).ravel()
+                up = slice(int(i), n)
+                worst = max(worst, float(np.max(np.abs(row[up] - want[up]) / np.maximum(want[up], 1e-30)
+                                                * (want[up] > 0))))
+                assert np.all(row[up][want[up] == 0] == 0)
+            res["sampled_rows_max_rel_err"] = worst
+            # trace = ||A||_F^2 (linearity): read the diagonal with a strided copy
+            diag = np.empty(n, dtype=np.float32)
+            rowbuf = np.empty(n, dtype=np.float32)
+            step = max(1, n // 512)
+            tr_got = tr_want = 0.0
+            sq = np.bincount(a.indices, weights=a.data.astype(np.float64) ** 2, minlength=n)
+            for i in range(0, n, step):
+                _lib.check(lib.sdb_memcpy(rowbuf.ctypes.data_as(C.c_void_p),
+                                          C.c_void_p(d_c.value + (i * n + i) * 4), 4, 2), "sdb_memcpy")
+                tr_got += float(rowbuf[0])
+                tr_want += float(sq[i])
+            res["diag_sample_rel_err"] = abs(tr_got - tr_want) / tr_want
+        finally:
+            lib.sdb_dev_free(d_c)
+    return res
+
+
+def run_c5bsr(block_rows, blocks_per_row, b, n):
+    """configs[4] BSR variant on 1 GPU: natively blocked matrix, dense b x b fp32 blocks, x dense (k x n)."""
+    rng = np.random.default_rng(5)
+    cols = np.sort(np.stack([rng.choice(block_rows, size=blocks_per_row, replace=False)
+                             for _ in range(min(block_rows, 4096))]), axis=1)
+    reps = (block_rows + cols.shape[0] - 1) // cols.shape[0]
+    cols = np.tile(cols, (reps, 1))[:block_rows]
+    cols = (cols + np.arange(block_rows)[:, None] * 7919) % block_rows
+    cols.sort(axis=1)
+    indptr = np.arange(0, block_rows * blocks_per_row + 1, blocks_per_row, dtype=np.int32)
+    data = (rng.random((block_rows * blocks_per_row, b, b), dtype=np.float32) + 0.5)
+    a = sp.bsr_matrix((data, cols.ravel().astype(np.int32), indptr), shape=(block_rows * b, block_rows * b))
+    x = rng.random((block_rows * b, n), dtype=np.float32)
+    res = {"config": "c5bsr", "rows": block_rows * b, "nnz": int(data.size), "block": b, "n": n}
+    ha, _, _ = H.create(a)
+    with ha:
+        d_x, d_y = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.sdb_dev_alloc(C.byref(d_x), x.nbytes), "alloc")
+        _lib.check(lib.sdb_dev_alloc(C.byref(d_y), x.nbytes), "alloc")
+        try:
+            _lib.check(lib.sdb_memcpy(d_x, x.ctypes.data_as(C.c_void_p), x.nbytes, 1), "memcpy")
+            one, zero = _lib.scalar_pair(1.0), _lib.scalar_pair(0.0)
+            call = lambda: _lib.check(lib.sdb_spmm_dev(_lib.OP_N, one, ha.ref, _lib.LAYOUT_C, d_x, n, n, zero, d_y,
+                                                       n, None), "sdb_spmm_dev")
+            ms0, _ = timed(call)
+            ms, _ = timed(call, reps=5)
+            res["first_call_ms"] = ms0
+            res["spmm_ms"] = ms
+            g = data.size * 4 + cols.size * 4 + cols.size * b * n * 4 + block_rows * b * n * 4
+            res["gather_model_gbs"] = g / (ms * 1e-3) / 1e9
+            res["gflops"] = 2.0 * data.size * n / (ms * 1e-3) / 1e9
+            rows = np.sort(rng.choice(block_rows * b, size=16, replace=False))
+            worst = 0.0
+            csr_rows = a.tocsr()[rows].astype(np.float64)
+            want = csr_rows @ x.astype(np.float64)
+            for j, r in enumerate(rows):
+                got = np.empty(n, dtype=np.float32)
+                _lib.check(lib.sdb_memcpy(got.ctypes.data_as(C.c_void_p), C.c_void_p(d_y.value + int(r) * n * 4),
+                                          n * 4, 2), "memcpy")
+                worst = max(worst, float(np.max(np.abs(got - want[j]) / np.abs(want[j]))))
+            res["sampled_rows_max_rel_err"] = worst
+        finally:
+            lib.sdb_dev_free(d_x)
+            lib.sdb_dev_free(d_y)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", nargs="*", default=["c1", "c3", "c4", "c5bsr"])
+    ap.add_argument("--scale", type=int, default=20)
+    ap.add_argument("--ef", type=int, default=1)
+    ap.add_argument("--no-full-check", action="store_true")
+    ap.add_argument("--gram-m", type=int, default=2_000_000)
+    ap.add_argument("--gram-n", type=int, default=100_000)
+    ap.add_argument("--bsr-block-rows", type=int, default=62_500)
+    args = ap.parse_args()
+    print(sdb.get_version_string(), flush=True)
+    for w in args.which:
+        t0 = time.perf_counter()
+        if w == "c1":
+            r = run_c1()
+        elif w == "c3":
+            r = run_c3(args.scale, args.ef, not args.no_full_check)
+        elif w == "c4":
+            r = run_c4(args.gram_m, args.gram_n, 100)
+        elif w == "c5bsr":
+            r = run_c5bsr(args.bsr_block_rows, 4, 16, 256)
+        else:
+            raise SystemExit(f"unknown config {w}")
+        r["wall_s"] = time.perf_counter() - t0
+        print(json.dumps(r), flush=True)
+
+
+if __name__ == "__main__":
+    main()

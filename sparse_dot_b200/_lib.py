@@ -47,6 +47,7 @@ PROTOTYPES = {
     "sdb_order": (_i32, [_vp]),
     "sdb_convert_csr": (_i32, [_vp, _i32, _pvp]),
     "sdb_spmm": (_i32, [_i32, _pd, _vp, _i32, _vp, _i64, _i64, _pd, _vp, _i64]),
+    "sdb_spmm_csr_host": (_i32, [_i64, _i64, _vp, _vp, _i32, _vp, _i32, _pd, _vp, _i64, _i64, _pd, _vp, _i64]),
     "sdb_spmm_dev": (_i32, [_i32, _pd, _vp, _i32, _vp, _i64, _i64, _pd, _vp, _i64, _vp]),
     "sdb_spmm_dev_allgather": (_i32, [_pd, _vp, _vp, _i64, _i64, _pd, _pvp, _i32, _i32, _i64, _i64, _vp]),
     "sdb_spgemm": (_i32, [_i32, _vp, _vp, _pvp]),

@@ -46,6 +46,8 @@ def sparse_times_dense(a_sparse, b_dense, scalar=1.0, transpose=False, out=None,
     m = a_sparse.shape[1] if transpose else a_sparse.shape[0]
     shape = (m, b_dense.shape[1])
     layout, ldb = _v.dense_layout(b_dense, other=out)
+    if layout == _lib.LAYOUT_C and not transpose and _v.is_csr(a_sparse):
+        return _csr_times_rowmajor(a_sparse, b_dense, shape, scalar, out, out_scalar, out_t)
     handle, dbl, cplx = _h.create(a_sparse)
     with handle:
         dtype = _v.OUTPUT_DTYPES[(dbl, cplx)]
@@ -63,6 +65,30 @@ def sparse_times_dense(a_sparse, b_dense, scalar=1.0, transpose=False, out=None,
         if SDB.DEBUG:
             h2d, krn, d2h = _lib.last_timing_ms()
             print(f"sdb_spmm device time: H2D {h2d:.3f} ms, kernels {krn:.3f} ms, D2H {d2h:.3f} ms")
+    return result
+
+
+def _csr_times_rowmajor(a, b, shape, scalar, out, out_scalar, out_t):
+    """CSR @ C-ordered array: one library call does upload, product and download
+    (sdb_spmm_csr_host; a three-stream row-chunk pipeline when the host arrays
+    are page-locked, the create + spmm + destroy triple otherwise)."""
+    dbl, cplx = _v.precision_flags(a)
+    dtype = _v.OUTPUT_DTYPES[(dbl, cplx)]
+    result = _v.output_array(shape, dtype, "C", out=out, out_t=out_t, zero=False)
+    beta = 0.0 if out is None else (1.0 if out_scalar is None else out_scalar)
+    indptr, indices, bits = _h._index_arrays(a)
+    data = np.ascontiguousarray(a.data)
+    if data.shape[0] != indices.shape[0] or indptr.shape[0] != a.shape[0] + 1:
+        raise ValueError("Sparse matrix arrays are inconsistent with its shape")
+    status = SDB.lib.sdb_spmm_csr_host(
+        a.shape[0], a.shape[1], _ptr(indptr), _ptr(indices), bits, _ptr(data), _h._DTYPE_CODE[np.dtype(a.dtype)],
+        scalar_pair(1.0 if scalar is None else scalar), _ptr(b), shape[1], shape[1], scalar_pair(beta),
+        _ptr(result), shape[1],
+    )
+    check(status, "sdb_spmm_csr_host")
+    if SDB.DEBUG:
+        t0, t1, t2 = _lib.last_timing_ms()
+        print(f"sdb_spmm_csr_host device time: {t0:.3f} / {t1:.3f} / {t2:.3f} ms (see sdb200.h)")
     return result
 
 

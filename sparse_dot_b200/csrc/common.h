@@ -67,6 +67,7 @@ struct Context {
     int device = -1;
     cudaStream_t stream = nullptr;   // compute + H2D
     cudaStream_t d2h_stream = nullptr;
+    cudaStream_t h2d_stream = nullptr;  // uploads of the pipelined host entry points
     int sm_count = 0;
     size_t l2_bytes = 0;
     // pinned staging ring
@@ -116,6 +117,7 @@ struct DevBuf {
 // on ctx->stream; h2d returns once the host buffer may be reused, d2h returns
 // once the bytes are in `dst`.  2-D variants copy `rows` rows of `row_bytes`
 // with independent pitches (dense panels with ld != n).
+bool is_pinned(const void* p);  // page-locked (or managed) host memory: DMA without staging
 sdb_status h2d(Context* ctx, void* d_dst, const void* h_src, size_t bytes);
 sdb_status d2h(Context* ctx, void* h_dst, const void* d_src, size_t bytes);
 sdb_status h2d_2d(Context* ctx, void* d_dst, size_t d_pitch, const void* h_src, size_t h_pitch,

@@ -41,6 +41,7 @@ sdb_status get_context(Context** out) {
     if (c->device < 0) {
         SDB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         SDB_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        SDB_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
         cudaDeviceProp prop;
         SDB_CUDA(cudaGetDeviceProperties(&prop, dev));
         c->sm_count = prop.multiProcessorCount;
@@ -79,7 +80,7 @@ void dev_free(void* p, cudaStream_t s) {
     if (p) cudaFreeAsync(p, s);
 }
 
-static bool is_pinned(const void* p) {
+bool is_pinned(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
         cudaGetLastError();
