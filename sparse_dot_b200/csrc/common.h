@@ -199,4 +199,9 @@ sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int d
 sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a, const double* alpha,
                        const double* beta, int layout, const void* dX, int64_t n, int64_t ldx,
                        void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy);
+// Native BSR x dense kernel (spmm_bsr.cu): availability test + launch.
+bool spmm_bsr_supported(const sdb_mat* a, int op, int layout, const void* dX, int64_t n, int64_t ldx, const void* dY,
+                        int64_t ldy);
+sdb_status spmm_bsr_device(cudaStream_t s, const sdb_mat* a, const double* alpha, const double* beta, const void* dX,
+                           int64_t n, int64_t ldx, void* dY, int64_t ldy);
 }  // namespace sdb

@@ -18,6 +18,8 @@
 // warp keeps kUnroll * 512 B in flight.  The alpha/beta epilogue is fused and
 // the finished row slice is stored once to every peer panel (n_peers = 1
 // normally; > 1 is the fused all-gather over NVLink peer mappings, §8e).
+#include <cstdlib>
+
 #include "common.h"
 #include "prims.h"
 #include "types.cuh"
@@ -83,15 +85,15 @@ template <typename T, int VEC> __device__ __forceinline__ void store_pack(T* p, 
     *reinterpret_cast<Pack<T, VEC>*>(p) = a;
 }
 
-template <typename T, int VEC, int LANES>
-__global__ void __launch_bounds__(kSpmmWarps * 32)
+template <typename T, int VEC, int LANES, int UNROLL = kUnroll, int MINB = 1>
+__global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
     spmm_rowmajor_kernel(int64_t rows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                          const T* __restrict__ values, bool conj_a, const T* __restrict__ X, int64_t ldx, int64_t n,
                          T alpha, T beta, T* __restrict__ y_self, PeerPanels<T> out, int n_peers, int self, int64_t row0,
                          int64_t ldy) {
     constexpr int kRowsPerWarp = 32 / LANES;
     constexpr unsigned kFull = 0xffffffffu;
-    constexpr int kU = LANES < kUnroll ? LANES : kUnroll;  // gathers in flight per lane
+    constexpr int kU = LANES < UNROLL ? LANES : UNROLL;  // gathers in flight per lane
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES;  // position inside the row group
     const int64_t warp = int64_t(blockIdx.x) * kSpmmWarps + (threadIdx.x >> 5);
@@ -178,9 +180,27 @@ static sdb_status launch_rowmajor(cudaStream_t s, const CsrView& a, bool conj_a,
     const int64_t gx = (a.rows + kRowsPerCta - 1) / kRowsPerCta;
     const int64_t gy = (n + int64_t(LANES) * VEC - 1) / (int64_t(LANES) * VEC);
     SDB_REQUIRE(gx < (int64_t(1) << 31) && gy < 65536, SDB_STATUS_NOT_SUPPORTED, "spmm: grid too large");
-    SDB_LAUNCH((spmm_rowmajor_kernel<T, VEC, LANES>), dim3(unsigned(gx), unsigned(gy)), kSpmmWarps * 32, 0, s, a.rows,
-               a.indptr, a.indices, static_cast<const T*>(a.values), conj_a, X, ldx, n, alpha, beta, out.y[self], out,
-               n_peers, self, row0, ldy);
+#define SDB_SPMM_LAUNCH(U, MB)                                                                                  \
+    SDB_LAUNCH((spmm_rowmajor_kernel<T, VEC, LANES, U, MB>), dim3(unsigned(gx), unsigned(gy)), kSpmmWarps * 32, 0, s, \
+               a.rows, a.indptr, a.indices, static_cast<const T*>(a.values), conj_a, X, ldx, n, alpha, beta,        \
+               out.y[self], out, n_peers, self, row0, ldy)
+    if (LANES == 32 && VEC * sizeof(T) == 16) {
+        // full-warp rows (the headline shape): tuning variants selectable for experiments
+        static const int tune = [] {
+            const char* e = getenv("SDB_SPMM_TUNE");
+            return e ? atoi(e) : 0;
+        }();
+        switch (tune) {
+            case 1: SDB_SPMM_LAUNCH(4, 4); return SDB_STATUS_SUCCESS;
+            case 2: SDB_SPMM_LAUNCH(8, 4); return SDB_STATUS_SUCCESS;
+            case 3: SDB_SPMM_LAUNCH(16, 2); return SDB_STATUS_SUCCESS;
+            case 4: SDB_SPMM_LAUNCH(4, 6); return SDB_STATUS_SUCCESS;
+            case 5: SDB_SPMM_LAUNCH(2, 8); return SDB_STATUS_SUCCESS;
+            default: break;
+        }
+    }
+    SDB_SPMM_LAUNCH(kUnroll, 1);
+#undef SDB_SPMM_LAUNCH
     return SDB_STATUS_SUCCESS;
 }
 
@@ -281,6 +301,11 @@ sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, int layou
     SDB_REQUIRE(n >= 0, SDB_STATUS_INVALID_VALUE, "spmm: negative n");
     Context* ctx;
     SDB_TRY(get_context(&ctx));
+    if (spmm_bsr_supported(A, op, layout, dX, n, ldx, dY, ldy)) {
+        SDB_REQUIRE(ldx >= n && ldy >= n, SDB_STATUS_INVALID_VALUE, "spmm: leading dimension smaller than n");
+        return spmm_bsr_device(stream ? static_cast<cudaStream_t>(stream) : ctx->stream, A, alpha, beta, dX, n, ldx,
+                               dY, ldy);
+    }
     CsrView v;
     SDB_TRY(csr_view(ctx, A, op != SDB_OP_NON_TRANSPOSE, &v));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
@@ -322,9 +347,21 @@ sdb_status sdb_spmm(int op, const double* alpha, const sdb_mat* A, int layout, c
     PhaseTimer timer;
     SDB_TRY(timer.init(s));
     SDB_TRY(timer.mark(0));
-    CsrView v;
-    SDB_TRY(csr_view(ctx, A, op != SDB_OP_NON_TRANSPOSE, &v));
     const size_t es = dtype_size(A->dtype);
+    // BSR with a natively supported block size: no CSR expansion (packed device panels are 16-byte aligned)
+    const bool native_bsr = n > 0 && spmm_bsr_supported(A, op, layout, reinterpret_cast<const void*>(uintptr_t(16)), n,
+                                                       n, reinterpret_cast<const void*>(uintptr_t(16)), n);
+    CsrView v;
+    if (native_bsr) {
+        v.rows = A->rows * A->block;
+        v.cols = A->cols * A->block;
+        v.nnz = A->nnz * A->block * A->block;
+        v.indptr = nullptr;
+        v.indices = nullptr;
+        v.values = nullptr;
+    } else {
+        SDB_TRY(csr_view(ctx, A, op != SDB_OP_NON_TRANSPOSE, &v));
+    }
     const bool row_major = layout == SDB_LAYOUT_ROW_MAJOR;
     const bool beta_zero = beta[0] == 0.0 && beta[1] == 0.0;
     // host panels: `lines` contiguous runs of `run` elements, pitch ld
@@ -339,8 +376,12 @@ sdb_status sdb_spmm(int op, const double* alpha, const sdb_mat* A, int layout, c
         SDB_TRY(h2d_2d(ctx, dy.p, size_t(y_run) * es, Y, size_t(ldy) * es, size_t(y_run) * es, size_t(y_lines)));
     SDB_TRY(timer.mark(1));
     void* yp[1] = {dy.p};
-    SDB_TRY(spmm_device(ctx, s, v, A->dtype, op == SDB_OP_CONJUGATE_TRANSPOSE, alpha, beta, layout, dx.p, n, x_run,
-                        yp, 1, 0, 0, y_run));
+    if (native_bsr) {
+        SDB_TRY(spmm_bsr_device(s, A, alpha, beta, dx.p, n, x_run, dy.p, y_run));
+    } else {
+        SDB_TRY(spmm_device(ctx, s, v, A->dtype, op == SDB_OP_CONJUGATE_TRANSPOSE, alpha, beta, layout, dx.p, n, x_run,
+                            yp, 1, 0, 0, y_run));
+    }
     SDB_TRY(timer.mark(2));
     SDB_TRY(d2h_2d(ctx, Y, size_t(ldy) * es, dy.p, size_t(y_run) * es, size_t(y_run) * es, size_t(y_lines)));
     SDB_TRY(timer.mark(3));

@@ -206,6 +206,36 @@ def test_spmm_widths_against_c_oracle(n, dtype):
     assert cs.rel_err(got.reshape(want.shape), want, bound) <= cs.TOL[np.dtype(dtype)]
 
 
+@pytest.mark.parametrize("dtype", REAL)
+@pytest.mark.parametrize("b", [4, 8, 16, 32])
+@pytest.mark.parametrize("n", [4, 36, 100, 128, 256, 260])
+def test_bsr_native_kernel(dtype, b, n):
+    """The TMA-staged BSR x dense kernel (block sizes 4/8/16/32), incl. ragged
+    column chunks, empty block rows, beta != 0 and column-major blocks."""
+    rng = np.random.default_rng(b * 1000 + n)
+    mb, kb = 37, 29
+    dense_mask = rng.random((mb, kb)) < 0.2
+    dense_mask[3, :] = False  # an empty block row
+    dense_mask[5, :] = True   # a full one (more blocks than pipeline stages)
+    a = sp.bsr_matrix(sp.kron(sp.csr_matrix(dense_mask.astype(dtype)), np.ones((b, b), dtype=dtype)), blocksize=(b, b))
+    a.data[:] = rng.random(a.data.shape) + 0.5
+    x = rng.random((kb * b, n)).astype(dtype)
+    want = orc.c_spmm(a.tocsr(), x)
+    bound = orc.value_bound(abs(a.tocsr()), abs(x))
+    got = sdb.dot_product_mkl(a, x)
+    assert cs.rel_err(got, want, bound) <= cs.TOL[np.dtype(dtype)]
+    y0 = rng.random((mb * b, n)).astype(dtype)
+    got = sdb.dot_product_mkl(a, x, out=y0.copy(), out_scalar=0.5)
+    want2 = orc.c_spmm(a.tocsr(), x, beta=0.5, y=y0.copy())
+    assert cs.rel_err(got, want2, bound + 0.5 * y0) <= cs.TOL[np.dtype(dtype)]
+    # column-major blocks: same matrix, data stored transposed per block
+    af = a.copy()
+    af.data = np.ascontiguousarray(a.data.transpose(0, 2, 1)).transpose(0, 2, 1)
+    assert not af.data.flags.c_contiguous
+    got = sdb.dot_product_mkl(af, x)
+    assert cs.rel_err(got, want, bound) <= cs.TOL[np.dtype(dtype)]
+
+
 def test_spmm_ignores_garbage_in_fresh_output_and_nan_free():
     a = cs.uniform_rows_csr(500, 400, 9, np.float32, seed=1)
     x = np.random.default_rng(0).random((400, 16)).astype(np.float32)
