@@ -75,6 +75,8 @@ def run_c3(scale, ef, full_check):
             _lib.check(lib.sdb_spgemm(_lib.OP_N, ha.ref, hb.ref, C.byref(ref)), "sdb_spgemm")
             return H.Handle(ref, np.float32)
 
+        with mult() as warm:  # first call pays for growing the device memory pool (GBs of cudaMalloc)
+            H.order(warm)
         ms, hc = timed(mult)
         with hc:
             res["spgemm_ms"] = ms

@@ -49,6 +49,10 @@ extern std::atomic<int64_t> g_launches;
         SDB_CUDA(cudaGetLastError());                                      \
     } while (0)
 
+// Phase tracing for development (SDB_TRACE=1): synchronises `s` and prints the milliseconds since
+// the previous trace point on this thread.  A no-op (no sync) when the variable is unset.
+void trace(cudaStream_t s, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+
 // ---------------------------------------------------------------- dtypes
 inline size_t dtype_size(int dtype) {
     switch (dtype) {
@@ -189,6 +193,8 @@ sdb_status csr_view(Context* ctx, const sdb_mat* m, bool transpose, CsrView* v);
 sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indptr, int32_t* indices,
                      void* values, int64_t elems_per_entry);
 sdb_status expand_bsr(Context* ctx, const sdb_mat* bsr, sdb_mat** out_csr);
+// CSR made of whole b-blocks (rows sorted) -> BSR with row-major blocks.
+sdb_status compress_to_bsr(Context* ctx, const sdb_mat* csr, int64_t b, sdb_mat** out);
 // True when every row's column indices are non-decreasing (device reduction + sync).
 sdb_status rows_sorted(Context* ctx, int64_t rows, const int64_t* indptr, const int32_t* indices,
                        bool* sorted);

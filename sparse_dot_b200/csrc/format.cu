@@ -29,17 +29,19 @@ __global__ void __launch_bounds__(256) classify_rows_kernel(int64_t rows, const 
                                                             int32_t* __restrict__ med_rows,
                                                             int32_t* __restrict__ long_rows,
                                                             unsigned* __restrict__ counters /*[3]: med, long, unsorted*/) {
-    int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    // one warp per row: lanes compare neighbouring entries 32 at a time
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (r >= rows) return;
     const int64_t b = indptr[r], e = indptr[r + 1];
     const int64_t len = e - b;
     bool unsorted = false;
-    for (int64_t p = b + 1; p < e; ++p)
-        if (indices[p] < indices[p - 1]) {
-            unsorted = true;
-            break;
-        }
-    if (!unsorted) return;
+    for (int64_t p0 = b + 1; p0 < e && !unsorted; p0 += 32) {
+        const int64_t p = p0 + lane;
+        const bool bad = p < e && indices[p] < indices[p - 1];
+        unsorted = __any_sync(0xffffffffu, bad);
+    }
+    if (!unsorted || lane != 0) return;
     atomicAdd(&counters[2], 1u);
     if (len > kSmemSortMax) long_rows[atomicAdd(&counters[1], 1u)] = int32_t(r);
     else if (len > 32) med_rows[atomicAdd(&counters[0], 1u)] = int32_t(r);
@@ -246,7 +248,7 @@ sdb_status rows_sorted(Context* ctx, int64_t rows, const int64_t* indptr, const 
     SDB_TRY(counters.alloc(3 * sizeof(unsigned), s));
     SDB_TRY(dummy.alloc(size_t(rows) * sizeof(int32_t), s));
     SDB_CUDA(cudaMemsetAsync(counters.p, 0, 3 * sizeof(unsigned), s));
-    SDB_LAUNCH(classify_rows_kernel, blocks_for(rows, 256), 256, 0, s, rows, indptr, indices, dummy.as<int32_t>(),
+    SDB_LAUNCH(classify_rows_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, indices, dummy.as<int32_t>(),
                dummy.as<int32_t>(), counters.as<unsigned>());
     unsigned h[3];
     SDB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -265,13 +267,15 @@ sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indpt
     SDB_TRY(med.alloc(size_t(rows) * sizeof(int32_t), s));
     SDB_TRY(lng.alloc(size_t(rows) * sizeof(int32_t), s));
     SDB_CUDA(cudaMemsetAsync(counters.p, 0, 3 * sizeof(unsigned), s));
-    SDB_LAUNCH(classify_rows_kernel, blocks_for(rows, 256), 256, 0, s, rows, indptr, indices, med.as<int32_t>(),
+    SDB_LAUNCH(classify_rows_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, indices, med.as<int32_t>(),
                lng.as<int32_t>(), counters.as<unsigned>());
     unsigned h[3];
     int64_t nnz = 0;
     SDB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     SDB_CUDA(cudaMemcpyAsync(&nnz, indptr + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     SDB_CUDA(cudaStreamSynchronize(s));
+    trace(s, "sort_rows: classified %lld rows: %u unsorted (%u in shared memory, %u in global memory)", (long long)rows,
+          h[2], h[0], h[1]);
     if (h[2] == 0 || nnz == 0) return SDB_STATUS_SUCCESS;  // already in order: nothing moves
 
     DevBuf perm, tmp;
@@ -288,6 +292,7 @@ sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indpt
         SDB_LAUNCH(sort_rows_global_kernel, h[1], 1024, 0, s, lng.as<int32_t>(), indptr, indices,
                    perm.as<int32_t>(), scratch.as<uint64_t>());
     }
+    trace(s, "sort_rows: columns sorted");
     if (values != nullptr) {
         const size_t entry_bytes = dtype_size(dtype) * size_t(elems_per_entry);
         SDB_TRY(tmp.alloc(size_t(nnz) * entry_bytes, s));
@@ -295,6 +300,7 @@ sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indpt
                    static_cast<const uint32_t*>(values), tmp.as<uint32_t>(), int64_t(entry_bytes / 4));
         SDB_CUDA(cudaMemcpyAsync(values, tmp.p, size_t(nnz) * entry_bytes, cudaMemcpyDeviceToDevice, s));
     }
+    trace(s, "sort_rows: values permuted");
     return SDB_STATUS_SUCCESS;
 }
 
@@ -413,6 +419,69 @@ sdb_status expand_bsr(Context* ctx, const sdb_mat* m, sdb_mat** out_csr) {
         }
     }
     *out_csr = c;
+    return SDB_STATUS_SUCCESS;
+}
+
+// ============================================================ CSR -> BSR
+// Inverse of expand_bsr for a CSR matrix whose rows come in groups of b with an
+// identical, sorted pattern made of whole b-wide column blocks (what a product
+// of two expanded BSR matrices looks like).  Used by BSR x BSR SpGEMM.
+__global__ void __launch_bounds__(256) bsr_row_blocks_kernel(int64_t block_rows, int b,
+                                                             const int64_t* __restrict__ indptr,
+                                                             int32_t* __restrict__ nblk) {
+    const int64_t I = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (I >= block_rows) return;
+    nblk[I] = int32_t((indptr[I * b + 1] - indptr[I * b]) / b);
+}
+
+__global__ void __launch_bounds__(256) compress_bsr_kernel(int64_t block_rows, int b,
+                                                           const int64_t* __restrict__ indptr,
+                                                           const int32_t* __restrict__ indices,
+                                                           const uint32_t* __restrict__ values, int words,
+                                                           const int64_t* __restrict__ bptr,
+                                                           int32_t* __restrict__ bidx, uint32_t* __restrict__ bval) {
+    const int lane = threadIdx.x & 31;
+    const int64_t I = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (I >= block_rows) return;
+    const int64_t q0 = bptr[I], nb = bptr[I + 1] - q0;
+    const int64_t first = indptr[I * b];
+    for (int64_t t = lane; t < nb; t += 32) bidx[q0 + t] = indices[first + t * b] / b;
+    const int64_t per_block = int64_t(b) * b;
+    for (int64_t e = lane; e < nb * per_block; e += 32) {
+        const int64_t t = e / per_block;
+        const int rc = int(e - t * per_block);
+        const int r = rc / b, c = rc - r * b;
+        const int64_t src = indptr[I * b + r] + t * b + c;
+        for (int w = 0; w < words; ++w) bval[(q0 * per_block + e) * words + w] = values[src * words + w];
+    }
+}
+
+sdb_status compress_to_bsr(Context* ctx, const sdb_mat* csr, int64_t b, sdb_mat** out) {
+    cudaStream_t s = ctx->stream;
+    SDB_REQUIRE(b >= 1 && csr->rows % b == 0 && csr->cols % b == 0 && csr->nnz % (b * b) == 0,
+                SDB_STATUS_INTERNAL_ERROR, "compress_to_bsr: matrix is not made of whole %lld-blocks", (long long)b);
+    const int64_t block_rows = csr->rows / b;
+    sdb_mat* m;
+    SDB_TRY(new_handle(&m, SDB_FMT_BSR, csr->dtype, block_rows, csr->cols / b, csr->nnz / (b * b), b,
+                       SDB_LAYOUT_ROW_MAJOR, s));
+    sdb_status st = [&]() -> sdb_status {
+        DevBuf nblk;
+        SDB_TRY(nblk.alloc(size_t(block_rows + 1) * 4, s));
+        if (block_rows > 0)
+            SDB_LAUNCH(bsr_row_blocks_kernel, blocks_for(block_rows, 256), 256, 0, s, block_rows, int(b), csr->indptr,
+                       nblk.as<int32_t>());
+        SDB_TRY(exclusive_scan_i32_to_i64(s, nblk.as<int32_t>(), m->indptr, block_rows));
+        if (block_rows > 0 && m->nnz > 0)
+            SDB_LAUNCH(compress_bsr_kernel, blocks_for(block_rows * 32, 256), 256, 0, s, block_rows, int(b),
+                       csr->indptr, csr->indices, static_cast<const uint32_t*>(csr->values),
+                       int(dtype_size(csr->dtype) / 4), m->indptr, m->indices, static_cast<uint32_t*>(m->values));
+        return SDB_STATUS_SUCCESS;
+    }();
+    if (st != SDB_STATUS_SUCCESS) {
+        free_handle(m);
+        return st;
+    }
+    *out = m;
     return SDB_STATUS_SUCCESS;
 }
 

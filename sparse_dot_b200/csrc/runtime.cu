@@ -1,6 +1,7 @@
 // runtime.cu — host runtime of libsdb200: error plumbing, per-thread context,
 // stream-ordered memory, pinned staging copies, phase timers and the small
 // host-only ABI entry points (version string, device selection, row partitioner).
+#include <chrono>
 #include <cstdarg>
 #include <cstdlib>
 #include <mutex>
@@ -28,6 +29,24 @@ sdb_status cuda_fail(cudaError_t e, const char* what, const char* file, int line
               base ? base + 1 : file, line);
     cudaGetLastError();  // clear the sticky-free error state
     return e == cudaErrorMemoryAllocation ? SDB_STATUS_ALLOC_FAILED : SDB_STATUS_EXECUTION_FAILED;
+}
+
+void trace(cudaStream_t s, const char* fmt, ...) {
+    static const bool on = [] {
+        const char* e = getenv("SDB_TRACE");
+        return e && *e && *e != '0';
+    }();
+    if (!on) return;
+    static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    char msg[256];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(msg, sizeof(msg), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "[sdb %9.3f ms] %s\n", std::chrono::duration<double, std::milli>(now - last).count(), msg);
+    last = std::chrono::steady_clock::now();
 }
 
 // ---------------------------------------------------------------- context

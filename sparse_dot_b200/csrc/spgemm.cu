@@ -141,6 +141,53 @@ __device__ __forceinline__ int hash_row(int64_t i, int tid, int team, const int6
     return added;
 }
 
+// CTA-wide walk over the products of row i: the L entries' R-row bounds (and values) are staged in
+// shared memory kStageEntries at a time with coalesced loads, then the warps take staged entries
+// round-robin and their lanes stride the R row.  f(col, a, q) is called once per product.
+constexpr int kStageEntries = 256;
+constexpr int kLongRRow = 512;  // R rows longer than this are shared by all warps of the CTA
+template <typename T> struct LStage {
+    int64_t rb[kStageEntries];
+    int64_t re[kStageEntries];
+    T a[kStageEntries];
+};
+
+template <typename T, bool NEED_VAL, typename F>
+__device__ __forceinline__ void for_each_product_cta(int64_t i, const int64_t* __restrict__ l_ptr,
+                                                     const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
+                                                     const int64_t* __restrict__ r_ptr,
+                                                     const int32_t* __restrict__ r_idx, LStage<T>& st, F f) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int64_t l_end = l_ptr[i + 1];
+    for (int64_t base = l_ptr[i]; base < l_end; base += kStageEntries) {
+        const int cnt = int(min(int64_t(kStageEntries), l_end - base));
+        __syncthreads();  // the previous round has been consumed
+        for (int e = tid; e < cnt; e += blockDim.x) {
+            const int32_t k = l_idx[base + e];
+            st.rb[e] = r_ptr[k];
+            st.re[e] = r_ptr[k + 1];
+            if (NEED_VAL) st.a[e] = l_val[base + e];
+        }
+        __syncthreads();
+        // short R rows: one warp each, round-robin
+        for (int e = warp; e < cnt; e += nwarps) {
+            const int64_t qb = st.rb[e], qe = st.re[e];
+            if (qe - qb > kLongRRow) continue;
+            T a = Num<T>::zero();
+            if (NEED_VAL) a = st.a[e];
+            for (int64_t q = qb + lane; q < qe; q += 32) f(r_idx[q], a, q);
+        }
+        // long R rows (power-law tails): the whole CTA strides each of them
+        for (int e = 0; e < cnt; ++e) {
+            const int64_t qb = st.rb[e], qe = st.re[e];
+            if (qe - qb <= kLongRRow) continue;
+            T a = Num<T>::zero();
+            if (NEED_VAL) a = st.a[e];
+            for (int64_t q = qb + tid; q < qe; q += blockDim.x) f(r_idx[q], a, q);
+        }
+    }
+}
+
 template <typename T, bool NUMERIC>
 __global__ void __launch_bounds__(kHashWarps * 32)
     spgemm_warp_kernel(const int32_t* __restrict__ list, unsigned n_list, const int64_t* __restrict__ l_ptr,
@@ -202,8 +249,15 @@ __global__ void __launch_bounds__(kCtaThreads)
     }
     if (threadIdx.x == 0) total = 0;
     __syncthreads();
-    int added = hash_row<T, NUMERIC, kCtaSlots, kCtaSlotsLog2>(i, threadIdx.x, kCtaThreads, l_ptr, l_idx, l_val,
-                                                               r_ptr, r_idx, r_val, upper, keys, vals);
+    __shared__ LStage<T> stage;
+    int added = 0;
+    for_each_product_cta<T, NUMERIC>(i, l_ptr, l_idx, l_val, r_ptr, r_idx, stage,
+                                     [&](int32_t col, T a, int64_t q) {
+                                         if (upper && int64_t(col) < i) return;
+                                         uint32_t slot;
+                                         added += hash_insert<kCtaSlots, kCtaSlotsLog2>(keys, col, &slot);
+                                         if (NUMERIC) atomic_add(vals + slot, mul(a, r_val[q]));
+                                     });
     if (!NUMERIC) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) added += __shfl_xor_sync(0xffffffffu, added, d);
@@ -229,44 +283,65 @@ __global__ void __launch_bounds__(kCtaThreads)
     }
 }
 
-// Wide rows: bitmap (and dense values) of the whole column range per resident
-// CTA, in global memory.  Grid-stride over the listed rows.
+// Wide rows (more than kCtaMax entries): one CTA per row at a time with a bitmap of the whole
+// column range in a per-CTA slice of global memory (L2 resident).  No hash probing and only
+// fire-and-forget atomics:
+//   1. walk the products, atomicOr the column bits;
+//   2. sweep the bitmap in pieces of 128 words (one coalesced 16-byte load per lane): piece
+//      populations -> one block-wide scan -> output offsets;   [symbolic stops here: c_len]
+//   3. second sweep: every word gets its output rank (word_rank), columns are written in
+//      ascending order and their values zeroed IN the output row;
+//   4. walk the products again: rank = word_rank[col / 32] + popc(lower bits) and the product
+//      is atomically added to c_val[row start + rank] (a compact, L2-resident target);
+//   5. clear the bitmap.
+// The result rows are sorted, so sdb_order has nothing to do for them.
+constexpr int kPieceWords = 128;
+constexpr int kPiecesPerRound = 1024;  // == blockDim.x of the wide kernel
+
 template <typename T, bool NUMERIC>
 __global__ void __launch_bounds__(1024)
-    spgemm_wide_kernel(const int32_t* __restrict__ list, unsigned n_list, int64_t n_cols,
+    spgemm_wide_kernel(const int32_t* __restrict__ list, unsigned n_list, int64_t words_padded,
                        const int64_t* __restrict__ l_ptr, const int32_t* __restrict__ l_idx,
                        const T* __restrict__ l_val, const int64_t* __restrict__ r_ptr,
                        const int32_t* __restrict__ r_idx, const T* __restrict__ r_val, bool upper,
-                       unsigned* __restrict__ bitmaps, T* __restrict__ dense, int32_t* __restrict__ c_len,
-                       const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
+                       unsigned* __restrict__ bitmaps, int32_t* __restrict__ word_ranks,
+                       int32_t* __restrict__ c_len, const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx,
+                       T* __restrict__ c_val) {
+    __shared__ int piece_off[kPiecesPerRound];
     __shared__ int warp_tot[32];
     __shared__ int64_t running;
-    const int64_t words = (n_cols + 31) >> 5;
-    unsigned* bm = bitmaps + int64_t(blockIdx.x) * words;
-    T* acc = NUMERIC ? dense + int64_t(blockIdx.x) * n_cols : nullptr;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    __shared__ LStage<T> stage;
+    unsigned* bm = bitmaps + int64_t(blockIdx.x) * words_padded;
+    int32_t* word_rank = NUMERIC ? word_ranks + int64_t(blockIdx.x) * words_padded : nullptr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int64_t n_pieces = words_padded / kPieceWords;
     for (unsigned li = blockIdx.x; li < n_list; li += gridDim.x) {
         const int64_t i = list[li];
-        // scatter
-        for (int64_t p = l_ptr[i] + warp; p < l_ptr[i + 1]; p += nwarps) {
-            const int32_t k = l_idx[p];
-            T a = Num<T>::zero();
-            if (NUMERIC) a = l_val[p];
-            for (int64_t q = r_ptr[k] + lane; q < r_ptr[k + 1]; q += 32) {
-                const int32_t col = r_idx[q];
-                if (upper && int64_t(col) < i) continue;
-                atomicOr(&bm[col >> 5], 1u << (col & 31));
-                if (NUMERIC) atomic_add(acc + col, mul(a, r_val[q]));
-            }
-        }
-        if (threadIdx.x == 0) running = 0;
+        // ---- 1. membership
+        for_each_product_cta<T, false>(i, l_ptr, l_idx, l_val, r_ptr, r_idx, stage,
+                                       [&](int32_t col, T, int64_t) {
+                                           if (upper && int64_t(col) < i) return;
+                                           atomicOr(&bm[col >> 5], 1u << (col & 31));
+                                       });
+        if (tid == 0) running = 0;
         __syncthreads();
-        // ordered emission / count, one bitmap word per thread per sweep
-        for (int64_t w0 = 0; w0 < words; w0 += blockDim.x) {
-            const int64_t w = w0 + threadIdx.x;
-            unsigned bits = w < words ? __ldcg(bm + w) : 0u;
-            int cnt = __popc(bits);
-            int incl = cnt;
+        const int64_t out0 = NUMERIC ? c_ptr[i] : 0;
+        // ---- 2./3. count, scan, ordered emission
+        for (int64_t piece0 = 0; piece0 < n_pieces; piece0 += kPiecesPerRound) {
+            const int round = int(min(int64_t(kPiecesPerRound), n_pieces - piece0));
+            for (int pc = warp; pc < round; pc += nwarps) {
+                uint4* wp = reinterpret_cast<uint4*>(bm + (piece0 + pc) * kPieceWords) + lane;
+                const uint4 b = __ldcg(wp);
+                int c = __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+                if (!NUMERIC && c) *wp = make_uint4(0u, 0u, 0u, 0u);  // symbolic: count and clear in one go
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                if (lane == 0) piece_off[pc] = c;
+            }
+            __syncthreads();
+            // exclusive scan of piece_off[0..round) by the whole block (one entry per thread)
+            const int v = tid < round ? piece_off[tid] : 0;
+            int incl = v;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const int o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -274,31 +349,71 @@ __global__ void __launch_bounds__(1024)
             }
             if (lane == 31) warp_tot[warp] = incl;
             __syncthreads();
-            int before = 0, sweep = 0;
+            int before = 0, total = 0;
             for (int x = 0; x < nwarps; ++x) {
                 const int t = warp_tot[x];
                 if (x < warp) before += t;
-                sweep += t;
+                total += t;
             }
-            const int64_t base = running;
-            if (NUMERIC && bits) {
-                int64_t o = c_ptr[i] + base + before + incl - cnt;
-                while (bits) {
-                    const int b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const int64_t col = (w << 5) + b;
-                    c_idx[o] = int32_t(col);
-                    c_val[o] = ldcg(acc + col);
-                    acc[col] = Num<T>::zero();
-                    ++o;
+            if (tid < round) piece_off[tid] = before + incl - v;
+            __syncthreads();
+            if (NUMERIC) {
+                const int rank0 = int(running);
+                for (int pc = warp; pc < round; pc += nwarps) {
+                    const int64_t w0 = (piece0 + pc) * kPieceWords + lane * 4;
+                    const uint4 b = __ldcg(reinterpret_cast<const uint4*>(bm + w0));
+                    const int c0 = __popc(b.x), c1 = __popc(b.y), c2 = __popc(b.z), c3 = __popc(b.w);
+                    const int c = c0 + c1 + c2 + c3;
+                    int pre = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, pre, d);
+                        if (lane >= d) pre += o;
+                    }
+                    const int r0 = rank0 + piece_off[pc] + pre - c;  // rank of this lane's first word
+                    *reinterpret_cast<int4*>(word_rank + w0) = make_int4(r0, r0 + c0, r0 + c0 + c1, r0 + c0 + c1 + c2);
+                    if (c) {
+                        int64_t o = out0 + r0;
+                        const unsigned ws[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            unsigned bits = ws[t];
+                            while (bits) {
+                                const int bit = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                c_idx[o] = int32_t(((w0 + t) << 5) + bit);
+                                c_val[o] = Num<T>::zero();
+                                ++o;
+                            }
+                        }
+                    }
                 }
             }
-            if (w < words && cnt) bm[w] = 0u;
             __syncthreads();
-            if (threadIdx.x == 0) running = base + sweep;
+            if (tid == 0) running += total;
             __syncthreads();
         }
-        if (!NUMERIC && threadIdx.x == 0) c_len[i] = int32_t(running);
+        if (!NUMERIC) {
+            if (tid == 0) c_len[i] = int32_t(running);
+            __syncthreads();
+            continue;
+        }
+        // ---- 4. values: every product is added at its column's rank
+        for_each_product_cta<T, true>(i, l_ptr, l_idx, l_val, r_ptr, r_idx, stage,
+                                      [&](int32_t col, T a, int64_t q) {
+                                          if (upper && int64_t(col) < i) return;
+                                          const int w = col >> 5;
+                                          const unsigned below = __ldcg(bm + w) & ((1u << (col & 31)) - 1u);
+                                          const int rank = __ldcg(word_rank + w) + __popc(below);
+                                          atomic_add(c_val + out0 + rank, mul(a, r_val[q]));
+                                      });
+        __syncthreads();
+        // ---- 5. clear
+        for (int64_t w = int64_t(tid) * 4; w < words_padded; w += int64_t(blockDim.x) * 4) {
+            uint4* wp = reinterpret_cast<uint4*>(bm + w);
+            const uint4 b = __ldcg(wp);
+            if (b.x | b.y | b.z | b.w) *wp = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncthreads();
     }
 }
@@ -319,6 +434,7 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
     unsigned h[3];
     SDB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     SDB_CUDA(cudaStreamSynchronize(s));
+    trace(s, "spgemm %s: bins warp %u, cta %u, wide %u", NUMERIC ? "numeric" : "symbolic", h[0], h[1], h[2]);
     const int64_t* lp = l.indptr;
     const int32_t* li = l.indices;
     const T* lv = static_cast<const T*>(l.values);
@@ -331,6 +447,7 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
                                       int(smem)));
         SDB_LAUNCH((spgemm_warp_kernel<T, NUMERIC>), (h[0] + kHashWarps - 1) / kHashWarps, kHashWarps * 32, smem, s,
                    lw.as<int32_t>(), h[0], lp, li, lv, rp, ri, rv, upper, c_len, c_ptr, c_idx, c_val);
+        trace(s, "spgemm: warp bin done");
     }
     if (h[1] > 0) {
         const size_t smem = size_t(kCtaSlots) * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0));
@@ -338,23 +455,22 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
                                       int(smem)));
         SDB_LAUNCH((spgemm_cta_kernel<T, NUMERIC>), h[1], kCtaThreads, smem, s, lc.as<int32_t>(), lp, li, lv, rp, ri,
                    rv, upper, c_len, c_ptr, c_idx, c_val);
+        trace(s, "spgemm: cta bin done");
     }
     if (h[2] > 0) {
         const int64_t n_cols = r.cols;
-        const int64_t words = (n_cols + 31) >> 5;
-        // resident CTAs: bounded by the list, the SM count and ~2 GiB of scratch
-        const int64_t per_cta = words * 4 + (NUMERIC ? n_cols * int64_t(sizeof(T)) : 0);
-        int64_t ctas = std::min<int64_t>(h[2], ctx->sm_count);
+        const int64_t words = (((n_cols + 31) >> 5) + kPieceWords - 1) / kPieceWords * kPieceWords;  // padded
+        // resident CTAs: bounded by the list, two per SM, and ~2 GiB of scratch
+        const int64_t per_cta = words * 4 * (NUMERIC ? 2 : 1);
+        int64_t ctas = std::min<int64_t>(h[2], 2 * int64_t(ctx->sm_count));
         ctas = std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t(2) << 30) / std::max<int64_t>(per_cta, 1)));
-        DevBuf bm, dense;
+        DevBuf bm, ranks;
         SDB_TRY(bm.alloc(size_t(ctas * words) * 4, s));
         SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(ctas * words) * 4, s));
-        if (NUMERIC) {
-            SDB_TRY(dense.alloc(size_t(ctas * n_cols) * sizeof(T), s));
-            SDB_CUDA(cudaMemsetAsync(dense.p, 0, size_t(ctas * n_cols) * sizeof(T), s));
-        }
-        SDB_LAUNCH((spgemm_wide_kernel<T, NUMERIC>), unsigned(ctas), 1024, 0, s, lg.as<int32_t>(), h[2], n_cols, lp,
-                   li, lv, rp, ri, rv, upper, bm.as<unsigned>(), dense.as<T>(), c_len, c_ptr, c_idx, c_val);
+        if (NUMERIC) SDB_TRY(ranks.alloc(size_t(ctas * words) * 4, s));
+        SDB_LAUNCH((spgemm_wide_kernel<T, NUMERIC>), unsigned(ctas), 1024, 0, s, lg.as<int32_t>(), h[2], words, lp, li,
+                   lv, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx, c_val);
+        trace(s, "spgemm: wide bin done (%lld CTAs)", (long long)ctas);
     }
     return SDB_STATUS_SUCCESS;
 }
@@ -405,10 +521,11 @@ sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int d
 // optional col >= row restriction.  One CTA per (row, column tile); the tile
 // accumulates in shared memory (shared-memory atomics, every R entry lands
 // once) and is written to HBM once, coalesced.
-constexpr int kDenseThreads = 512;
+constexpr int kDenseMaxThreads = 1024;
+constexpr int kDenseRowsInFlight = 4;  // R rows whose entry loads are issued together by one warp
 
 template <typename T>
-__global__ void __launch_bounds__(kDenseThreads)
+__global__ void __launch_bounds__(kDenseMaxThreads)
     spgemm_dense_kernel(int64_t n_cols, int tile_cols, const int64_t* __restrict__ l_ptr,
                         const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
                         const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
@@ -416,29 +533,65 @@ __global__ void __launch_bounds__(kDenseThreads)
                         T* __restrict__ C, int64_t ldc, bool col_major) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* acc = reinterpret_cast<T*>(smem_raw);
+    const int nthreads = blockDim.x;
     const int64_t i = blockIdx.x;
-    const int64_t j0 = int64_t(blockIdx.y) * tile_cols;
+    // column tiles start at the first column this row owns (the diagonal for a triangular result)
+    const int64_t base = upper ? i : 0;
+    const int64_t j0 = base + int64_t(blockIdx.y) * tile_cols;
     const int64_t j1 = min(n_cols, j0 + tile_cols);
-    const int64_t lo = upper ? max(j0, i) : j0;  // first column this CTA owns
-    if (upper && zero_lower)  // fresh result: the strict lower triangle is defined to be zero
-        for (int64_t j = j0 + threadIdx.x; j < min(lo, j1); j += kDenseThreads)
+    if (upper && zero_lower && blockIdx.y == 0)  // fresh result: the strict lower triangle is defined to be zero
+        for (int64_t j = threadIdx.x; j < i; j += nthreads)
             *(col_major ? C + j * ldc + i : C + i * ldc + j) = Num<T>::zero();
-    if (lo >= j1) return;
-    for (int64_t j = lo - j0 + threadIdx.x; j < j1 - j0; j += kDenseThreads) acc[j] = Num<T>::zero();
+    if (j0 >= n_cols) return;
+    for (int64_t j = threadIdx.x; j < j1 - j0; j += nthreads) acc[j] = Num<T>::zero();
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int kWarps = kDenseThreads / 32;
-    for (int64_t p = l_ptr[i] + warp; p < l_ptr[i + 1]; p += kWarps) {
-        const int32_t k = l_idx[p];
-        const T a = l_val[p];
-        for (int64_t q = r_ptr[k] + lane; q < r_ptr[k + 1]; q += 32) {
-            const int64_t col = r_idx[q];
-            if (col >= lo && col < j1) atomic_add(acc + (col - j0), mul(a, r_val[q]));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
+    const int64_t l_end = l_ptr[i + 1];
+    // Each warp takes 32 L entries at a time (one coalesced load of k, a and the R row bounds), then
+    // walks their R rows kDenseRowsInFlight at a time so that many independent loads are in flight.
+    for (int64_t p0 = l_ptr[i] + int64_t(warp) * 32; p0 < l_end; p0 += int64_t(nwarps) * 32) {
+        const int64_t mine = p0 + lane;
+        int64_t rb = 0, re = 0;
+        T a = Num<T>::zero();
+        if (mine < l_end) {
+            const int32_t k = l_idx[mine];
+            a = l_val[mine];
+            rb = r_ptr[k];
+            re = r_ptr[k + 1];
+        }
+        const int cnt = int(min(int64_t(32), l_end - p0));
+        for (int j = 0; j < cnt; j += kDenseRowsInFlight) {
+            int64_t qb[kDenseRowsInFlight];
+            int len[kDenseRowsInFlight];
+            T av[kDenseRowsInFlight];
+            int maxlen = 0;
+#pragma unroll
+            for (int u = 0; u < kDenseRowsInFlight; ++u) {
+                const int src = (j + u) & 31;
+                qb[u] = __shfl_sync(0xffffffffu, rb, src);
+                const int64_t qe = __shfl_sync(0xffffffffu, re, src);
+                av[u] = shfl(0xffffffffu, a, src, 32);
+                len[u] = (j + u) < cnt ? int(min(qe - qb[u], int64_t(INT32_MAX))) : 0;
+                maxlen = max(maxlen, len[u]);
+            }
+            for (int off = lane; off < maxlen; off += 32) {
+                int64_t col[kDenseRowsInFlight];
+                T v[kDenseRowsInFlight];
+#pragma unroll
+                for (int u = 0; u < kDenseRowsInFlight; ++u) {
+                    const bool ok = off < len[u];
+                    col[u] = ok ? int64_t(__ldg(r_idx + qb[u] + off)) : int64_t(-1);
+                    v[u] = ok ? ldg(r_val + qb[u] + off) : Num<T>::zero();
+                }
+#pragma unroll
+                for (int u = 0; u < kDenseRowsInFlight; ++u)
+                    if (col[u] >= j0 && col[u] < j1) atomic_add(acc + (col[u] - j0), mul(av[u], v[u]));
+            }
         }
     }
     __syncthreads();
     const bool beta_zero = Num<T>::is_zero(beta);
-    for (int64_t j = lo + threadIdx.x; j < j1; j += kDenseThreads) {
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += nthreads) {
         T* c = col_major ? C + j * ldc + i : C + i * ldc + j;
         const T v = mul(alpha, acc[j - j0]);
         *c = beta_zero ? v : madd(beta, *c, v);
@@ -457,14 +610,16 @@ sdb_status spgemm_dense_device(Context* ctx, cudaStream_t s, const CsrView& l, c
     const bool col_major = layout == SDB_LAYOUT_COL_MAJOR;
     SDB_REQUIRE(ldc >= (col_major ? m : n), SDB_STATUS_INVALID_VALUE, "dense product: ldc too small");
     return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
-        const int64_t max_tile = (192 * 1024) / int64_t(sizeof(T));
+        const int64_t max_tile = (200 * 1024) / int64_t(sizeof(T));
         const int64_t tiles = (n + max_tile - 1) / max_tile;
         const int64_t tile = std::min<int64_t>(max_tile, ((n + tiles - 1) / tiles + 31) / 32 * 32);
         const size_t smem = size_t(tile) * sizeof(T);
+        // wide tiles leave room for one CTA per SM: give it all 32 warps; small problems use small CTAs
+        const int threads = smem > 96 * 1024 ? 1024 : (smem > 32 * 1024 ? 512 : 256);
         SDB_REQUIRE(tiles < 65536, SDB_STATUS_NOT_SUPPORTED, "dense product: too many column tiles");
         SDB_CUDA(cudaFuncSetAttribute(spgemm_dense_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(std::max<size_t>(smem, 48 * 1024))));
-        SDB_LAUNCH(spgemm_dense_kernel<T>, dim3(unsigned(m), unsigned(tiles)), kDenseThreads, smem, s, n, int(tile),
+        SDB_LAUNCH(spgemm_dense_kernel<T>, dim3(unsigned(m), unsigned(tiles)), threads, smem, s, n, int(tile),
                    l.indptr, l.indices, static_cast<const T*>(l.values), r.indptr, r.indices,
                    static_cast<const T*>(r.values), upper, zero_lower, Num<T>::make(alpha[0], alpha[1]),
                    Num<T>::make(beta[0], beta[1]), static_cast<T*>(dC), ldc, col_major);
@@ -494,8 +649,9 @@ sdb_status sdb_spgemm(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C) {
     SDB_TRY(check_pair("spgemm", A, B));
     SDB_REQUIRE(op == SDB_OP_NON_TRANSPOSE || op == SDB_OP_TRANSPOSE, SDB_STATUS_NOT_SUPPORTED,
                 "spgemm: op %d not supported", op);
-    SDB_REQUIRE(A->format != SDB_FMT_BSR && B->format != SDB_FMT_BSR, SDB_STATUS_NOT_SUPPORTED,
-                "spgemm: BSR operands are not supported for a sparse result");
+    const bool bsr = A->format == SDB_FMT_BSR || B->format == SDB_FMT_BSR;
+    SDB_REQUIRE(!bsr || (A->format == B->format && A->block == B->block), SDB_STATUS_NOT_SUPPORTED,
+                "spgemm: a BSR operand needs a BSR partner with the same block size");
     const bool ta = op == SDB_OP_TRANSPOSE;
     const int64_t inner_a = ta ? logical_rows(A) : logical_cols(A);
     SDB_REQUIRE(inner_a == logical_rows(B), SDB_STATUS_INVALID_VALUE, "spgemm: inner dimensions differ");
@@ -503,7 +659,18 @@ sdb_status sdb_spgemm(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C) {
     SDB_TRY(get_context(&ctx));
     CsrView l, r;
     sdb_mat* c = nullptr;
-    if (A->format == SDB_FMT_CSC) {
+    if (bsr) {
+        // BSR x BSR -> BSR: multiply the CSR expansions (whole blocks, explicit zeros kept, so the
+        // product is made of whole blocks too), order the rows, fold b x b entries back into blocks
+        SDB_TRY(csr_view(ctx, A, ta, &l));
+        SDB_TRY(csr_view(ctx, B, false, &r));
+        sdb_mat* flat = nullptr;
+        SDB_TRY(spgemm_device(ctx, l, r, A->dtype, false, &flat));
+        sdb_status st = sort_rows(ctx, flat->dtype, flat->rows, flat->indptr, flat->indices, flat->values, 1);
+        if (st == SDB_STATUS_SUCCESS) st = compress_to_bsr(ctx, flat, A->block, &c);
+        free_handle(flat);
+        SDB_TRY(st);
+    } else if (A->format == SDB_FMT_CSC) {
         // result in A's format: CSC(C) = CSR(C^T) = CSR(B^T) * CSR(op(A)^T)
         SDB_TRY(csr_view(ctx, B, true, &l));
         SDB_TRY(csr_view(ctx, A, !ta, &r));

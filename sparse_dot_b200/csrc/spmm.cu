@@ -102,16 +102,21 @@ __global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
     const bool row_ok = row < rows;
     const bool col_ok = col0 < n;  // n % VEC == 0 on the vector path, VEC == 1 otherwise
 
-    int64_t p = 0, end = 0;
+    // 32-bit counters relative to the row start keep the hot loop small (a row never holds 2^31 entries)
+    int len = 0;
+    const int32_t* ci = indices;
+    const T* cv = values;
     if (row_ok) {
-        p = indptr[row];
-        end = indptr[row + 1];
+        const int64_t start = indptr[row];
+        len = int(min(indptr[row + 1] - start, int64_t(INT32_MAX)));
+        ci += start;
+        cv += start;
     }
     // the warp iterates together: shuffles need every lane, groups may differ in length
-    int64_t len = end - p;
+    int maxlen = len;
     if (LANES < 32) {
 #pragma unroll
-        for (int d = 16; d >= LANES; d >>= 1) len = max(len, __shfl_xor_sync(kFull, len, d));
+        for (int d = 16; d >= LANES; d >>= 1) maxlen = max(maxlen, __shfl_xor_sync(kFull, maxlen, d));
     }
 
     Pack<T, VEC> acc;
@@ -119,16 +124,16 @@ __global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
     for (int i = 0; i < VEC; ++i) acc.v[i] = Num<T>::zero();
 
     const T* xcol = X + col0;
-    for (int64_t done = 0; done < len; done += LANES, p += LANES) {
-        const int64_t mine = p + sub;
+    for (int base = 0; base < maxlen; base += LANES) {
+        const int mine = base + sub;
         int32_t c = 0;
         T v = Num<T>::zero();
-        if (mine < end) {
-            c = __ldg(indices + mine);
-            v = ldg(values + mine);
+        if (mine < len) {
+            c = __ldg(ci + mine);
+            v = ldg(cv + mine);
             if (conj_a) v = conj_(v);
         }
-        const int batch = int(min(int64_t(LANES), len - done));  // warp-uniform
+        const int batch = min(LANES, maxlen - base);  // warp-uniform
         for (int j0 = 0; j0 < batch; j0 += kU) {
             Pack<T, VEC> x[kU];
             T a[kU];
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
                 const int j = j0 + u;  // may run past LANES: shuffles wrap, the predicate masks it
                 const int32_t cj = __shfl_sync(kFull, c, j, LANES);
                 a[u] = shfl(kFull, v, j, LANES);
-                const bool live = col_ok && j < LANES && (p + j) < end;
+                const bool live = col_ok && j < LANES && (base + j) < len;
                 if (live) {
                     x[u] = load_pack<T, VEC>(xcol + int64_t(cj) * ldx);
                 } else {
@@ -196,8 +201,18 @@ static sdb_status launch_rowmajor(cudaStream_t s, const CsrView& a, bool conj_a,
             case 3: SDB_SPMM_LAUNCH(16, 2); return SDB_STATUS_SUCCESS;
             case 4: SDB_SPMM_LAUNCH(4, 6); return SDB_STATUS_SUCCESS;
             case 5: SDB_SPMM_LAUNCH(2, 8); return SDB_STATUS_SUCCESS;
+            case 6: SDB_SPMM_LAUNCH(1, 8); return SDB_STATUS_SUCCESS;
+            case 7: SDB_SPMM_LAUNCH(2, 6); return SDB_STATUS_SUCCESS;
+            case 8: SDB_SPMM_LAUNCH(4, 5); return SDB_STATUS_SUCCESS;
+            case 9: SDB_SPMM_LAUNCH(3, 8); return SDB_STATUS_SUCCESS;
+            case 10: SDB_SPMM_LAUNCH(3, 6); return SDB_STATUS_SUCCESS;
+            case 11: SDB_SPMM_LAUNCH(kUnroll, 1); return SDB_STATUS_SUCCESS;
             default: break;
         }
+        // measured on B200 (profiles/README.md, round 1): full occupancy (32 registers, 8 CTAs x 8 warps per
+        // SM) with 2 gathers in flight per lane beats deeper unrolling at 3 CTAs/SM by 22 %
+        SDB_SPMM_LAUNCH(2, 8);
+        return SDB_STATUS_SUCCESS;
     }
     SDB_SPMM_LAUNCH(kUnroll, 1);
 #undef SDB_SPMM_LAUNCH
@@ -217,6 +232,58 @@ static sdb_status pick_lanes(cudaStream_t s, const CsrView& a, bool conj_a, cons
     if (packs > 1) SDB_GO(2);
     SDB_GO(1);
 #undef SDB_GO
+}
+
+// ------------------------------------------------------------------ SpMV (n == 1)
+// mkl_sparse_?_mv (_sparse_vector.py:20-25,84-92): y = alpha * op(A) * x + beta * y.
+// A group of LANES lanes reduces one row: lanes stride the row's entries (coalesced index / value
+// loads, gathered x), then a shuffle tree adds the partial sums.  LANES follows the mean row length.
+template <typename T, int LANES>
+__global__ void __launch_bounds__(256) spmv_kernel(int64_t rows, const int64_t* __restrict__ indptr,
+                                                   const int32_t* __restrict__ indices,
+                                                   const T* __restrict__ values, bool conj_a,
+                                                   const T* __restrict__ x, int64_t incx, T alpha, T beta,
+                                                   T* __restrict__ y, int64_t incy) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LANES;
+    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / LANES;
+    T acc = Num<T>::zero();
+    if (row < rows) {
+        const int64_t e = indptr[row + 1];
+        for (int64_t p = indptr[row] + sub; p < e; p += LANES) {
+            T v = ldg(values + p);
+            if (conj_a) v = conj_(v);
+            acc = madd(v, ldg(x + int64_t(__ldg(indices + p)) * incx), acc);
+        }
+    }
+#pragma unroll
+    for (int d = LANES / 2; d > 0; d >>= 1) acc = add(acc, shfl(0xffffffffu, acc, (lane ^ d), 32));
+    if (row < rows && sub == 0) {
+        T* out = y + row * incy;
+        *out = Num<T>::is_zero(beta) ? mul(alpha, acc) : madd(alpha, acc, mul(beta, *out));
+    }
+}
+
+template <typename T>
+static sdb_status spmv(cudaStream_t s, const CsrView& a, bool conj_a, const double* alpha_d, const double* beta_d,
+                       const void* dX, int64_t incx, void* dY, int64_t incy) {
+    const T alpha = Num<T>::make(alpha_d[0], alpha_d[1]), beta = Num<T>::make(beta_d[0], beta_d[1]);
+    const double mean = a.rows > 0 ? double(a.nnz) / double(a.rows) : 0.0;
+#define SDB_SPMV(L)                                                                                            \
+    do {                                                                                                       \
+        const int64_t blocks = (a.rows * L + 255) / 256;                                                       \
+        SDB_REQUIRE(blocks < (int64_t(1) << 31), SDB_STATUS_NOT_SUPPORTED, "spmv: grid too large");             \
+        SDB_LAUNCH((spmv_kernel<T, L>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices,              \
+                   static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,      \
+                   static_cast<T*>(dY), incy);                                                                 \
+        return SDB_STATUS_SUCCESS;                                                                             \
+    } while (0)
+    if (mean > 48) SDB_SPMV(32);
+    if (mean > 24) SDB_SPMV(16);
+    if (mean > 12) SDB_SPMV(8);
+    if (mean > 6) SDB_SPMV(4);
+    SDB_SPMV(2);
+#undef SDB_SPMV
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -252,6 +319,13 @@ sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype
     SDB_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && self >= 0 && self < n_peers, SDB_STATUS_INVALID_VALUE,
                 "spmm: bad peer configuration (%d peers, self %d)", n_peers, self);
     if (a.rows == 0 || n == 0) return SDB_STATUS_SUCCESS;
+    if (n == 1 && n_peers == 1 && row0 == 0) {
+        // one column: the panel layout only decides the element strides
+        const bool rm = layout == SDB_LAYOUT_ROW_MAJOR;
+        return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
+            return spmv<T>(s, a, conj_a, alpha, beta, dX, rm ? ldx : 1, dY_peers[0], rm ? ldy : 1);
+        });
+    }
     if (layout == SDB_LAYOUT_ROW_MAJOR) {
         SDB_REQUIRE(ldx >= n && ldy >= n, SDB_STATUS_INVALID_VALUE, "spmm: leading dimension smaller than n");
         return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {

@@ -397,6 +397,72 @@ def test_spgemm_all_row_bins(dtype):
     _check_sparse_product(got, a, b, dtype, False)
 
 
+@pytest.mark.parametrize("dtype", REAL)
+@pytest.mark.parametrize("upper", [False, True])
+def test_spgemm_every_bin_by_construction(dtype, upper):
+    """Rows built to land in the warp (<=256), CTA (<=4096), large (<=65536, global hash) and
+    wide (>65536, bitmap + dense accumulator) bins; also the triangular (syrk) filter."""
+    rng = np.random.default_rng(7)
+    k, n = 2000, 30000
+    b = sp.random(k, n, density=0.01, format="csr", dtype=dtype, random_state=3)
+    b.data[:] = rng.random(b.nnz) + 0.5
+    per_row = [0, 1, 2, 10, 12, 60, 100, 150, 290, 320, 1, 0, 7]
+    rows = []
+    for cnt in per_row:
+        cols = np.sort(rng.choice(k, size=cnt, replace=False))
+        rows.append(sp.csr_matrix((rng.random(cnt).astype(dtype) + 0.5, (np.zeros(cnt, dtype=int), cols)), shape=(1, k)))
+    a = sp.vstack(rows).tocsr().astype(dtype)
+    if not upper:
+        got = sdb.dot_product_mkl(a, b, reorder_output=True)
+        want = orc.c_spgemm(a, b, sort=True)
+    else:
+        # gram of M = [a; b-ish]: use syrk on a matrix whose A^T A rows span the bins
+        m = sp.vstack([a, a[::-1]]).tocsr()
+        got = sdb.gram_matrix_mkl(m, reorder_output=True)
+        want = orc.c_syrk(m, sort=True)
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    assert cs.rel_err(got.data, want.data) <= cs.TOL[np.dtype(dtype)]
+
+
+@pytest.mark.parametrize("dtype", ALL)
+@pytest.mark.parametrize("b", [10, 4])
+def test_spgemm_bsr(dtype, b):
+    """test_sparse_sparse.py:250-262 (TestMultiplicationBSR): BSR x BSR -> BSR with the same blocks."""
+    m1, m2 = _pair(dtype)
+    a1, a2 = m1.tobsr(blocksize=(b, b)), m2.tobsr(blocksize=(b, b))
+    got = sdb.dot_product_mkl(a1, a2)
+    assert isinstance(got, sp.bsr_matrix) and got.blocksize == (b, b) and got.dtype == np.dtype(dtype)
+    _close(got, m1, m2, dtype)
+    want = (a1 @ a2).tobsr(blocksize=(b, b))
+    want.sort_indices()
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    got_arr = sdb.dot_product_mkl(sp.bsr_array(a1), sp.bsr_array(a2), reorder_output=True)
+    assert isinstance(got_arr, sp.bsr_array)
+    dense = sdb.dot_product_mkl(a1, a2, dense=True)
+    _close(dense, m1, m2, dtype)
+    with pytest.raises(ValueError):
+        sdb.dot_product_mkl(m1, a2)  # CSR x BSR: not supported (the reference skips it too, :174-182)
+
+
+@pytest.mark.parametrize("dtype", REAL)
+@pytest.mark.parametrize("per_row", [1, 5, 20, 70])
+def test_spmv_kernel_widths(dtype, per_row):
+    """Dedicated SpMV kernel: every lanes-per-row specialisation, both ops, strided out."""
+    a = cs.uniform_rows_csr(5000, 3000, per_row, dtype, seed=per_row)
+    v = np.random.default_rng(1).random(3000).astype(dtype)
+    got = sdb.dot_product_mkl(a, v)
+    want = orc.c_spmm(a, v.reshape(-1, 1)).ravel()
+    assert cs.rel_err(got, want) <= cs.TOL[np.dtype(dtype)]
+    w = np.random.default_rng(2).random(5000).astype(dtype)
+    got = sdb.dot_product_mkl(w, a)
+    want = orc.c_spmm(a, w.reshape(-1, 1), op=orc.OP_T).ravel()
+    assert cs.rel_err(got, want) <= cs.TOL[np.dtype(dtype)]
+    out = np.ones((5000, 1), dtype=dtype)
+    got = sdb.dot_product_mkl(a, v.reshape(-1, 1), out=out, out_scalar=0.5)
+    assert got is out
+    assert cs.rel_err(got.ravel(), orc.c_spmm(a, v.reshape(-1, 1)).ravel() + 0.5) <= cs.TOL[np.dtype(dtype)]
+
+
 def test_spgemm_structural_zeros_are_kept():
     """MKL convention (SURVEY §8c hazard 2): cancellation keeps the entry."""
     a = sp.csr_matrix(np.array([[1.0, -1.0], [2.0, 0.0]]))
