@@ -165,6 +165,11 @@ struct sdb_mat {
     // Lazily built CSR expansion of a BSR handle (every stored block becomes
     // block*block explicit entries); lets BSR reuse the CSR kernels.
     sdb_mat* expanded;
+    // Optional cross positions (built together with the transposed companion when a triangular
+    // product asks for them): for stored entry p = (line i, index k), pos[p] is the position of
+    // index i inside line k of the companion.  Valid only while strict_sorted == 1.
+    int32_t* pos;
+    int strict_sorted;  // 0 unknown, 1 every line strictly ascending (no duplicates), -1 not
 };
 
 namespace sdb {
@@ -181,17 +186,21 @@ void free_handle(sdb_mat* m);
 
 // Internal device-level operations shared between translation units -------------
 // CSR(A) -> CSR(A^T) as a new owned handle (rows/cols swapped), rows sorted.
-sdb_status transpose_compressed(Context* ctx, const sdb_mat* a, sdb_mat** out);
+sdb_status transpose_compressed(Context* ctx, sdb_mat* a, sdb_mat** out, bool with_pos = false);
 // The CSR view of `m` for op(A): returns arrays such that row r lists op(A)[r,:].
 struct CsrView {
     int64_t rows, cols, nnz;
     const int64_t* indptr;
     const int32_t* indices;
     const void* values;
+    // For entry p = (row i, column k): where column i sits in row k of the TRANSPOSE of this view
+    // (nullptr when not requested / not available).  A triangular product L * L^T restricted to
+    // col >= row starts its walk of row k of L^T there instead of at the row's first entry.
+    const int32_t* pos = nullptr;
 };
-sdb_status csr_view(Context* ctx, const sdb_mat* m, bool transpose, CsrView* v);
+sdb_status csr_view(Context* ctx, const sdb_mat* m, bool transpose, CsrView* v, bool want_pos = false);
 sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indptr, int32_t* indices,
-                     void* values, int64_t elems_per_entry);
+                     void* values, int64_t elems_per_entry, int32_t* extra = nullptr);
 sdb_status expand_bsr(Context* ctx, const sdb_mat* bsr, sdb_mat** out_csr);
 // CSR made of whole b-blocks (rows sorted) -> BSR with row-major blocks.
 sdb_status compress_to_bsr(Context* ctx, const sdb_mat* csr, int64_t b, sdb_mat** out);

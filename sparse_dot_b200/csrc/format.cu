@@ -240,6 +240,37 @@ __global__ void __launch_bounds__(256) permute_values_kernel(int64_t rows, const
 
 static unsigned blocks_for(int64_t n, int per_block) { return unsigned((n + per_block - 1) / per_block); }
 
+__global__ void __launch_bounds__(256) strict_rows_kernel(int64_t rows, const int64_t* __restrict__ indptr,
+                                                          const int32_t* __restrict__ indices,
+                                                          unsigned* __restrict__ violations) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const int64_t b = indptr[r], e = indptr[r + 1];
+    bool bad = false;
+    for (int64_t p = b + 1 + lane; p < e; p += 32) bad |= indices[p] <= indices[p - 1];
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(violations, 1u);
+}
+
+// every line strictly ascending (sorted, no duplicate index)?  cached on the handle
+static sdb_status ensure_strict_flag(Context* ctx, sdb_mat* m) {
+    if (m->strict_sorted != 0) return SDB_STATUS_SUCCESS;
+    cudaStream_t s = ctx->stream;
+    const int64_t lines = major_dim(m);
+    unsigned h = 0;
+    if (lines > 0 && m->nnz > 0) {
+        DevBuf v;
+        SDB_TRY(v.alloc(sizeof(unsigned), s));
+        SDB_CUDA(cudaMemsetAsync(v.p, 0, sizeof(unsigned), s));
+        SDB_LAUNCH(strict_rows_kernel, blocks_for(lines * 32, 256), 256, 0, s, lines, m->indptr, m->indices,
+                   v.as<unsigned>());
+        SDB_CUDA(cudaMemcpyAsync(&h, v.p, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+        SDB_CUDA(cudaStreamSynchronize(s));
+    }
+    m->strict_sorted = h == 0 ? 1 : -1;
+    return SDB_STATUS_SUCCESS;
+}
+
 sdb_status rows_sorted(Context* ctx, int64_t rows, const int64_t* indptr, const int32_t* indices, bool* sorted) {
     *sorted = true;
     if (rows <= 0) return SDB_STATUS_SUCCESS;
@@ -258,7 +289,7 @@ sdb_status rows_sorted(Context* ctx, int64_t rows, const int64_t* indptr, const 
 }
 
 sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indptr, int32_t* indices,
-                     void* values, int64_t elems_per_entry) {
+                     void* values, int64_t elems_per_entry, int32_t* extra) {
     if (rows <= 0) return SDB_STATUS_SUCCESS;
     cudaStream_t s = ctx->stream;
     SDB_REQUIRE(rows < (int64_t(1) << 31), SDB_STATUS_NOT_SUPPORTED, "sort_rows: too many rows");
@@ -300,6 +331,13 @@ sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indpt
                    static_cast<const uint32_t*>(values), tmp.as<uint32_t>(), int64_t(entry_bytes / 4));
         SDB_CUDA(cudaMemcpyAsync(values, tmp.p, size_t(nnz) * entry_bytes, cudaMemcpyDeviceToDevice, s));
     }
+    if (extra != nullptr) {  // a second per-entry payload (one 4-byte word) travels the same way
+        DevBuf tmp2;
+        SDB_TRY(tmp2.alloc(size_t(nnz) * 4, s));
+        SDB_LAUNCH(permute_values_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, perm.as<int32_t>(),
+                   reinterpret_cast<const uint32_t*>(extra), tmp2.as<uint32_t>(), int64_t(1));
+        SDB_CUDA(cudaMemcpyAsync(extra, tmp2.p, size_t(nnz) * 4, cudaMemcpyDeviceToDevice, s));
+    }
     trace(s, "sort_rows: values permuted");
     return SDB_STATUS_SUCCESS;
 }
@@ -324,7 +362,8 @@ __global__ void __launch_bounds__(256) scatter_transpose_kernel(int64_t rows, co
                                                                 int words_per_entry,
                                                                 unsigned long long* __restrict__ cursor,
                                                                 int32_t* __restrict__ t_indices,
-                                                                uint32_t* __restrict__ t_values) {
+                                                                uint32_t* __restrict__ t_values,
+                                                                int32_t* __restrict__ t_pos) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (r >= rows) return;
@@ -332,11 +371,25 @@ __global__ void __launch_bounds__(256) scatter_transpose_kernel(int64_t rows, co
     for (int64_t p = b + lane; p < e; p += 32) {
         const unsigned long long q = atomicAdd(&cursor[indices[p]], 1ull);
         t_indices[q] = int32_t(r);
+        if (t_pos) t_pos[q] = int32_t(p - b);
         for (int w = 0; w < words_per_entry; ++w) t_values[q * words_per_entry + w] = values[p * words_per_entry + w];
     }
 }
 
-sdb_status transpose_compressed(Context* ctx, const sdb_mat* a, sdb_mat** out) {
+// after the companion is final: a.pos[source entry] = position of its image inside the companion line
+__global__ void __launch_bounds__(256) back_positions_kernel(int64_t t_lines, const int64_t* __restrict__ t_ptr,
+                                                             const int32_t* __restrict__ t_idx,
+                                                             const int32_t* __restrict__ t_pos,
+                                                             const int64_t* __restrict__ a_ptr,
+                                                             int32_t* __restrict__ a_pos) {
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (k >= t_lines) return;
+    const int64_t b = t_ptr[k], e = t_ptr[k + 1];
+    for (int64_t q = b + lane; q < e; q += 32) a_pos[a_ptr[t_idx[q]] + t_pos[q]] = int32_t(q - b);
+}
+
+sdb_status transpose_compressed(Context* ctx, sdb_mat* a, sdb_mat** out, bool with_pos) {
     // `a` is read as a compressed matrix with major_dim(a) lines over minor_dim(a) indices
     cudaStream_t s = ctx->stream;
     const int64_t major = major_dim(a), minor = minor_dim(a);
@@ -344,8 +397,16 @@ sdb_status transpose_compressed(Context* ctx, const sdb_mat* a, sdb_mat** out) {
     sdb_mat* t;
     // the result has `minor` lines; describe it as a CSR (minor x major) matrix
     SDB_TRY(new_handle(&t, SDB_FMT_CSR, a->dtype, minor, major, a->nnz, 1, SDB_LAYOUT_ROW_MAJOR, s));
+    if (with_pos) {
+        SDB_TRY(ensure_strict_flag(ctx, a));
+        with_pos = a->strict_sorted == 1 && a->nnz > 0;
+    }
     sdb_status st = [&]() -> sdb_status {
         DevBuf counts, cursor;
+        if (with_pos) {
+            SDB_TRY(dev_alloc(reinterpret_cast<void**>(&t->pos), size_t(a->nnz) * 4, s));
+            if (!a->pos) SDB_TRY(dev_alloc(reinterpret_cast<void**>(&a->pos), size_t(a->nnz) * 4, s));
+        }
         SDB_TRY(counts.alloc(size_t(minor + 1) * sizeof(int32_t), s));
         SDB_CUDA(cudaMemsetAsync(counts.p, 0, size_t(minor + 1) * sizeof(int32_t), s));
         if (a->nnz > 0) {
@@ -358,8 +419,15 @@ sdb_status transpose_compressed(Context* ctx, const sdb_mat* a, sdb_mat** out) {
         SDB_CUDA(cudaMemcpyAsync(cursor.p, t->indptr, size_t(minor) * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
         SDB_LAUNCH(scatter_transpose_kernel, blocks_for(major * 32, 256), 256, 0, s, major, a->indptr, a->indices,
                    static_cast<const uint32_t*>(a->values), int(dtype_size(a->dtype) / 4),
-                   cursor.as<unsigned long long>(), t->indices, static_cast<uint32_t*>(t->values));
-        return sort_rows(ctx, t->dtype, minor, t->indptr, t->indices, t->values, 1);
+                   cursor.as<unsigned long long>(), t->indices, static_cast<uint32_t*>(t->values), t->pos);
+        SDB_TRY(sort_rows(ctx, t->dtype, minor, t->indptr, t->indices, t->values, 1, t->pos));
+        if (with_pos) {
+            // the source has no duplicates, so the companion's lines are strictly ascending too
+            t->strict_sorted = 1;
+            SDB_LAUNCH(back_positions_kernel, blocks_for(minor * 32, 256), 256, 0, s, minor, t->indptr, t->indices,
+                       t->pos, a->indptr, a->pos);
+        }
+        return SDB_STATUS_SUCCESS;
     }();
     if (st != SDB_STATUS_SUCCESS) {
         free_handle(t);
@@ -486,7 +554,7 @@ sdb_status compress_to_bsr(Context* ctx, const sdb_mat* csr, int64_t b, sdb_mat*
 }
 
 // ============================================================ CSR view of op(A)
-sdb_status csr_view(Context* ctx, const sdb_mat* m_in, bool transpose, CsrView* v) {
+sdb_status csr_view(Context* ctx, const sdb_mat* m_in, bool transpose, CsrView* v, bool want_pos) {
     sdb_mat* m = const_cast<sdb_mat*>(m_in);  // companions are a cache, not a logical mutation
     if (m->format == SDB_FMT_BSR) {
         if (!m->expanded) SDB_TRY(expand_bsr(ctx, m, &m->expanded));
@@ -494,7 +562,20 @@ sdb_status csr_view(Context* ctx, const sdb_mat* m_in, bool transpose, CsrView* 
     }
     // the stored arrays list lines of A (CSR) or of A^T (CSC)
     const bool stored_is_transposed = m->format == SDB_FMT_CSC;
+    v->pos = nullptr;
+    if (want_pos) {
+        // positions need the companion, built WITH positions; a companion cached without them is rebuilt
+        if (m->transposed && !m->transposed->pos) {
+            SDB_TRY(ensure_strict_flag(ctx, m));
+            if (m->strict_sorted == 1 && m->nnz > 0) {
+                free_handle(m->transposed);
+                m->transposed = nullptr;
+            }
+        }
+        if (!m->transposed) SDB_TRY(transpose_compressed(ctx, m, &m->transposed, true));
+    }
     if (stored_is_transposed == transpose) {
+        if (want_pos && m->transposed && m->transposed->pos) v->pos = m->pos;
         v->rows = major_dim(m);
         v->cols = minor_dim(m);
         v->nnz = m->nnz;
@@ -505,6 +586,7 @@ sdb_status csr_view(Context* ctx, const sdb_mat* m_in, bool transpose, CsrView* 
     }
     if (!m->transposed) SDB_TRY(transpose_compressed(ctx, m, &m->transposed));
     const sdb_mat* t = m->transposed;
+    if (want_pos) v->pos = t->pos;
     v->rows = t->rows;
     v->cols = t->cols;
     v->nnz = t->nnz;
@@ -537,6 +619,11 @@ sdb_status sdb_order(sdb_mat* m) {
         free_handle(m->expanded);
         m->expanded = nullptr;
     }
+    if (m->pos) {
+        cudaFreeAsync(m->pos, ctx->stream);
+        m->pos = nullptr;
+    }
+    m->strict_sorted = 0;
     SDB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SDB_STATUS_SUCCESS;
 }

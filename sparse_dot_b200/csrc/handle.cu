@@ -52,6 +52,10 @@ void free_handle(sdb_mat* m) {
         if (m->indices) cudaFreeAsync(m->indices, s);
         if (m->values) cudaFreeAsync(m->values, s);
     }
+    if (m->pos) {
+        Context* ctx = nullptr;
+        cudaFreeAsync(m->pos, get_context(&ctx) == SDB_STATUS_SUCCESS ? ctx->stream : nullptr);
+    }
     m->magic = 0;
     free(m);
 }

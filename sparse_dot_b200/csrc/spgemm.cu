@@ -17,6 +17,8 @@
 // sdb_syrk is the same two passes on (A^T, A) or (A, A^T) with a col >= row
 // filter.  Dense results accumulate one output row (column tile) per CTA in
 // shared memory and write it once.  HBM/L2-bound integer + FMA work.
+#include <cstdlib>
+
 #include "common.h"
 #include "prims.h"
 #include "types.cuh"
@@ -56,6 +58,7 @@ __device__ __forceinline__ int hash_insert(int32_t* keys, int32_t col, uint32_t*
 // ub[i] = sum over entries (i,k) of L of len(R[k]), clamped to INT32_MAX
 __global__ void __launch_bounds__(256) row_products_kernel(int64_t rows, const int64_t* __restrict__ l_ptr,
                                                            const int32_t* __restrict__ l_idx,
+                                                           const int32_t* __restrict__ l_pos,
                                                            const int64_t* __restrict__ r_ptr,
                                                            int32_t* __restrict__ ub) {
     const int lane = threadIdx.x & 31;
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(256) row_products_kernel(int64_t rows, const i
     int64_t acc = 0;
     for (int64_t p = l_ptr[i] + lane; p < l_ptr[i + 1]; p += 32) {
         const int32_t k = l_idx[p];
-        acc += r_ptr[k + 1] - r_ptr[k];
+        acc += r_ptr[k + 1] - r_ptr[k] - (l_pos ? l_pos[p] : 0);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(256) bin_rows_kernel(int64_t rows, const int32
 template <typename T, bool NUMERIC, int SLOTS, int LOG2>
 __device__ __forceinline__ int hash_row(int64_t i, int tid, int team, const int64_t* __restrict__ l_ptr,
                                         const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
-                                        const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
+                                        const int32_t* __restrict__ l_pos, const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
                                         const T* __restrict__ r_val, bool upper, int32_t* keys, T* vals) {
     int added = 0;
     const int lane = tid & 31;
@@ -120,7 +123,7 @@ __device__ __forceinline__ int hash_row(int64_t i, int tid, int team, const int6
         T a = Num<T>::zero();
         if (mine < l_ptr[i + 1]) {
             const int32_t k = l_idx[mine];
-            rb = r_ptr[k];
+            rb = r_ptr[k] + (l_pos ? l_pos[mine] : 0);
             re = r_ptr[k + 1];
             if (NUMERIC) a = l_val[mine];
         }
@@ -155,6 +158,7 @@ template <typename T> struct LStage {
 template <typename T, bool NEED_VAL, typename F>
 __device__ __forceinline__ void for_each_product_cta(int64_t i, const int64_t* __restrict__ l_ptr,
                                                      const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
+                                                     const int32_t* __restrict__ l_pos,
                                                      const int64_t* __restrict__ r_ptr,
                                                      const int32_t* __restrict__ r_idx, LStage<T>& st, F f) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -164,7 +168,7 @@ __device__ __forceinline__ void for_each_product_cta(int64_t i, const int64_t* _
         __syncthreads();  // the previous round has been consumed
         for (int e = tid; e < cnt; e += blockDim.x) {
             const int32_t k = l_idx[base + e];
-            st.rb[e] = r_ptr[k];
+            st.rb[e] = r_ptr[k] + (l_pos ? l_pos[base + e] : 0);
             st.re[e] = r_ptr[k + 1];
             if (NEED_VAL) st.a[e] = l_val[base + e];
         }
@@ -192,7 +196,7 @@ template <typename T, bool NUMERIC>
 __global__ void __launch_bounds__(kHashWarps * 32)
     spgemm_warp_kernel(const int32_t* __restrict__ list, unsigned n_list, const int64_t* __restrict__ l_ptr,
                        const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
-                       const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
+                       const int32_t* __restrict__ l_pos, const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
                        const T* __restrict__ r_val, bool upper, int32_t* __restrict__ c_len,
                        const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(kHashWarps * 32)
         if (NUMERIC) vals[s] = Num<T>::zero();
     }
     __syncwarp();
-    int added = hash_row<T, NUMERIC, kWarpSlots, kWarpSlotsLog2>(i, lane, 32, l_ptr, l_idx, l_val, r_ptr, r_idx,
+    int added = hash_row<T, NUMERIC, kWarpSlots, kWarpSlotsLog2>(i, lane, 32, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx,
                                                                 r_val, upper, keys, vals);
     __syncwarp();
     if (!NUMERIC) {
@@ -235,7 +239,7 @@ template <typename T, bool NUMERIC>
 __global__ void __launch_bounds__(kCtaThreads)
     spgemm_cta_kernel(const int32_t* __restrict__ list, const int64_t* __restrict__ l_ptr,
                       const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
-                      const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
+                      const int32_t* __restrict__ l_pos, const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
                       const T* __restrict__ r_val, bool upper, int32_t* __restrict__ c_len,
                       const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -251,7 +255,7 @@ __global__ void __launch_bounds__(kCtaThreads)
     __syncthreads();
     __shared__ LStage<T> stage;
     int added = 0;
-    for_each_product_cta<T, NUMERIC>(i, l_ptr, l_idx, l_val, r_ptr, r_idx, stage,
+    for_each_product_cta<T, NUMERIC>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
                                      [&](int32_t col, T a, int64_t q) {
                                          if (upper && int64_t(col) < i) return;
                                          uint32_t slot;
@@ -302,9 +306,10 @@ template <typename T, bool NUMERIC>
 __global__ void __launch_bounds__(1024)
     spgemm_wide_kernel(const int32_t* __restrict__ list, unsigned n_list, int64_t words_padded,
                        const int64_t* __restrict__ l_ptr, const int32_t* __restrict__ l_idx,
-                       const T* __restrict__ l_val, const int64_t* __restrict__ r_ptr,
-                       const int32_t* __restrict__ r_idx, const T* __restrict__ r_val, bool upper,
-                       unsigned* __restrict__ bitmaps, int32_t* __restrict__ word_ranks,
+                       const T* __restrict__ l_val, const int32_t* __restrict__ l_pos,
+                       const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
+                       const T* __restrict__ r_val, bool upper, unsigned* __restrict__ bitmaps,
+                       int32_t* __restrict__ word_ranks,
                        int32_t* __restrict__ c_len, const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx,
                        T* __restrict__ c_val) {
     __shared__ int piece_off[kPiecesPerRound];
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(1024)
     for (unsigned li = blockIdx.x; li < n_list; li += gridDim.x) {
         const int64_t i = list[li];
         // ---- 1. membership
-        for_each_product_cta<T, false>(i, l_ptr, l_idx, l_val, r_ptr, r_idx, stage,
+        for_each_product_cta<T, false>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
                                        [&](int32_t col, T, int64_t) {
                                            if (upper && int64_t(col) < i) return;
                                            atomicOr(&bm[col >> 5], 1u << (col & 31));
@@ -399,7 +404,7 @@ __global__ void __launch_bounds__(1024)
             continue;
         }
         // ---- 4. values: every product is added at its column's rank
-        for_each_product_cta<T, true>(i, l_ptr, l_idx, l_val, r_ptr, r_idx, stage,
+        for_each_product_cta<T, true>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
                                       [&](int32_t col, T a, int64_t q) {
                                           if (upper && int64_t(col) < i) return;
                                           const int w = col >> 5;
@@ -438,6 +443,7 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
     const int64_t* lp = l.indptr;
     const int32_t* li = l.indices;
     const T* lv = static_cast<const T*>(l.values);
+    const int32_t* lq = upper ? l.pos : nullptr;  // start offsets into R rows (triangular products only)
     const int64_t* rp = r.indptr;
     const int32_t* ri = r.indices;
     const T* rv = static_cast<const T*>(r.values);
@@ -446,15 +452,15 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
         SDB_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel<T, NUMERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem)));
         SDB_LAUNCH((spgemm_warp_kernel<T, NUMERIC>), (h[0] + kHashWarps - 1) / kHashWarps, kHashWarps * 32, smem, s,
-                   lw.as<int32_t>(), h[0], lp, li, lv, rp, ri, rv, upper, c_len, c_ptr, c_idx, c_val);
+                   lw.as<int32_t>(), h[0], lp, li, lv, lq, rp, ri, rv, upper, c_len, c_ptr, c_idx, c_val);
         trace(s, "spgemm: warp bin done");
     }
     if (h[1] > 0) {
         const size_t smem = size_t(kCtaSlots) * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0));
         SDB_CUDA(cudaFuncSetAttribute(spgemm_cta_kernel<T, NUMERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem)));
-        SDB_LAUNCH((spgemm_cta_kernel<T, NUMERIC>), h[1], kCtaThreads, smem, s, lc.as<int32_t>(), lp, li, lv, rp, ri,
-                   rv, upper, c_len, c_ptr, c_idx, c_val);
+        SDB_LAUNCH((spgemm_cta_kernel<T, NUMERIC>), h[1], kCtaThreads, smem, s, lc.as<int32_t>(), lp, li, lv, lq, rp,
+                   ri, rv, upper, c_len, c_ptr, c_idx, c_val);
         trace(s, "spgemm: cta bin done");
     }
     if (h[2] > 0) {
@@ -469,7 +475,7 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
         SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(ctas * words) * 4, s));
         if (NUMERIC) SDB_TRY(ranks.alloc(size_t(ctas * words) * 4, s));
         SDB_LAUNCH((spgemm_wide_kernel<T, NUMERIC>), unsigned(ctas), 1024, 0, s, lg.as<int32_t>(), h[2], words, lp, li,
-                   lv, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx, c_val);
+                   lv, lq, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx, c_val);
         trace(s, "spgemm: wide bin done (%lld CTAs)", (long long)ctas);
     }
     return SDB_STATUS_SUCCESS;
@@ -486,7 +492,7 @@ sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int d
     sdb_mat* c = nullptr;
     if (rows > 0) {
         SDB_LAUNCH(row_products_kernel, unsigned((rows * 32 + 255) / 256), 256, 0, s, rows, l.indptr, l.indices,
-                   r.indptr, ub.as<int32_t>());
+                   upper ? l.pos : nullptr, r.indptr, ub.as<int32_t>());
         SDB_TRY(SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
             return run_pass<T, false>(ctx, l, r, upper, ub.as<int32_t>(), c_len.as<int32_t>(), nullptr, nullptr,
                                       nullptr);
@@ -528,7 +534,7 @@ template <typename T>
 __global__ void __launch_bounds__(kDenseMaxThreads)
     spgemm_dense_kernel(int64_t n_cols, int tile_cols, const int64_t* __restrict__ l_ptr,
                         const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
-                        const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
+                        const int32_t* __restrict__ l_pos, const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
                         const T* __restrict__ r_val, bool upper, bool zero_lower, T alpha, T beta,
                         T* __restrict__ C, int64_t ldc, bool col_major) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -556,7 +562,7 @@ __global__ void __launch_bounds__(kDenseMaxThreads)
         if (mine < l_end) {
             const int32_t k = l_idx[mine];
             a = l_val[mine];
-            rb = r_ptr[k];
+            rb = r_ptr[k] + (l_pos ? l_pos[mine] : 0);  // triangular: start at the diagonal entry
             re = r_ptr[k + 1];
         }
         const int cnt = int(min(int64_t(32), l_end - p0));
@@ -598,6 +604,76 @@ __global__ void __launch_bounds__(kDenseMaxThreads)
     }
 }
 
+// Variant without shared memory: the output row itself is the accumulator.  The CTA first scales
+// (or zeroes) its row segment with coalesced stores, then every product is a fire-and-forget
+// red.global.add into C[i, col] — the row (n * sv bytes) stays L2-resident while its CTA works on
+// it, so the atomics resolve in L2 and the row reaches HBM once.  One pass over the R rows whatever
+// n is (no column tiles), and global fp32 reductions are native whereas shared-memory fp32
+// atomicAdd is a compare-and-swap loop.
+template <typename T>
+__global__ void __launch_bounds__(kDenseMaxThreads)
+    spgemm_dense_red_kernel(int64_t n_cols, const int64_t* __restrict__ l_ptr, const int32_t* __restrict__ l_idx,
+                            const T* __restrict__ l_val, const int32_t* __restrict__ l_pos,
+                            const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
+                            const T* __restrict__ r_val, bool upper, bool zero_lower, T alpha, T beta,
+                            T* __restrict__ C, int64_t ldc, bool col_major) {
+    const int nthreads = blockDim.x;
+    const int64_t i = blockIdx.x;
+    const int64_t base = upper ? i : 0;
+    const int64_t row_stride = col_major ? 1 : ldc, col_stride = col_major ? ldc : 1;
+    T* crow = C + i * row_stride;
+    if (upper && zero_lower)
+        for (int64_t j = threadIdx.x; j < base; j += nthreads) crow[j * col_stride] = Num<T>::zero();
+    const bool beta_zero = Num<T>::is_zero(beta);
+    for (int64_t j = base + threadIdx.x; j < n_cols; j += nthreads) {
+        T* c = crow + j * col_stride;
+        *c = beta_zero ? Num<T>::zero() : mul(beta, *c);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nthreads >> 5;
+    const int64_t l_end = l_ptr[i + 1];
+    for (int64_t p0 = l_ptr[i] + int64_t(warp) * 32; p0 < l_end; p0 += int64_t(nwarps) * 32) {
+        const int64_t mine = p0 + lane;
+        int64_t rb = 0, re = 0;
+        T a = Num<T>::zero();
+        if (mine < l_end) {
+            const int32_t k = l_idx[mine];
+            a = mul(alpha, l_val[mine]);
+            rb = r_ptr[k] + (l_pos ? l_pos[mine] : 0);
+            re = r_ptr[k + 1];
+        }
+        const int cnt = int(min(int64_t(32), l_end - p0));
+        for (int j = 0; j < cnt; j += kDenseRowsInFlight) {
+            int64_t qb[kDenseRowsInFlight];
+            int len[kDenseRowsInFlight];
+            T av[kDenseRowsInFlight];
+            int maxlen = 0;
+#pragma unroll
+            for (int u = 0; u < kDenseRowsInFlight; ++u) {
+                const int src = (j + u) & 31;
+                qb[u] = __shfl_sync(0xffffffffu, rb, src);
+                const int64_t qe = __shfl_sync(0xffffffffu, re, src);
+                av[u] = shfl(0xffffffffu, a, src, 32);
+                len[u] = (j + u) < cnt ? int(min(qe - qb[u], int64_t(INT32_MAX))) : 0;
+                maxlen = max(maxlen, len[u]);
+            }
+            for (int off = lane; off < maxlen; off += 32) {
+                int64_t col[kDenseRowsInFlight];
+                T v[kDenseRowsInFlight];
+#pragma unroll
+                for (int u = 0; u < kDenseRowsInFlight; ++u) {
+                    const bool ok = off < len[u];
+                    col[u] = ok ? int64_t(__ldg(r_idx + qb[u] + off)) : int64_t(-1);
+                    v[u] = ok ? ldg(r_val + qb[u] + off) : Num<T>::zero();
+                }
+#pragma unroll
+                for (int u = 0; u < kDenseRowsInFlight; ++u)
+                    if (col[u] >= base) atomic_add(crow + col[u] * col_stride, mul(av[u], v[u]));
+            }
+        }
+    }
+}
+
 sdb_status spgemm_dense_device(Context* ctx, cudaStream_t s, const CsrView& l, const CsrView& r, int dtype,
                                bool upper, bool zero_lower, const double* alpha, const double* beta, int layout,
                                void* dC, int64_t ldc) {
@@ -609,6 +685,21 @@ sdb_status spgemm_dense_device(Context* ctx, cudaStream_t s, const CsrView& l, c
     SDB_REQUIRE(m < (int64_t(1) << 31), SDB_STATUS_NOT_SUPPORTED, "dense product: too many rows");
     const bool col_major = layout == SDB_LAYOUT_COL_MAJOR;
     SDB_REQUIRE(ldc >= (col_major ? m : n), SDB_STATUS_INVALID_VALUE, "dense product: ldc too small");
+    // accumulate in shared-memory column tiles (small rows) or directly in the L2-resident output row
+    static const int forced_mode = [] {
+        const char* e = getenv("SDB_DENSE_MODE");
+        return e ? atoi(e) : 0;  // 1 = shared-memory tiles, 2 = global reductions
+    }();
+    const bool use_red = forced_mode ? forced_mode == 2 : size_t(n) * dtype_size(dtype) > size_t(64) * 1024;
+    if (use_red) {
+        return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
+            SDB_LAUNCH(spgemm_dense_red_kernel<T>, unsigned(m), 1024, 0, s, n, l.indptr, l.indices,
+                       static_cast<const T*>(l.values), upper ? l.pos : nullptr, r.indptr, r.indices,
+                       static_cast<const T*>(r.values), upper, zero_lower, Num<T>::make(alpha[0], alpha[1]),
+                       Num<T>::make(beta[0], beta[1]), static_cast<T*>(dC), ldc, col_major);
+            return SDB_STATUS_SUCCESS;
+        });
+    }
     return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
         const int64_t max_tile = (200 * 1024) / int64_t(sizeof(T));
         const int64_t tiles = (n + max_tile - 1) / max_tile;
@@ -620,8 +711,8 @@ sdb_status spgemm_dense_device(Context* ctx, cudaStream_t s, const CsrView& l, c
         SDB_CUDA(cudaFuncSetAttribute(spgemm_dense_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(std::max<size_t>(smem, 48 * 1024))));
         SDB_LAUNCH(spgemm_dense_kernel<T>, dim3(unsigned(m), unsigned(tiles)), threads, smem, s, n, int(tile),
-                   l.indptr, l.indices, static_cast<const T*>(l.values), r.indptr, r.indices,
-                   static_cast<const T*>(r.values), upper, zero_lower, Num<T>::make(alpha[0], alpha[1]),
+                   l.indptr, l.indices, static_cast<const T*>(l.values), upper ? l.pos : nullptr, r.indptr,
+                   r.indices, static_cast<const T*>(r.values), upper, zero_lower, Num<T>::make(alpha[0], alpha[1]),
                    Num<T>::make(beta[0], beta[1]), static_cast<T*>(dC), ldc, col_major);
         return SDB_STATUS_SUCCESS;
     });
@@ -698,8 +789,8 @@ sdb_status sdb_syrk(int op, const sdb_mat* A, sdb_mat** C) {
     Context* ctx;
     SDB_TRY(get_context(&ctx));
     CsrView a, at;
-    SDB_TRY(csr_view(ctx, A, false, &a));
-    SDB_TRY(csr_view(ctx, A, true, &at));
+    SDB_TRY(csr_view(ctx, A, false, &a, true));
+    SDB_TRY(csr_view(ctx, A, true, &at, true));
     // op = TRANSPOSE: A^T A = (A^T) * A;  op = NON_TRANSPOSE: A A^T = A * (A^T)
     sdb_mat* c = nullptr;
     if (op == SDB_OP_TRANSPOSE) SDB_TRY(spgemm_device(ctx, at, a, A->dtype, true, &c));
@@ -767,8 +858,8 @@ static sdb_status syrkd_dev_impl(int op, const sdb_mat* A, const double* alpha, 
     Context* ctx;
     SDB_TRY(get_context(&ctx));
     CsrView a, at;
-    SDB_TRY(csr_view(ctx, A, false, &a));
-    SDB_TRY(csr_view(ctx, A, true, &at));
+    SDB_TRY(csr_view(ctx, A, false, &a, true));
+    SDB_TRY(csr_view(ctx, A, true, &at, true));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     if (s != ctx->stream) SDB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (op == SDB_OP_TRANSPOSE)

@@ -16,6 +16,8 @@
 // tile out of shared memory and release the stage through a second mbarrier.
 // Tensor cores are NOT used: fp32 parity (1e-5) rules out single-pass TF32 and
 // the kernel is HBM-bound with FFMA (see DESIGN.md §3 K2 for the measurement).
+#include <cstdlib>
+
 #include "common.h"
 #include "types.cuh"
 
@@ -23,7 +25,6 @@ namespace sdb {
 
 namespace {
 
-constexpr int kBsrStages = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -72,7 +73,7 @@ template <> struct Vec16<double> {
 
 // One CTA = one block row x CW columns.  Threads: (CW / VEC) column groups x 2 row halves;
 // each thread owns B/2 rows x VEC columns of the output tile.
-template <typename T, int B, int CW, bool COL_MAJOR_BLOCKS>
+template <typename T, int B, int CW, bool COL_MAJOR_BLOCKS, int kBsrStages>
 __global__ void __launch_bounds__(2 * CW / Vec16<T>::N)
     spmm_bsr_kernel(int64_t block_rows, const int64_t* __restrict__ bptr, const int32_t* __restrict__ bidx,
                     const T* __restrict__ bval, const T* __restrict__ X, int64_t ldx, int64_t n, T alpha, T beta,
@@ -193,9 +194,9 @@ __global__ void __launch_bounds__(2 * CW / Vec16<T>::N)
     }
 }
 
-template <typename T, int B, int CW>
-static sdb_status launch_bsr(cudaStream_t s, const sdb_mat* a, const T* X, int64_t ldx, int64_t n, T alpha, T beta,
-                             T* Y, int64_t ldy) {
+template <typename T, int B, int CW, int kBsrStages>
+static sdb_status launch_bsr_s(cudaStream_t s, const sdb_mat* a, const T* X, int64_t ldx, int64_t n, T alpha, T beta,
+                               T* Y, int64_t ldy) {
     constexpr int VEC = Vec16<T>::N;
     constexpr int kThreads = 2 * CW / VEC;
     const size_t smem = size_t(kBsrStages) * (B * B + B * CW) * sizeof(T) + 2 * kBsrStages * sizeof(uint64_t);
@@ -203,17 +204,33 @@ static sdb_status launch_bsr(cudaStream_t s, const sdb_mat* a, const T* X, int64
     SDB_REQUIRE(a->rows < (int64_t(1) << 31) && gy < 65536, SDB_STATUS_NOT_SUPPORTED, "spmm_bsr: grid too large");
     const dim3 grid(unsigned(a->rows), unsigned(gy));
     if (a->block_layout == SDB_LAYOUT_COL_MAJOR) {
-        SDB_CUDA(cudaFuncSetAttribute(spmm_bsr_kernel<T, B, CW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SDB_CUDA(cudaFuncSetAttribute(spmm_bsr_kernel<T, B, CW, true, kBsrStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem)));
-        SDB_LAUNCH((spmm_bsr_kernel<T, B, CW, true>), grid, kThreads, smem, s, a->rows, a->indptr, a->indices,
+        SDB_LAUNCH((spmm_bsr_kernel<T, B, CW, true, kBsrStages>), grid, kThreads, smem, s, a->rows, a->indptr, a->indices,
                    static_cast<const T*>(a->values), X, ldx, n, alpha, beta, Y, ldy);
     } else {
-        SDB_CUDA(cudaFuncSetAttribute(spmm_bsr_kernel<T, B, CW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SDB_CUDA(cudaFuncSetAttribute(spmm_bsr_kernel<T, B, CW, false, kBsrStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem)));
-        SDB_LAUNCH((spmm_bsr_kernel<T, B, CW, false>), grid, kThreads, smem, s, a->rows, a->indptr, a->indices,
+        SDB_LAUNCH((spmm_bsr_kernel<T, B, CW, false, kBsrStages>), grid, kThreads, smem, s, a->rows, a->indptr, a->indices,
                    static_cast<const T*>(a->values), X, ldx, n, alpha, beta, Y, ldy);
     }
     return SDB_STATUS_SUCCESS;
+}
+
+// Ring depth: short block rows (a handful of blocks) finish before a deep ring pays off and a shallow
+// ring lets more CTAs share the SM; long block rows want the deeper prefetch.
+template <typename T, int B, int CW>
+static sdb_status launch_bsr(cudaStream_t s, const sdb_mat* a, const T* X, int64_t ldx, int64_t n, T alpha, T beta,
+                             T* Y, int64_t ldy) {
+    static const int forced = [] {
+        const char* e = getenv("SDB_BSR_STAGES");
+        return e ? atoi(e) : 0;
+    }();
+    const double mean_blocks = a->rows > 0 ? double(a->nnz) / double(a->rows) : 0.0;
+    const int stages = forced ? forced : (mean_blocks <= 6.0 ? 2 : 4);
+    if (stages <= 2) return launch_bsr_s<T, B, CW, 2>(s, a, X, ldx, n, alpha, beta, Y, ldy);
+    if (stages == 3) return launch_bsr_s<T, B, CW, 3>(s, a, X, ldx, n, alpha, beta, Y, ldy);
+    return launch_bsr_s<T, B, CW, 4>(s, a, X, ldx, n, alpha, beta, Y, ldy);
 }
 
 template <typename T, int B>

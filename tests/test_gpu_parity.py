@@ -534,6 +534,31 @@ def test_gram_dense(dtype, aat):
     assert cs.rel_err(got2[iu], want2[iu], (bound + 14.0)[iu]) <= cs.TOL[np.dtype(dtype)]
 
 
+@pytest.mark.parametrize("aat", [False, True])
+def test_gram_unsorted_rows_and_duplicate_entries(aat):
+    """Triangular products start each R-row walk at the diagonal only when every row is strictly
+    ascending; shuffled rows and duplicate (unsummed) entries must take the plain filtered walk."""
+    m1, _ = _pair(np.float64)
+    rng = np.random.default_rng(3)
+    shuffled = m1.copy()
+    for i in range(shuffled.shape[0]):
+        s0, e0 = shuffled.indptr[i], shuffled.indptr[i + 1]
+        p = rng.permutation(e0 - s0)
+        shuffled.indices[s0:e0] = shuffled.indices[s0:e0][p]
+        shuffled.data[s0:e0] = shuffled.data[s0:e0][p]
+    shuffled.has_sorted_indices = False
+    dup = sp.csr_matrix((np.concatenate([m1.data, m1.data[:50]]), np.concatenate([m1.indices, m1.indices[:50]]),
+                         np.concatenate([m1.indptr[:1], m1.indptr[1:] + 50])), shape=m1.shape)
+    dup.indices[: m1.indptr[1] + 50] = np.concatenate([m1.indices[: m1.indptr[1]], m1.indices[:50]])
+    for a in (shuffled, dup):
+        ref = sp.csr_matrix(a.toarray())  # canonical copy: duplicates summed, sorted
+        want = orc.np_gram_upper(ref, aat=aat)
+        got = sdb.gram_matrix_mkl(a, transpose=aat, dense=True)
+        assert np.abs(got - want).max() <= 1e-10
+        got_s = sdb.gram_matrix_mkl(a, transpose=aat, reorder_output=True)
+        assert np.abs(got_s.toarray() - want).max() <= 1e-10
+
+
 def test_gram_errors():
     m1, _ = _pair(np.float64)
     with pytest.raises(ValueError):
