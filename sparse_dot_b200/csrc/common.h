@@ -170,6 +170,11 @@ struct sdb_mat {
     // index i inside line k of the companion.  Valid only while strict_sorted == 1.
     int32_t* pos;
     int strict_sorted;  // 0 unknown, 1 every line strictly ascending (no duplicates), -1 not
+    // Optional column-slab index for the L2-tiled SpMM (spmm_slab.cu): slab_off[s * lines + r] is the
+    // offset, inside line r, of its first entry with index >= s * slab_width (s = 0 .. slab_count).
+    int32_t* slab_off;
+    int slab_count;
+    int64_t slab_width;
 };
 
 namespace sdb {
@@ -197,6 +202,8 @@ struct CsrView {
     // (nullptr when not requested / not available).  A triangular product L * L^T restricted to
     // col >= row starts its walk of row k of L^T there instead of at the row's first entry.
     const int32_t* pos = nullptr;
+    // the handle whose arrays these are (nullptr for ad-hoc views): lets kernels cache per-matrix indexes
+    sdb_mat* owner = nullptr;
 };
 sdb_status csr_view(Context* ctx, const sdb_mat* m, bool transpose, CsrView* v, bool want_pos = false);
 sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indptr, int32_t* indices,
@@ -214,6 +221,12 @@ sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int d
 sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a, const double* alpha,
                        const double* beta, int layout, const void* dX, int64_t n, int64_t ldx,
                        void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy);
+// L2-tiled SpMM (spmm_slab.cu): returns SDB_STATUS_NOT_SUPPORTED when the call does not qualify.
+bool spmm_slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx);
+sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a,
+                            const double* alpha, const double* beta, const void* dX, int64_t n, int64_t ldx,
+                            void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy);
+sdb_status ensure_strict_flag(Context* ctx, sdb_mat* m);
 // Native BSR x dense kernel (spmm_bsr.cu): availability test + launch.
 bool spmm_bsr_supported(const sdb_mat* a, int op, int layout, const void* dX, int64_t n, int64_t ldx, const void* dY,
                         int64_t ldy);

@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) strict_rows_kernel(int64_t rows, const in
 }
 
 // every line strictly ascending (sorted, no duplicate index)?  cached on the handle
-static sdb_status ensure_strict_flag(Context* ctx, sdb_mat* m) {
+sdb_status ensure_strict_flag(Context* ctx, sdb_mat* m) {
     if (m->strict_sorted != 0) return SDB_STATUS_SUCCESS;
     cudaStream_t s = ctx->stream;
     const int64_t lines = major_dim(m);
@@ -576,6 +576,7 @@ sdb_status csr_view(Context* ctx, const sdb_mat* m_in, bool transpose, CsrView* 
     }
     if (stored_is_transposed == transpose) {
         if (want_pos && m->transposed && m->transposed->pos) v->pos = m->pos;
+        v->owner = m;
         v->rows = major_dim(m);
         v->cols = minor_dim(m);
         v->nnz = m->nnz;
@@ -585,8 +586,9 @@ sdb_status csr_view(Context* ctx, const sdb_mat* m_in, bool transpose, CsrView* 
         return SDB_STATUS_SUCCESS;
     }
     if (!m->transposed) SDB_TRY(transpose_compressed(ctx, m, &m->transposed));
-    const sdb_mat* t = m->transposed;
+    sdb_mat* t = m->transposed;
     if (want_pos) v->pos = t->pos;
+    v->owner = t;
     v->rows = t->rows;
     v->cols = t->cols;
     v->nnz = t->nnz;
@@ -622,6 +624,11 @@ sdb_status sdb_order(sdb_mat* m) {
     if (m->pos) {
         cudaFreeAsync(m->pos, ctx->stream);
         m->pos = nullptr;
+    }
+    if (m->slab_off) {
+        cudaFreeAsync(m->slab_off, ctx->stream);
+        m->slab_off = nullptr;
+        m->slab_count = 0;
     }
     m->strict_sorted = 0;
     SDB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -52,9 +52,11 @@ void free_handle(sdb_mat* m) {
         if (m->indices) cudaFreeAsync(m->indices, s);
         if (m->values) cudaFreeAsync(m->values, s);
     }
-    if (m->pos) {
+    if (m->pos || m->slab_off) {
         Context* ctx = nullptr;
-        cudaFreeAsync(m->pos, get_context(&ctx) == SDB_STATUS_SUCCESS ? ctx->stream : nullptr);
+        cudaStream_t fs = get_context(&ctx) == SDB_STATUS_SUCCESS ? ctx->stream : nullptr;
+        if (m->pos) cudaFreeAsync(m->pos, fs);
+        if (m->slab_off) cudaFreeAsync(m->slab_off, fs);
     }
     m->magic = 0;
     free(m);

@@ -690,7 +690,9 @@ sdb_status spgemm_dense_device(Context* ctx, cudaStream_t s, const CsrView& l, c
         const char* e = getenv("SDB_DENSE_MODE");
         return e ? atoi(e) : 0;  // 1 = shared-memory tiles, 2 = global reductions
     }();
-    const bool use_red = forced_mode ? forced_mode == 2 : size_t(n) * dtype_size(dtype) > size_t(64) * 1024;
+    // measured (profiles/r1_logs/dense_modes.log): one shared-memory tile beats global reductions 1.8x at
+    // n = 10k; once a row needs several tiles (n = 100k fp32) the single-pass global variant wins 1.3x
+    const bool use_red = forced_mode ? forced_mode == 2 : size_t(n) * dtype_size(dtype) > size_t(200) * 1024;
     if (use_red) {
         return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
             SDB_LAUNCH(spgemm_dense_red_kernel<T>, unsigned(m), 1024, 0, s, n, l.indptr, l.indices,

@@ -315,7 +315,6 @@ static sdb_status spmm_rowmajor(cudaStream_t s, const CsrView& a, bool conj_a, c
 sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a, const double* alpha,
                        const double* beta, int layout, const void* dX, int64_t n, int64_t ldx,
                        void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy) {
-    (void)ctx;
     SDB_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && self >= 0 && self < n_peers, SDB_STATUS_INVALID_VALUE,
                 "spmm: bad peer configuration (%d peers, self %d)", n_peers, self);
     if (a.rows == 0 || n == 0) return SDB_STATUS_SUCCESS;
@@ -328,6 +327,16 @@ sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype
     }
     if (layout == SDB_LAYOUT_ROW_MAJOR) {
         SDB_REQUIRE(ldx >= n && ldy >= n, SDB_STATUS_INVALID_VALUE, "spmm: leading dimension smaller than n");
+        // panels far larger than L2: the slab-tiled kernel (spmm_slab.cu) when the shape qualifies
+        if (spmm_slab_wanted(a, dtype, n, ldx) && aligned16(dX) && (ldy * int64_t(dtype_size(dtype))) % 16 == 0) {
+            bool ok = true;
+            for (int q = 0; q < n_peers; ++q) ok = ok && aligned16(dY_peers[q]);
+            if (ok) {
+                const sdb_status st = spmm_slab_device(ctx, s, a, dtype, conj_a, alpha, beta, dX, n, ldx, dY_peers,
+                                                       n_peers, self, row0, ldy);
+                if (st != SDB_STATUS_NOT_SUPPORTED) return st;
+            }
+        }
         return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
             return spmm_rowmajor<T>(s, a, conj_a, alpha, beta, dX, n, ldx, dY_peers, n_peers, self, row0, ldy);
         });

@@ -1,0 +1,286 @@
+// spmm_slab.cu — L2-tiled CSR x dense SpMM for panels much larger than the L2 cache.
+//
+// The row-gather kernel (spmm.cu) reads one n-wide row of X per stored entry; when X is several
+// times the 126 MB L2 and the columns are scattered, ~85 % of those gathers come from HBM and the
+// kernel sits on the DRAM roofline at ~22 GB of traffic for a problem whose unique bytes are
+// ~2 GB (profiles/README.md).  This kernel cuts the traffic instead of chasing bandwidth:
+//
+//   * the columns are cut into S slabs of W rows of X, W chosen so that one slab (W * n * sv
+//     bytes) stays L2-resident;
+//   * a persistent grid of one CTA per SM walks row blocks; every warp owns 32 rows whose
+//     accumulators live in SHARED MEMORY (32 x n x sv bytes per warp) for the whole sweep;
+//   * all CTAs sweep the slabs in the same order, so at any moment the whole chip gathers from
+//     the same L2-resident slab: X is read from HBM once per wave of row blocks
+//     (rows / (SMs * rows per CTA) times) instead of once per stored entry;
+//   * per slab a warp flattens the entries of its 32 rows that fall into the slab (a per-row
+//     offset table built once per matrix and cached on the handle gives the segment bounds),
+//     issues the X-row gathers 8 at a time and adds each row's partial sum into shared memory once.
+//
+// The bound moves from DRAM (22 GB) to L2 bandwidth (every stored entry still pulls n * sv bytes
+// from L2 into an SM).  Requirements: row-major panels, n * sv = 512 bytes per X row (one 16-byte
+// pack per lane), rows strictly ascending (the slab table is a binary search per row and slab).
+#include <cstdlib>
+
+#include "common.h"
+#include "types.cuh"
+
+namespace sdb {
+
+namespace {
+
+constexpr int kSlabWarps = 13;               // 13 x 32 rows x 512 B = 208 KB of accumulators per CTA
+constexpr int kSlabRowsPerCta = kSlabWarps * 32;
+constexpr int kSlabUnroll = 8;
+constexpr int kSlabMaxPeers = 8;
+
+template <typename T> struct SlabPeers {
+    T* y[kSlabMaxPeers];
+};
+
+// off[s * rows + r] = number of entries of row r with column < s * width   (s = 0 .. S)
+__global__ void __launch_bounds__(256) slab_offsets_kernel(int64_t rows, const int64_t* __restrict__ indptr,
+                                                           const int32_t* __restrict__ indices, int S,
+                                                           int64_t width, int32_t* __restrict__ off) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const int64_t b = indptr[r];
+    const int len = int(indptr[r + 1] - b);
+    for (int s = lane; s <= S; s += 32) {
+        const int64_t key = int64_t(s) * width;  // first entry with column >= key
+        int lo = 0, hi = len;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (int64_t(indices[b + mid]) < key) lo = mid + 1;
+            else hi = mid;
+        }
+        off[int64_t(s) * rows + r] = s == S ? len : lo;
+    }
+}
+
+template <typename T> struct alignas(16) Pack16 {
+    static constexpr int N = 16 / int(sizeof(T));
+    T v[N];
+};
+
+template <typename T> __device__ __forceinline__ Pack16<T> ldg16(const T* p) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    Pack16<T> r;
+    *reinterpret_cast<float4*>(&r) = q;
+    return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kSlabWarps * 32, 1)
+    spmm_slab_kernel(int64_t rows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                     const T* __restrict__ values, bool conj_a, const int32_t* __restrict__ slab_off, int S,
+                     const T* __restrict__ X, int64_t ldx, T alpha, T beta, T* __restrict__ y_self,
+                     SlabPeers<T> peers, int n_peers, int self, int64_t row0, int64_t ldy) {
+    constexpr int VEC = Pack16<T>::N;
+    constexpr unsigned kFull = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // this warp's accumulators: [32 rows][32 lanes] packs of 16 bytes
+    Pack16<T>* acc = reinterpret_cast<Pack16<T>*>(smem_raw) + warp * 32 * 32;
+    const T* xlane = X + lane * VEC;
+    const int64_t n_blocks = (rows + kSlabRowsPerCta - 1) / kSlabRowsPerCta;
+
+    for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) {
+        const int64_t row_base = rb * kSlabRowsPerCta + int64_t(warp) * 32;
+        Pack16<T> zero;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) zero.v[i] = Num<T>::zero();
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) acc[r * 32 + lane] = zero;
+        __syncwarp();
+
+        const int64_t my_row = row_base + lane;
+        const bool valid = my_row < rows;
+        const int64_t rstart = valid ? indptr[my_row] : 0;
+        int off_prev = 0;  // entries with column < 0
+
+        for (int s = 0; s < S; ++s) {
+            const int off_next = valid ? __ldg(slab_off + int64_t(s + 1) * rows + my_row) : off_prev;
+            const int cnt = off_next - off_prev;      // this row's entries inside slab s
+            const int64_t seg = rstart + off_prev;    // where they start
+            off_prev = off_next;
+            // inclusive prefix of cnt over the 32 rows of the warp
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const int total = __shfl_sync(kFull, incl, 31);
+            if (total == 0) continue;
+
+            Pack16<T> cur = zero;
+            int cur_row = -1;
+            for (int f0 = 0; f0 < total; f0 += 32) {
+                // flat entry f0 + lane: find its row (first row whose inclusive prefix exceeds it)
+                const int f = f0 + lane;
+                int lo = 0, hi = 31;
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const int mid = (lo + hi) >> 1;
+                    const int pm = __shfl_sync(kFull, incl, mid);
+                    if (f >= pm) lo = mid + 1;
+                    else hi = mid;
+                }
+                const int my_r = lo;  // valid when f < total
+                const int r_incl = __shfl_sync(kFull, incl, my_r);
+                const int r_cnt = __shfl_sync(kFull, cnt, my_r);
+                const int64_t r_seg = __shfl_sync(kFull, seg, my_r);
+                int32_t c = 0;
+                T v = Num<T>::zero();
+                if (f < total) {
+                    const int64_t p = r_seg + (f - (r_incl - r_cnt));
+                    c = __ldg(indices + p);
+                    v = ldg(values + p);
+                    if (conj_a) v = conj_(v);
+                }
+                const int batch = min(32, total - f0);
+                for (int u0 = 0; u0 < batch; u0 += kSlabUnroll) {
+                    Pack16<T> x[kSlabUnroll];
+                    T a[kSlabUnroll];
+                    int rr[kSlabUnroll];
+#pragma unroll
+                    for (int u = 0; u < kSlabUnroll; ++u) {
+                        const int src = (u0 + u) & 31;
+                        const int32_t cj = __shfl_sync(kFull, c, src);
+                        a[u] = shfl(kFull, v, src, 32);
+                        rr[u] = __shfl_sync(kFull, my_r, src);
+                        if (u0 + u < batch) x[u] = ldg16<T>(xlane + int64_t(cj) * ldx);
+                        else x[u] = zero;
+                    }
+#pragma unroll
+                    for (int u = 0; u < kSlabUnroll; ++u) {
+                        if (u0 + u < batch) {  // warp-uniform
+                            if (rr[u] != cur_row) {
+                                if (cur_row >= 0) {
+                                    Pack16<T> t = acc[cur_row * 32 + lane];
+#pragma unroll
+                                    for (int i = 0; i < VEC; ++i) t.v[i] = add(t.v[i], cur.v[i]);
+                                    acc[cur_row * 32 + lane] = t;
+                                }
+                                cur = zero;
+                                cur_row = rr[u];
+                            }
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) cur.v[i] = madd(a[u], x[u].v[i], cur.v[i]);
+                        }
+                    }
+                }
+            }
+            if (cur_row >= 0) {
+                Pack16<T> t = acc[cur_row * 32 + lane];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) t.v[i] = add(t.v[i], cur.v[i]);
+                acc[cur_row * 32 + lane] = t;
+            }
+        }
+        __syncwarp();
+
+        // epilogue: y = alpha * acc + beta * y, one 512-byte row per iteration
+        const bool beta_zero = Num<T>::is_zero(beta);
+        const int live_rows = int(min(int64_t(32), rows - row_base));
+        for (int r = 0; r < live_rows; ++r) {
+            const int64_t o = (row0 + row_base + r) * ldy + lane * VEC;
+            const Pack16<T> t = acc[r * 32 + lane];
+            Pack16<T> out;
+            if (beta_zero) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) out.v[i] = mul(alpha, t.v[i]);
+            } else {
+                Pack16<T> old;
+                *reinterpret_cast<float4*>(&old) = *reinterpret_cast<const float4*>(y_self + o);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) out.v[i] = madd(alpha, t.v[i], mul(beta, old.v[i]));
+            }
+            *reinterpret_cast<float4*>(y_self + o) = *reinterpret_cast<const float4*>(&out);
+            if (n_peers > 1) {
+#pragma unroll
+                for (int q = 0; q < kSlabMaxPeers; ++q)
+                    if (q < n_peers && q != self)
+                        *reinterpret_cast<float4*>(peers.y[q] + o) = *reinterpret_cast<const float4*>(&out);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+size_t slab_target_bytes() {
+    static const size_t v = [] {
+        const char* e = getenv("SDB_SLAB_MB");
+        return size_t(e ? atoi(e) : 24) << 20;
+    }();
+    return v;
+}
+
+int slab_mode() {  // 0 = automatic, 1 = never, 2 = whenever the shape allows
+    static const int v = [] {
+        const char* e = getenv("SDB_SLAB");
+        return e ? atoi(e) : 0;
+    }();
+    return v;
+}
+
+}  // namespace
+
+bool spmm_slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx) {
+    if (slab_mode() == 1 || a.owner == nullptr) return false;
+    if (dtype != SDB_F32 && dtype != SDB_F64) return false;
+    const size_t sv = dtype_size(dtype);
+    if (size_t(n) * sv != 512 || ldx != n) return false;
+    if (a.owner->strict_sorted == -1) return false;
+    if (slab_mode() == 2) return a.rows > 0 && a.nnz > 0;
+    // worth it only when X is several L2s large and there is enough work to fill the persistent grid
+    const size_t x_bytes = size_t(a.cols) * size_t(n) * sv;
+    return x_bytes > (size_t(256) << 20) && a.rows >= 8 * int64_t(kSlabRowsPerCta) * 148 / 8 && a.nnz > a.rows * 8;
+}
+
+sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a,
+                            const double* alpha, const double* beta, const void* dX, int64_t n, int64_t ldx,
+                            void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy) {
+    sdb_mat* m = a.owner;
+    SDB_REQUIRE(m != nullptr, SDB_STATUS_NOT_SUPPORTED, "spmm_slab: ad-hoc view");
+    if (m->strict_sorted == 0) {
+        // the check runs on the library stream; the caller's stream must not race with it
+        SDB_TRY(ensure_strict_flag(ctx, m));
+    }
+    if (m->strict_sorted != 1) return SDB_STATUS_NOT_SUPPORTED;
+    const size_t sv = dtype_size(dtype);
+    int64_t width = std::max<int64_t>(1024, int64_t(slab_target_bytes() / (size_t(n) * sv)));
+    const int S = int((a.cols + width - 1) / width);
+    if (S < 2 || S > 4096) return SDB_STATUS_NOT_SUPPORTED;
+    if (m->slab_off == nullptr || m->slab_count != S || m->slab_width != width) {
+        cudaStream_t ls = ctx->stream;
+        if (m->slab_off) cudaFreeAsync(m->slab_off, ls);
+        m->slab_off = nullptr;
+        SDB_TRY(dev_alloc(reinterpret_cast<void**>(&m->slab_off), size_t(S + 1) * size_t(a.rows) * 4, ls));
+        SDB_LAUNCH(slab_offsets_kernel, unsigned((a.rows * 32 + 255) / 256), 256, 0, ls, a.rows, a.indptr, a.indices,
+                   S, width, m->slab_off);
+        m->slab_count = S;
+        m->slab_width = width;
+        if (s != ls) SDB_CUDA(cudaStreamSynchronize(ls));
+    }
+    const size_t smem = size_t(kSlabRowsPerCta) * 512;
+    const int64_t n_blocks = (a.rows + kSlabRowsPerCta - 1) / kSlabRowsPerCta;
+    const unsigned grid = unsigned(std::min<int64_t>(n_blocks, ctx->sm_count));
+    return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
+        if constexpr (sizeof(T) > 8) {
+            return SDB_STATUS_NOT_SUPPORTED;
+        } else {
+            SlabPeers<T> peers;
+            for (int q = 0; q < kSlabMaxPeers; ++q) peers.y[q] = q < n_peers ? static_cast<T*>(dY_peers[q]) : nullptr;
+            SDB_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            SDB_LAUNCH(spmm_slab_kernel<T>, grid, kSlabWarps * 32, smem, s, a.rows, a.indptr, a.indices,
+                       static_cast<const T*>(a.values), conj_a, m->slab_off, S, static_cast<const T*>(dX), ldx,
+                       Num<T>::make(alpha[0], alpha[1]), Num<T>::make(beta[0], beta[1]), peers.y[self], peers, n_peers,
+                       self, row0, ldy);
+            return SDB_STATUS_SUCCESS;
+        }
+    });
+}
+
+}  // namespace sdb
