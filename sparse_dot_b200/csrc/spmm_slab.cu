@@ -28,8 +28,7 @@ namespace sdb {
 
 namespace {
 
-constexpr int kSlabWarps = 13;               // 13 x 32 rows x 512 B = 208 KB of accumulators per CTA
-constexpr int kSlabRowsPerCta = kSlabWarps * 32;
+constexpr int kSlabRowsPerCta = 416;         // 416 rows x 512 B = 208 KB of accumulators per CTA
 constexpr int kSlabUnroll = 8;
 constexpr int kSlabMaxPeers = 8;
 
@@ -70,8 +69,9 @@ template <typename T> __device__ __forceinline__ Pack16<T> ldg16(const T* p) {
     return r;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kSlabWarps * 32, 1)
+// RPW rows per warp: fewer rows per warp = more warps per CTA (416 / RPW) = more independent chains
+template <typename T, int RPW>
+__global__ void __launch_bounds__((kSlabRowsPerCta / RPW) * 32, 1)
     spmm_slab_kernel(int64_t rows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                      const T* __restrict__ values, bool conj_a, const int32_t* __restrict__ slab_off, int S,
                      const T* __restrict__ X, int64_t ldx, T alpha, T beta, T* __restrict__ y_self,
@@ -80,27 +80,29 @@ __global__ void __launch_bounds__(kSlabWarps * 32, 1)
     constexpr unsigned kFull = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // this warp's accumulators: [32 rows][32 lanes] packs of 16 bytes
-    Pack16<T>* acc = reinterpret_cast<Pack16<T>*>(smem_raw) + warp * 32 * 32;
+    // this warp's accumulators: [RPW rows][32 lanes] packs of 16 bytes
+    Pack16<T>* acc = reinterpret_cast<Pack16<T>*>(smem_raw) + warp * RPW * 32;
     const T* xlane = X + lane * VEC;
     const int64_t n_blocks = (rows + kSlabRowsPerCta - 1) / kSlabRowsPerCta;
 
     for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) {
-        const int64_t row_base = rb * kSlabRowsPerCta + int64_t(warp) * 32;
+        const int64_t row_base = rb * kSlabRowsPerCta + int64_t(warp) * RPW;
         Pack16<T> zero;
 #pragma unroll
         for (int i = 0; i < VEC; ++i) zero.v[i] = Num<T>::zero();
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) acc[r * 32 + lane] = zero;
+        for (int r = 0; r < RPW; ++r) acc[r * 32 + lane] = zero;
         __syncwarp();
 
         const int64_t my_row = row_base + lane;
-        const bool valid = my_row < rows;
+        const bool valid = lane < RPW && my_row < rows;
         const int64_t rstart = valid ? indptr[my_row] : 0;
         int off_prev = 0;  // entries with column < 0
 
+        int off_ahead = valid ? __ldg(slab_off + rows + my_row) : 0;  // boundary of slab 0 | 1, loaded one slab ahead
         for (int s = 0; s < S; ++s) {
-            const int off_next = valid ? __ldg(slab_off + int64_t(s + 1) * rows + my_row) : off_prev;
+            const int off_next = off_ahead;
+            if (s + 1 < S && valid) off_ahead = __ldg(slab_off + int64_t(s + 2) * rows + my_row);
             const int cnt = off_next - off_prev;      // this row's entries inside slab s
             const int64_t seg = rstart + off_prev;    // where they start
             off_prev = off_next;
@@ -114,12 +116,10 @@ __global__ void __launch_bounds__(kSlabWarps * 32, 1)
             const int total = __shfl_sync(kFull, incl, 31);
             if (total == 0) continue;
 
-            Pack16<T> cur = zero;
-            int cur_row = -1;
-            for (int f0 = 0; f0 < total; f0 += 32) {
-                // flat entry f0 + lane: find its row (first row whose inclusive prefix exceeds it)
+            // (column, value, row) of flat entry f0 + lane of this slab
+            auto fetch = [&](int f0, int32_t& c_out, T& v_out, int& r_out) {
                 const int f = f0 + lane;
-                int lo = 0, hi = 31;
+                int lo = 0, hi = 31;  // first row whose inclusive prefix exceeds f
 #pragma unroll
                 for (int it = 0; it < 5; ++it) {
                     const int mid = (lo + hi) >> 1;
@@ -127,36 +127,48 @@ __global__ void __launch_bounds__(kSlabWarps * 32, 1)
                     if (f >= pm) lo = mid + 1;
                     else hi = mid;
                 }
-                const int my_r = lo;  // valid when f < total
-                const int r_incl = __shfl_sync(kFull, incl, my_r);
-                const int r_cnt = __shfl_sync(kFull, cnt, my_r);
-                const int64_t r_seg = __shfl_sync(kFull, seg, my_r);
-                int32_t c = 0;
-                T v = Num<T>::zero();
+                r_out = lo;  // meaningful when f < total
+                const int r_incl = __shfl_sync(kFull, incl, lo);
+                const int r_cnt = __shfl_sync(kFull, cnt, lo);
+                const int64_t r_seg = __shfl_sync(kFull, seg, lo);
+                c_out = 0;
+                v_out = Num<T>::zero();
                 if (f < total) {
                     const int64_t p = r_seg + (f - (r_incl - r_cnt));
-                    c = __ldg(indices + p);
-                    v = ldg(values + p);
-                    if (conj_a) v = conj_(v);
+                    c_out = __ldg(indices + p);
+                    v_out = ldg(values + p);
+                    if (conj_a) v_out = conj_(v_out);
                 }
+            };
+
+            Pack16<T> cur = zero;
+            int cur_row = -1;
+            int32_t c, c_nx = 0;
+            T v, v_nx = Num<T>::zero();
+            int my_r, my_r_nx = 0;
+            fetch(0, c, v, my_r);
+            for (int f0 = 0; f0 < total; f0 += 32) {
+                // the next chunk's entries are requested before this chunk's gathers are consumed
+                if (f0 + 32 < total) fetch(f0 + 32, c_nx, v_nx, my_r_nx);
                 const int batch = min(32, total - f0);
+                // bit u set = flat entry u of this chunk starts a new row (relative to the entry before it)
+                const int prev_r = __shfl_up_sync(kFull, my_r, 1);
+                const unsigned starts = __ballot_sync(kFull, lane == 0 ? my_r != cur_row : my_r != prev_r);
                 for (int u0 = 0; u0 < batch; u0 += kSlabUnroll) {
                     Pack16<T> x[kSlabUnroll];
                     T a[kSlabUnroll];
-                    int rr[kSlabUnroll];
 #pragma unroll
                     for (int u = 0; u < kSlabUnroll; ++u) {
                         const int src = (u0 + u) & 31;
                         const int32_t cj = __shfl_sync(kFull, c, src);
                         a[u] = shfl(kFull, v, src, 32);
-                        rr[u] = __shfl_sync(kFull, my_r, src);
                         if (u0 + u < batch) x[u] = ldg16<T>(xlane + int64_t(cj) * ldx);
                         else x[u] = zero;
                     }
 #pragma unroll
                     for (int u = 0; u < kSlabUnroll; ++u) {
                         if (u0 + u < batch) {  // warp-uniform
-                            if (rr[u] != cur_row) {
+                            if ((starts >> (u0 + u)) & 1u) {
                                 if (cur_row >= 0) {
                                     Pack16<T> t = acc[cur_row * 32 + lane];
 #pragma unroll
@@ -164,13 +176,16 @@ __global__ void __launch_bounds__(kSlabWarps * 32, 1)
                                     acc[cur_row * 32 + lane] = t;
                                 }
                                 cur = zero;
-                                cur_row = rr[u];
+                                cur_row = __shfl_sync(kFull, my_r, u0 + u);
                             }
 #pragma unroll
                             for (int i = 0; i < VEC; ++i) cur.v[i] = madd(a[u], x[u].v[i], cur.v[i]);
                         }
                     }
                 }
+                c = c_nx;
+                v = v_nx;
+                my_r = my_r_nx;
             }
             if (cur_row >= 0) {
                 Pack16<T> t = acc[cur_row * 32 + lane];
@@ -183,7 +198,7 @@ __global__ void __launch_bounds__(kSlabWarps * 32, 1)
 
         // epilogue: y = alpha * acc + beta * y, one 512-byte row per iteration
         const bool beta_zero = Num<T>::is_zero(beta);
-        const int live_rows = int(min(int64_t(32), rows - row_base));
+        const int live_rows = int(max(int64_t(0), min(int64_t(RPW), rows - row_base)));
         for (int r = 0; r < live_rows; ++r) {
             const int64_t o = (row0 + row_base + r) * ldy + lane * VEC;
             const Pack16<T> t = acc[r * 32 + lane];
@@ -217,7 +232,7 @@ size_t slab_target_bytes() {
     return v;
 }
 
-int slab_mode() {  // 0 = automatic, 1 = never, 2 = whenever the shape allows
+int slab_mode() {  // 0 / 1 = off (default), 2 = whenever the shape allows
     static const int v = [] {
         const char* e = getenv("SDB_SLAB");
         return e ? atoi(e) : 0;
@@ -227,16 +242,48 @@ int slab_mode() {  // 0 = automatic, 1 = never, 2 = whenever the shape allows
 
 }  // namespace
 
+template <typename T, int RPW>
+static sdb_status launch_slab_rpw(cudaStream_t s, const CsrView& a, bool conj_a, const int32_t* slab_off, int S,
+                                  const T* X, int64_t ldx, T alpha, T beta, const SlabPeers<T>& peers, int n_peers,
+                                  int self, int64_t row0, int64_t ldy, unsigned grid, size_t smem) {
+    SDB_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<T, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    SDB_LAUNCH((spmm_slab_kernel<T, RPW>), grid, (kSlabRowsPerCta / RPW) * 32, smem, s, a.rows, a.indptr, a.indices,
+               static_cast<const T*>(a.values), conj_a, slab_off, S, X, ldx, alpha, beta, peers.y[self], peers,
+               n_peers, self, row0, ldy);
+    return SDB_STATUS_SUCCESS;
+}
+
+template <typename T>
+static sdb_status launch_slab(cudaStream_t s, const CsrView& a, bool conj_a, const int32_t* slab_off, int S,
+                              const T* X, int64_t ldx, T alpha, T beta, void* const* dY_peers, int n_peers, int self,
+                              int64_t row0, int64_t ldy, unsigned grid, size_t smem) {
+    static const int rpw = [] {
+        const char* e = getenv("SDB_SLAB_RPW");
+        return e ? atoi(e) : 13;
+    }();
+    SlabPeers<T> peers;
+    for (int q = 0; q < kSlabMaxPeers; ++q) peers.y[q] = q < n_peers ? static_cast<T*>(dY_peers[q]) : nullptr;
+    if (rpw == 32)
+        return launch_slab_rpw<T, 32>(s, a, conj_a, slab_off, S, X, ldx, alpha, beta, peers, n_peers, self, row0, ldy,
+                                      grid, smem);
+    if (rpw == 13)
+        return launch_slab_rpw<T, 13>(s, a, conj_a, slab_off, S, X, ldx, alpha, beta, peers, n_peers, self, row0, ldy,
+                                      grid, smem);
+    return launch_slab_rpw<T, 16>(s, a, conj_a, slab_off, S, X, ldx, alpha, beta, peers, n_peers, self, row0, ldy,
+                                  grid, smem);
+}
+
 bool spmm_slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx) {
     if (slab_mode() == 1 || a.owner == nullptr) return false;
     if (dtype != SDB_F32 && dtype != SDB_F64) return false;
     const size_t sv = dtype_size(dtype);
     if (size_t(n) * sv != 512 || ldx != n) return false;
     if (a.owner->strict_sorted == -1) return false;
-    if (slab_mode() == 2) return a.rows > 0 && a.nnz > 0;
-    // worth it only when X is several L2s large and there is enough work to fill the persistent grid
-    const size_t x_bytes = size_t(a.cols) * size_t(n) * sv;
-    return x_bytes > (size_t(256) << 20) && a.rows >= 8 * int64_t(kSlabRowsPerCta) * 148 / 8 && a.nnz > a.rows * 8;
+    // Measured on B200 (profiles/README.md, round 1c): on configs[1] this kernel cuts DRAM traffic from 22.2 GB to
+    // 10.1 GB as designed, but it becomes instruction-issue bound (68 % issue slots busy, IPC 2.7) at 3.99 ms
+    // against 3.54 ms for the row-gather kernel on the DRAM roofline — so it is opt-in (SDB_SLAB=2) until the
+    // per-entry instruction count comes down.
+    return slab_mode() == 2 && a.rows > 0 && a.nnz > 0;
 }
 
 sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a,
@@ -271,14 +318,9 @@ sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int 
         if constexpr (sizeof(T) > 8) {
             return SDB_STATUS_NOT_SUPPORTED;
         } else {
-            SlabPeers<T> peers;
-            for (int q = 0; q < kSlabMaxPeers; ++q) peers.y[q] = q < n_peers ? static_cast<T*>(dY_peers[q]) : nullptr;
-            SDB_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            SDB_LAUNCH(spmm_slab_kernel<T>, grid, kSlabWarps * 32, smem, s, a.rows, a.indptr, a.indices,
-                       static_cast<const T*>(a.values), conj_a, m->slab_off, S, static_cast<const T*>(dX), ldx,
-                       Num<T>::make(alpha[0], alpha[1]), Num<T>::make(beta[0], beta[1]), peers.y[self], peers, n_peers,
-                       self, row0, ldy);
-            return SDB_STATUS_SUCCESS;
+            return launch_slab<T>(s, a, conj_a, m->slab_off, S, static_cast<const T*>(dX), ldx,
+                                  Num<T>::make(alpha[0], alpha[1]), Num<T>::make(beta[0], beta[1]), dY_peers, n_peers,
+                                  self, row0, ldy, grid, smem);
         }
     });
 }
