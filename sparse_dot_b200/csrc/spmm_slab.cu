@@ -20,6 +20,7 @@
 // from L2 into an SM).  Requirements: row-major panels, n * sv = 512 bytes per X row (one 16-byte
 // pack per lane), rows strictly ascending (the slab table is a binary search per row and slab).
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.h"
 #include "types.cuh"
@@ -154,21 +155,22 @@ __global__ void __launch_bounds__((kSlabRowsPerCta / RPW) * 32, 1)
                 // bit u set = flat entry u of this chunk starts a new row (relative to the entry before it)
                 const int prev_r = __shfl_up_sync(kFull, my_r, 1);
                 const unsigned starts = __ballot_sync(kFull, lane == 0 ? my_r != cur_row : my_r != prev_r);
-                for (int u0 = 0; u0 < batch; u0 += kSlabUnroll) {
+                // one batch of kSlabUnroll gathers: loads first, then the FMAs with a row-change test per entry
+                auto run_batch = [&](int u0, auto full) {
+                    constexpr bool kFullBatch = decltype(full)::value;
                     Pack16<T> x[kSlabUnroll];
                     T a[kSlabUnroll];
 #pragma unroll
                     for (int u = 0; u < kSlabUnroll; ++u) {
-                        const int src = (u0 + u) & 31;
-                        const int32_t cj = __shfl_sync(kFull, c, src);
-                        a[u] = shfl(kFull, v, src, 32);
-                        if (u0 + u < batch) x[u] = ldg16<T>(xlane + int64_t(cj) * ldx);
-                        else x[u] = zero;
+                        const int32_t cj = __shfl_sync(kFull, c, u0 + u);
+                        a[u] = shfl(kFull, v, u0 + u, 32);
+                        if (kFullBatch || u0 + u < batch) x[u] = ldg16<T>(xlane + int64_t(cj) * ldx);
                     }
+                    const unsigned sb = starts >> u0;
 #pragma unroll
                     for (int u = 0; u < kSlabUnroll; ++u) {
-                        if (u0 + u < batch) {  // warp-uniform
-                            if ((starts >> (u0 + u)) & 1u) {
+                        if (kFullBatch || u0 + u < batch) {  // warp-uniform
+                            if (sb & (1u << u)) {
                                 if (cur_row >= 0) {
                                     Pack16<T> t = acc[cur_row * 32 + lane];
 #pragma unroll
@@ -182,6 +184,25 @@ __global__ void __launch_bounds__((kSlabRowsPerCta / RPW) * 32, 1)
                             for (int i = 0; i < VEC; ++i) cur.v[i] = madd(a[u], x[u].v[i], cur.v[i]);
                         }
                     }
+                };
+                int u0 = 0;
+                for (; u0 + kSlabUnroll <= batch; u0 += kSlabUnroll) run_batch(u0, std::true_type{});
+                for (; u0 < batch; ++u0) {  // ragged tail of the last chunk: one entry at a time
+                    const int32_t cj = __shfl_sync(kFull, c, u0);
+                    const T aj = shfl(kFull, v, u0, 32);
+                    const Pack16<T> xj = ldg16<T>(xlane + int64_t(cj) * ldx);
+                    if ((starts >> u0) & 1u) {
+                        if (cur_row >= 0) {
+                            Pack16<T> t = acc[cur_row * 32 + lane];
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) t.v[i] = add(t.v[i], cur.v[i]);
+                            acc[cur_row * 32 + lane] = t;
+                        }
+                        cur = zero;
+                        cur_row = __shfl_sync(kFull, my_r, u0);
+                    }
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) cur.v[i] = madd(aj, xj.v[i], cur.v[i]);
                 }
                 c = c_nx;
                 v = v_nx;
