@@ -170,6 +170,42 @@ def run_c4(m, n, per_row):
     return res
 
 
+def run_c5(rows, cols, per_row, n):
+    """configs[4], one GPU's shard: CSR(rows x cols, per_row nnz/row, fp32) x dense(cols x n), resident operands."""
+    a = cs.uniform_rows_csr(rows, cols, per_row, np.float32, seed=5)
+    x = np.random.default_rng(6).random((cols, n), dtype=np.float32)
+    res = {"config": "c5_shard", "rows": rows, "cols": cols, "nnz": int(a.nnz), "n": n}
+    ha, _, _ = H.create(a)
+    with ha:
+        d_x, d_y = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.sdb_dev_alloc(C.byref(d_x), x.nbytes), "alloc")
+        _lib.check(lib.sdb_dev_alloc(C.byref(d_y), rows * n * 4), "alloc")
+        try:
+            _lib.check(lib.sdb_memcpy(d_x, x.ctypes.data_as(C.c_void_p), x.nbytes, 1), "memcpy")
+            one, zero = _lib.scalar_pair(1.0), _lib.scalar_pair(0.0)
+            call = lambda: _lib.check(lib.sdb_spmm_dev(_lib.OP_N, one, ha.ref, _lib.LAYOUT_C, d_x, n, n, zero, d_y,
+                                                       n, None), "sdb_spmm_dev")
+            timed(call)
+            ms, _ = timed(call, reps=5)
+            res["spmm_ms"] = ms
+            g = a.nnz * 8 + a.nnz * n * 4 + rows * n * 4 + (rows + 1) * 8
+            res["gather_model_gbs"] = g / (ms * 1e-3) / 1e9
+            res["gflops"] = 2.0 * a.nnz * n / (ms * 1e-3) / 1e9
+            pick = np.sort(np.random.default_rng(0).choice(rows, size=16, replace=False))
+            want = a[pick].astype(np.float64) @ x.astype(np.float64)
+            worst = 0.0
+            for j, r in enumerate(pick):
+                got = np.empty(n, dtype=np.float32)
+                _lib.check(lib.sdb_memcpy(got.ctypes.data_as(C.c_void_p), C.c_void_p(d_y.value + int(r) * n * 4),
+                                          n * 4, 2), "memcpy")
+                worst = max(worst, float(np.max(np.abs(got - want[j]) / np.abs(want[j]))))
+            res["sampled_rows_max_rel_err"] = worst
+        finally:
+            lib.sdb_dev_free(d_x)
+            lib.sdb_dev_free(d_y)
+    return res
+
+
 def run_c5bsr(block_rows, blocks_per_row, b, n):
     """configs[4] BSR variant on 1 GPU: natively blocked matrix, dense b x b fp32 blocks, x dense (k x n)."""
     rng = np.random.default_rng(5)
@@ -236,6 +272,8 @@ def main():
             r = run_c3(args.scale, args.ef, not args.no_full_check)
         elif w == "c4":
             r = run_c4(args.gram_m, args.gram_n, 100)
+        elif w == "c5":
+            r = run_c5(1_000_000, 1_000_000, 64, 256)
         elif w == "c5bsr":
             r = run_c5bsr(args.bsr_block_rows, 4, 16, 256)
         else:

@@ -33,6 +33,19 @@ struct EventPool {
     }
 };
 
+// Declared AFTER the device buffers of a pipelined call, so it is destroyed BEFORE them: whatever way
+// the call leaves (including an early error return), all three streams have drained before the
+// buffers they use are handed back to the pool.
+struct StreamJoin {
+    cudaStream_t a, b, c;
+    ~StreamJoin() {
+        cudaStreamSynchronize(a);
+        cudaStreamSynchronize(b);
+        cudaStreamSynchronize(c);
+        cudaGetLastError();
+    }
+};
+
 int64_t index_at(const void* p, int bits, int64_t i) {
     return bits == 32 ? int64_t(static_cast<const int32_t*>(p)[i]) : static_cast<const int64_t*>(p)[i];
 }
@@ -77,6 +90,7 @@ extern "C" sdb_status sdb_spmm_csr_host(int64_t rows, int64_t cols, const void* 
     SDB_TRY(d_val.alloc(size_t(nnz) * es, s0));
     SDB_TRY(d_x.alloc(size_t(cols) * size_t(n) * es, s0));
     SDB_TRY(d_y.alloc(size_t(rows) * size_t(n) * es, s0));
+    StreamJoin join{s_up, s_dn, s0};
     cudaEvent_t e_start, e_alloc, e_end, e_last_up;
     SDB_TRY(pool.get(&e_start, true));
     SDB_TRY(pool.get(&e_alloc));
