@@ -226,6 +226,24 @@ def spot_check(plan, a, x, y0, steps, beta, n_rows=8):
     return {"rows_checked": int(n_rows), "max_rel_err": worst, "ok": bool(worst < 1e-5)}
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pin this rank to the CPU cores local to its GPU (NVML) BEFORE any host buffer is allocated, so
+    the page-locked arrays of the e2e leg are first-touched on the GPU's own NUMA node.  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -239,6 +257,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    local_cpus = bind_to_gpu_numa(local) if world > 1 else 0
     torch.cuda.set_device(local)
     lib = _lib.SDB.lib
     _lib.check(lib.sdb_set_device(local), "sdb_set_device")
@@ -319,7 +338,7 @@ def run_ours(args):
             "value": g1 * world / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3, "steps": e2e_steps,
             "h2d_bytes_per_step": int(a.data.nbytes + a.indices.nbytes + a.indptr.nbytes + x.nbytes + y0.nbytes),
             "d2h_bytes_per_step": int(y0.nbytes),
-            "host_memory": "pinned (sdb_host_alloc)",
+            "host_memory": "pinned (sdb_host_alloc)" + (f", rank bound to {local_cpus} GPU-local cores" if local_cpus else ""),
             "device_spans_ms": {"start_to_last_upload": phases[0], "kernel_sum": phases[1], "whole_call": phases[2]},
             "api": "sparse_dot_b200.dot_product_mkl(csr, ndarray, out=, out_scalar=) -> sdb_spmm_csr_host "
                    "(3-stream row-chunk pipeline: upload / kernel / download overlap)",

@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     set_debug_mode,
 )
 from ._lib import device_count, kernel_launches, last_timing_ms  # noqa: F401
+from .resident import ResidentCSR  # noqa: F401
 
 __all__ = [
     "dot_product_mkl",
@@ -25,4 +26,5 @@ __all__ = [
     "device_count",
     "kernel_launches",
     "last_timing_ms",
+    "ResidentCSR",
 ]

@@ -578,3 +578,87 @@ def test_gram_reduced_config4():
     want = orc.c_syrkd(a)
     assert np.all(got[np.tril_indices(2000, -1)] == 0)
     assert cs.rel_err(got, want, np.maximum(want, 0)) <= 1e-5
+
+
+# ===================================================== real-MKL golden vectors (tests/golden)
+def _gold(name):
+    import os
+
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+
+
+@pytest.mark.parametrize("dtype,tag", [(np.float32, "f32"), (np.float64, "f64")])
+def test_spmm_matches_mkl_golden(dtype, tag):
+    """The reference's own fixture through real oneMKL (oracle/gen_golden.py) vs the CUDA path."""
+    g = _gold(f"fixture_spmm_{tag}.npz")
+    m1, m2 = cs.fixture_pair(dtype)
+    b = m2.toarray()
+    tol = cs.TOL[np.dtype(dtype)]
+    bound = orc.value_bound(abs(m1), abs(b))
+    assert cs.rel_err(sdb.dot_product_mkl(m1, b), g["y"], bound) <= tol
+    got = sdb.dot_product_mkl(m1, b, out=np.ones((200, 100), dtype=dtype), out_scalar=3.0)
+    assert cs.rel_err(got, g["y_out3"], bound + 3.0) <= tol
+    x = np.ascontiguousarray(m1.toarray()[:, :50])
+    got = sdb.dot_product_mkl(x.T.copy(), m1).T  # (X^T A)^T = A^T X
+    assert cs.rel_err(got, g["yt"], orc.value_bound(abs(m1.T), abs(x))) <= tol
+
+
+def test_spmmd_gram_and_cancellation_match_mkl_golden():
+    m1, m2 = cs.fixture_pair(np.float64)
+    got = sdb.dot_product_mkl(m1, m2, dense=True)
+    assert cs.rel_err(got, _gold("fixture_spmmd.npz")["c"], orc.value_bound(abs(m1), abs(m2))) <= 1e-12
+    g = _gold("fixture_gram.npz")
+    for aat, key in ((False, "ata"), (True, "aat")):
+        c = sdb.gram_matrix_mkl(m1, transpose=aat, reorder_output=True)
+        assert np.array_equal(c.indptr, g[f"{key}_indptr"]) and np.array_equal(c.indices, g[f"{key}_indices"])
+        assert cs.rel_err(c.data, g[f"{key}_data"]) <= 1e-12
+    z = _gold("cancel_spgemm.npz")
+    a = sp.csr_matrix(np.array([[1.0, -1.0], [2.0, 0.0]]))
+    b = sp.csr_matrix(np.array([[1.0, 3.0], [1.0, 0.0]]))
+    c = sdb.dot_product_mkl(a, b, reorder_output=True)
+    assert np.array_equal(c.indptr, z["indptr"]) and np.array_equal(c.indices, z["indices"])
+    assert np.array_equal(c.data, z["data"])
+
+
+def test_config2_small_matches_mkl_golden():
+    g = _gold("c2_small_spmm_f32.npz")
+    a = cs.uniform_rows_csr(20_000, 20_000, 50, np.float32, seed=0)
+    x = np.random.default_rng(2).random((20_000, 128), dtype=np.float32)
+    y0 = np.random.default_rng(3).random((20_000, 128), dtype=np.float32)
+    y = sdb.dot_product_mkl(a, x, out=y0.copy(), out_scalar=0.5)
+    assert cs.rel_err(y[g["rows"]], g["y_rows"]) <= 1e-5
+    assert np.allclose(y.astype(np.float64).sum(axis=0), g["y_colsum"], rtol=1e-5)
+
+
+# ===================================================== device-resident operands (SURVEY §8f rank 3)
+def test_resident_operands():
+    import torch
+
+    m1, m2 = cs.fixture_pair(np.float32)
+    x = np.random.default_rng(0).random((300, 64), dtype=np.float32)
+    with sdb.ResidentCSR(m1) as a, sdb.ResidentCSR(m2) as b:
+        assert a.shape == (200, 300) and a.nnz == m1.nnz
+        want = orc.c_spmm(m1, x)
+        bound = orc.value_bound(abs(m1), abs(x))
+        for _ in range(3):  # repeated products, A uploaded once
+            assert cs.rel_err(a.dot(x), want, bound) <= 1e-5
+        got = a.dot(np.asfortranarray(x))
+        assert got.flags.f_contiguous and cs.rel_err(got, want, bound) <= 1e-5
+        xt = torch.from_numpy(x).cuda()
+        yt = torch.ones((200, 64), dtype=torch.float32, device="cuda")
+        a.dot_device(xt, yt, alpha=1.0, beta=3.0)
+        torch.cuda.synchronize()
+        assert cs.rel_err(yt.cpu().numpy(), want + 3.0, bound + 3.0) <= 1e-5
+        with a.matmat(b, reorder_output=True) as c:
+            got = c.to_scipy()
+            w = orc.c_spgemm(m1, m2, sort=True)
+            assert np.array_equal(got.indptr, w.indptr) and np.array_equal(got.indices, w.indices)
+            assert cs.rel_err(got.data, w.data) <= 1e-5
+        with a.gram(reorder_output=True) as g:
+            w = orc.c_syrk(m1, sort=True)
+            got = g.to_scipy()
+            assert np.array_equal(got.indices, w.indices) and cs.rel_err(got.data, w.data) <= 1e-5
+        with pytest.raises(ValueError):
+            a.dot(x.astype(np.float64))
+        with pytest.raises(ValueError):
+            a.dot(x[:100])
