@@ -82,7 +82,14 @@ template <> __device__ __forceinline__ Pack<cf32, 1> load_pack<cf32, 1>(const cf
 }
 
 template <typename T, int VEC> __device__ __forceinline__ void store_pack(T* p, const Pack<T, VEC>& a) {
-    *reinterpret_cast<Pack<T, VEC>*>(p) = a;
+    // Y is written once and not re-read by this kernel: streaming stores (evict-first)
+    if constexpr (sizeof(Pack<T, VEC>) == 16) {
+        __stcs(reinterpret_cast<float4*>(p), *reinterpret_cast<const float4*>(&a));
+    } else if constexpr (sizeof(Pack<T, VEC>) == 8) {
+        __stcs(reinterpret_cast<float2*>(p), *reinterpret_cast<const float2*>(&a));
+    } else {
+        *reinterpret_cast<Pack<T, VEC>*>(p) = a;
+    }
 }
 
 template <typename T, int VEC, int LANES, int UNROLL = kUnroll, int MINB = 1>
@@ -129,8 +136,9 @@ __global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
         int32_t c = 0;
         T v = Num<T>::zero();
         if (mine < len) {
-            c = __ldg(ci + mine);
-            v = ldg(cv + mine);
+            // A is streamed once: evict-first, so it does not push X rows out of L2
+            c = __ldcs(ci + mine);
+            v = ldcs(cv + mine);
             if (conj_a) v = conj_(v);
         }
         const int batch = min(LANES, maxlen - base);  // warp-uniform

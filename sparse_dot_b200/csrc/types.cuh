@@ -92,6 +92,18 @@ __device__ __forceinline__ cf64 ldg(const cf64* p) {
     return cf64{q.x, q.y};
 }
 
+// streaming loads (evict-first): data read exactly once, keep it from displacing reusable lines
+__device__ __forceinline__ float ldcs(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ double ldcs(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ cf32 ldcs(const cf32* p) {
+    const float2 q = __ldcs(reinterpret_cast<const float2*>(p));
+    return cf32{q.x, q.y};
+}
+__device__ __forceinline__ cf64 ldcs(const cf64* p) {
+    const double2 q = __ldcs(reinterpret_cast<const double2*>(p));
+    return cf64{q.x, q.y};
+}
+
 // L2-coherent loads (bypass L1): for data other threads update with atomics
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
