@@ -161,12 +161,38 @@ def cpu_spmm_runner(a, x, y0, threads=None):
     return step, "port", cores, "oracle/sdb_oracle.c orc_spmm_f32 (OpenMP)"
 
 
+def try_reference_package():
+    """The unmodified reference installed under baseline/_ref (pip --no-deps).  It needs libmkl_rt,
+    which this image does not have, so the import is expected to fail; the outcome is reported."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "sparse_dot_mkl")):
+        return None, "baseline/_ref/sparse_dot_mkl not installed"
+    sys.path.insert(0, ref)
+    try:
+        import sparse_dot_mkl  # noqa: F401
+
+        return sparse_dot_mkl, "imported"
+    except Exception as e:  # ImportError (no libmkl_rt) or AttributeError (partial MKL in libtorch_cpu)
+        return None, f"{type(e).__name__}: {str(e).splitlines()[0][:160]}"
+    finally:
+        sys.path.remove(ref)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    ref_pkg, ref_status = try_reference_package()
     a, x, y0 = make_workload(M_ROWS, K_COLS, NNZ_PER_ROW, N_DENSE, seed=0)
-    step, kind, cores, what = cpu_spmm_runner(a, x, y0)
+    if ref_pkg is not None:  # a real libmkl_rt is present: time the unmodified package itself
+        y = y0.copy()
+        cores, kind = os.cpu_count(), "reference"
+        what = "unmodified sparse_dot_mkl.dot_product_mkl(csr, ndarray, out=, out_scalar=) from baseline/_ref"
+
+        def step():
+            ref_pkg.dot_product_mkl(a, x, out=y, out_scalar=BETA)
+    else:
+        step, kind, cores, what = cpu_spmm_runner(a, x, y0)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -185,6 +211,7 @@ def run_reference_arm(args):
                          "sample": f"full workload, every step ({what})"},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_package": ref_status,
     }
     print(json.dumps(line))
 
