@@ -174,6 +174,13 @@ SDB_API sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A,
  * until sdb_order is called. */
 SDB_API sdb_status sdb_spgemm(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C);
 
+/* mkl_sparse_spmm followed by mkl_sparse_order on the result (the reference's
+ * reorder_output=True path, _sparse_sparse.py:219-228) as one call: every row of
+ * C comes out with ascending columns — the hash bins sort inside shared memory
+ * before they write, the bitmap bin emits in order anyway — so the result
+ * makes one trip to HBM instead of three. */
+SDB_API sdb_status sdb_spgemm_ordered(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C);
+
 /* mkl_sparse_?_spmmd (_cfunctions.py:600-609, called at _sparse_sparse.py:94-101):
  * dense C := op(A) * B, OVERWRITING the host array C (no beta). */
 SDB_API sdb_status sdb_spgemm_dense(int op, const sdb_mat* A, const sdb_mat* B,
@@ -187,6 +194,8 @@ SDB_API sdb_status sdb_spgemm_dense_dev(int op, const sdb_mat* A, const sdb_mat*
  * upper triangle of  A^T*A (op = SDB_OP_TRANSPOSE)  or  A*A^T
  * (op = SDB_OP_NON_TRANSPOSE)  as a new CSR handle. */
 SDB_API sdb_status sdb_syrk(int op, const sdb_mat* A, sdb_mat** C);
+/* ... with the result ordered (reorder_output=True, _gram_matrix.py:79-80). */
+SDB_API sdb_status sdb_syrk_ordered(int op, const sdb_mat* A, sdb_mat** C);
 
 /* mkl_sparse_?_syrkd (_cfunctions.py:639-649, called at _gram_matrix.py:149-157):
  * dense C := alpha * op-product + beta * C on the UPPER triangle of the host

@@ -58,6 +58,60 @@ def run_c1():
             "kernel_ms": sdb.last_timing_ms()[1]}
 
 
+def run_c3_resident(scale, ef):
+    """configs[2] at an edge factor whose result does not fit a host export comfortably: the product stays
+    in HBM; only the values come back (one array) for the checksum-of-checksums."""
+    a = cs.rmat_csr(scale, ef, np.float32, seed=1)
+    b = cs.rmat_csr(scale, ef, np.float32, seed=2)
+    products = int(np.dot(np.bincount(a.indices, minlength=a.shape[1]).astype(np.int64),
+                          np.diff(b.indptr).astype(np.int64)))
+    res = {"config": "c3_resident", "scale": scale, "edge_factor": ef, "nnz_a": int(a.nnz), "nnz_b": int(b.nnz),
+           "products": products}
+    ha, _, _ = H.create(a)
+    hb, _, _ = H.create(b)
+    with ha, hb:
+        def mult():
+            ref = C.c_void_p()
+            _lib.check(lib.sdb_spgemm(_lib.OP_N, ha.ref, hb.ref, C.byref(ref)), "sdb_spgemm")
+            return H.Handle(ref, np.float32)
+
+        ms0, hc = timed(mult)  # cold: grows the memory pool
+        hc.destroy()
+
+        def mult_ordered():
+            ref = C.c_void_p()
+            _lib.check(lib.sdb_spgemm_ordered(_lib.OP_N, ha.ref, hb.ref, C.byref(ref)), "sdb_spgemm_ordered")
+            return H.Handle(ref, np.float32)
+
+        ms_o, hco = timed(mult_ordered)
+        hco.destroy()
+        res["spgemm_ordered_ms"] = ms_o
+        ms, hc = timed(mult)
+        with hc:
+            res["spgemm_cold_ms"] = ms0
+            res["spgemm_ms"] = ms
+            info = H.info(hc)
+            nnz = int(info["nnz"])
+            res["nnz_c"] = nnz
+            res["result_gbytes"] = nnz * 8 / 1e9
+            res["g_products_per_s"] = products / (ms * 1e-3) / 1e9
+            try:
+                ms2, _ = timed(lambda: H.order(hc))
+                res["order_ms"] = ms2
+            except ValueError as e:
+                res["order_error"] = str(e)[:200]
+            vals = np.empty(nnz, dtype=np.float32)
+            t0 = time.perf_counter()
+            _lib.check(lib.sdb_export(hc.ref, None, 64, None, 32, vals.ctypes.data_as(C.c_void_p)), "sdb_export")
+            res["values_export_ms"] = (time.perf_counter() - t0) * 1e3
+            colsum_a = np.bincount(a.indices, weights=a.data.astype(np.float64), minlength=a.shape[1])
+            rowsum_b = np.asarray(b.astype(np.float64).sum(axis=1)).ravel()
+            want_total = float(np.dot(colsum_a, rowsum_b))
+            got_total = float(vals.sum(dtype=np.float64))
+            res["total_rel_err"] = abs(got_total - want_total) / want_total
+    return res
+
+
 def run_c3(scale, ef, full_check):
     """configs[2]: CSR x CSR SpGEMM, two R-MAT fp32 matrices, reorder_output=True."""
     a = cs.rmat_csr(scale, ef, np.float32, seed=1)
@@ -70,11 +124,17 @@ def run_c3(scale, ef, full_check):
     ha, _, _ = H.create(a)
     hb, _, _ = H.create(b)
     with ha, hb:
-        def mult():
+        def mult(ordered=False):
             ref = C.c_void_p()
-            _lib.check(lib.sdb_spgemm(_lib.OP_N, ha.ref, hb.ref, C.byref(ref)), "sdb_spgemm")
+            fn = lib.sdb_spgemm_ordered if ordered else lib.sdb_spgemm
+            _lib.check(fn(_lib.OP_N, ha.ref, hb.ref, C.byref(ref)), "sdb_spgemm")
             return H.Handle(ref, np.float32)
 
+        with mult(True) as warm:
+            pass
+        ms_o, hco = timed(lambda: mult(True))
+        hco.destroy()
+        res["spgemm_ordered_ms"] = ms_o
         with mult() as warm:  # first call pays for growing the device memory pool (GBs of cudaMalloc)
             H.order(warm)
         ms, hc = timed(mult)
@@ -270,6 +330,8 @@ def main():
             r = run_c1()
         elif w == "c3":
             r = run_c3(args.scale, args.ef, not args.no_full_check)
+        elif w == "c3res":
+            r = run_c3_resident(args.scale, args.ef)
         elif w == "c4":
             r = run_c4(args.gram_m, args.gram_n, 100)
         elif w == "c5":

@@ -51,9 +51,11 @@ PROTOTYPES = {
     "sdb_spmm_dev": (_i32, [_i32, _pd, _vp, _i32, _vp, _i64, _i64, _pd, _vp, _i64, _vp]),
     "sdb_spmm_dev_allgather": (_i32, [_pd, _vp, _vp, _i64, _i64, _pd, _pvp, _i32, _i32, _i64, _i64, _vp]),
     "sdb_spgemm": (_i32, [_i32, _vp, _vp, _pvp]),
+    "sdb_spgemm_ordered": (_i32, [_i32, _vp, _vp, _pvp]),
     "sdb_spgemm_dense": (_i32, [_i32, _vp, _vp, _i32, _vp, _i64]),
     "sdb_spgemm_dense_dev": (_i32, [_i32, _vp, _vp, _i32, _vp, _i64, _vp]),
     "sdb_syrk": (_i32, [_i32, _vp, _pvp]),
+    "sdb_syrk_ordered": (_i32, [_i32, _vp, _pvp]),
     "sdb_syrkd": (_i32, [_i32, _vp, _pd, _pd, _vp, _i32, _i64]),
     "sdb_syrkd_new": (_i32, [_i32, _vp, _pd, _vp, _i32, _i64]),
     "sdb_syrkd_dev": (_i32, [_i32, _vp, _pd, _pd, _vp, _i32, _i64, _vp]),

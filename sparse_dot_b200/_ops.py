@@ -152,10 +152,12 @@ def dot_sparse_vector(a, b, cast=False, scalar=1.0, out=None, out_scalar=None):
 
 
 # ---------------------------------------------------------------- sparse x sparse
-def _spgemm_handle(ha, hb):
-    """C = A @ B as a new device handle (reference: _matmul_mkl)."""
+def _spgemm_handle(ha, hb, ordered=False):
+    """C = A @ B as a new device handle (reference: _matmul_mkl); ``ordered`` fuses the
+    reference's separate mkl_sparse_order pass into the product."""
     ref = _ct.c_void_p()
-    check(SDB.lib.sdb_spgemm(_lib.OP_N, ha.ref, hb.ref, _ct.byref(ref)), "sdb_spgemm")
+    fn = "sdb_spgemm_ordered" if ordered else "sdb_spgemm"
+    check(getattr(SDB.lib, fn)(_lib.OP_N, ha.ref, hb.ref, _ct.byref(ref)), fn)
     return _h.Handle(ref, ha.dtype)
 
 
@@ -196,12 +198,9 @@ def dot_sparse_sparse(a, b, cast=False, reorder_output=False, dense=False, out=N
             result = _spgemm_dense(ha, hb, shape, _v.OUTPUT_DTYPES[(a_dbl or b_dbl, a_cplx)], out=out)
             _timer("Multiplied matrices", t)
             return result
-        hc = _spgemm_handle(ha, hb)
+        hc = _spgemm_handle(ha, hb, ordered=reorder_output)
     with hc:
-        t = _timer("Multiplied matrices", t)
-        if reorder_output:
-            _h.order(hc)
-            t = _timer("Reordered output indices", t)
+        t = _timer("Multiplied matrices" + (" (ordered)" if reorder_output else ""), t)
         result = _h.export(hc, output_type=ctor.__name__)
     _timer("Created python handle", t)
     return result
@@ -214,10 +213,9 @@ def _gram_sparse(a, aat=False, reorder_output=False):
     handle, _, _ = _h.create(a)
     with handle:
         ref = _ct.c_void_p()
-        check(SDB.lib.sdb_syrk(_lib.OP_N if aat else _lib.OP_T, handle.ref, _ct.byref(ref)), "sdb_syrk")
+        fn = "sdb_syrk_ordered" if reorder_output else "sdb_syrk"
+        check(getattr(SDB.lib, fn)(_lib.OP_N if aat else _lib.OP_T, handle.ref, _ct.byref(ref)), fn)
         with _h.Handle(ref, a.dtype) as hc:
-            if reorder_output:
-                _h.order(hc)
             return _h.export(hc, output_type="csr_matrix")
 
 

@@ -216,7 +216,7 @@ sdb_status rows_sorted(Context* ctx, int64_t rows, const int64_t* indptr, const 
                        bool* sorted);
 // SpGEMM core on CSR views: C = L * R (optionally only entries with col >= row).
 sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int dtype, bool upper,
-                         sdb_mat** out);
+                         sdb_mat** out, bool sort = false);
 
 sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a, const double* alpha,
                        const double* beta, int layout, const void* dX, int64_t n, int64_t ldx,

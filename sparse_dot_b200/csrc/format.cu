@@ -26,10 +26,11 @@ constexpr int kSortThreads = 256;
 
 __global__ void __launch_bounds__(256) classify_rows_kernel(int64_t rows, const int64_t* __restrict__ indptr,
                                                             const int32_t* __restrict__ indices,
+                                                            int32_t* __restrict__ short_rows,
                                                             int32_t* __restrict__ med_rows,
                                                             int32_t* __restrict__ long_rows,
-                                                            unsigned* __restrict__ counters /*[3]: med, long, unsorted*/) {
-    // one warp per row: lanes compare neighbouring entries 32 at a time
+                                                            unsigned* __restrict__ counters /*[4]: short, med, long, unsorted*/) {
+    // one warp per row: lanes compare neighbouring entries 32 at a time; unsorted rows are listed by size class
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (r >= rows) return;
@@ -42,19 +43,22 @@ __global__ void __launch_bounds__(256) classify_rows_kernel(int64_t rows, const 
         unsorted = __any_sync(0xffffffffu, bad);
     }
     if (!unsorted || lane != 0) return;
-    atomicAdd(&counters[2], 1u);
-    if (len > kSmemSortMax) long_rows[atomicAdd(&counters[1], 1u)] = int32_t(r);
-    else if (len > 32) med_rows[atomicAdd(&counters[0], 1u)] = int32_t(r);
+    atomicAdd(&counters[3], 1u);
+    if (len > kSmemSortMax) long_rows[atomicAdd(&counters[2], 1u)] = int32_t(r);
+    else if (len > 32) med_rows[atomicAdd(&counters[1], 1u)] = int32_t(r);
+    else short_rows[atomicAdd(&counters[0], 1u)] = int32_t(r);
 }
 
 // one warp per row of <= 32 entries; writes sorted columns in place and the
 // source position of every output entry into perm
-__global__ void __launch_bounds__(256) sort_rows_warp_kernel(int64_t rows, const int64_t* __restrict__ indptr,
+__global__ void __launch_bounds__(256) sort_rows_warp_kernel(const int32_t* __restrict__ row_list, unsigned n_list,
+                                                             const int64_t* __restrict__ indptr,
                                                              int32_t* __restrict__ indices,
                                                              int32_t* __restrict__ perm) {
     const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (r >= rows) return;
+    const int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_list) return;
+    const int64_t r = row_list[w];
     const int64_t b = indptr[r];
     const int len = int(min(int64_t(33), indptr[r + 1] - b));
     if (len > 32 || len == 0) return;  // warp-uniform
@@ -203,39 +207,44 @@ __global__ void __launch_bounds__(1024) sort_rows_global_kernel(const int32_t* _
     }
 }
 
-// identity permutation (rows that were already sorted keep perm[p] = p - row start)
-__global__ void __launch_bounds__(256) perm_identity_kernel(int64_t rows, const int64_t* __restrict__ indptr,
-                                                            int32_t* __restrict__ perm) {
+// For every LISTED row: dst entry p = src entry (row start + perm[p]); one entry is `words_per_entry`
+// 4-byte words (values move as raw words so every dtype / block size shares this).  Rows that were
+// already in order are not listed and are never touched.
+__global__ void __launch_bounds__(256) permute_rows_kernel(const int32_t* __restrict__ row_list, unsigned n_list,
+                                                           const int64_t* __restrict__ indptr,
+                                                           const int32_t* __restrict__ perm,
+                                                           const uint32_t* __restrict__ src,
+                                                           uint32_t* __restrict__ dst, int64_t words_per_entry) {
     const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (r >= rows) return;
-    const int64_t b = indptr[r], e = indptr[r + 1];
-    for (int64_t p = b + lane; p < e; p += 32) perm[p] = int32_t(p - b);
-}
-
-// dst entry p of row r = src entry (row start + perm[p]); one entry is `epe`
-// 4-byte words (values are moved as raw words so every dtype / block shares this)
-__global__ void __launch_bounds__(256) permute_values_kernel(int64_t rows, const int64_t* __restrict__ indptr,
-                                                             const int32_t* __restrict__ perm,
-                                                             const uint32_t* __restrict__ src,
-                                                             uint32_t* __restrict__ dst, int64_t words_per_entry) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (r >= rows) return;
+    const int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_list) return;
+    const int64_t r = row_list[w];
     const int64_t b = indptr[r], e = indptr[r + 1];
     if (words_per_entry == 1) {
         for (int64_t p = b + lane; p < e; p += 32) dst[p] = src[b + perm[p]];
     } else if (words_per_entry <= 4) {
         for (int64_t p = b + lane; p < e; p += 32) {
             const int64_t s = (b + perm[p]) * words_per_entry, d = p * words_per_entry;
-            for (int64_t w = 0; w < words_per_entry; ++w) dst[d + w] = src[s + w];
+            for (int64_t k = 0; k < words_per_entry; ++k) dst[d + k] = src[s + k];
         }
     } else {  // blocks: the whole warp moves one entry at a time
         for (int64_t p = b; p < e; ++p) {
             const int64_t s = (b + perm[p]) * words_per_entry, d = p * words_per_entry;
-            for (int64_t w = lane; w < words_per_entry; w += 32) dst[d + w] = src[s + w];
+            for (int64_t k = lane; k < words_per_entry; k += 32) dst[d + k] = src[s + k];
         }
     }
+}
+
+__global__ void __launch_bounds__(256) copy_rows_kernel(const int32_t* __restrict__ row_list, unsigned n_list,
+                                                        const int64_t* __restrict__ indptr,
+                                                        const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                        int64_t words_per_entry) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_list) return;
+    const int64_t r = row_list[w];
+    const int64_t b = indptr[r] * words_per_entry, e = indptr[r + 1] * words_per_entry;
+    for (int64_t p = b + lane; p < e; p += 32) dst[p] = src[p];
 }
 
 static unsigned blocks_for(int64_t n, int per_block) { return unsigned((n + per_block - 1) / per_block); }
@@ -276,15 +285,15 @@ sdb_status rows_sorted(Context* ctx, int64_t rows, const int64_t* indptr, const 
     if (rows <= 0) return SDB_STATUS_SUCCESS;
     cudaStream_t s = ctx->stream;
     DevBuf counters, dummy;
-    SDB_TRY(counters.alloc(3 * sizeof(unsigned), s));
+    SDB_TRY(counters.alloc(4 * sizeof(unsigned), s));
     SDB_TRY(dummy.alloc(size_t(rows) * sizeof(int32_t), s));
-    SDB_CUDA(cudaMemsetAsync(counters.p, 0, 3 * sizeof(unsigned), s));
+    SDB_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned), s));
     SDB_LAUNCH(classify_rows_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, indices, dummy.as<int32_t>(),
-               dummy.as<int32_t>(), counters.as<unsigned>());
-    unsigned h[3];
+               dummy.as<int32_t>(), dummy.as<int32_t>(), counters.as<unsigned>());
+    unsigned h[4];
     SDB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     SDB_CUDA(cudaStreamSynchronize(s));
-    *sorted = h[2] == 0;
+    *sorted = h[3] == 0;
     return SDB_STATUS_SUCCESS;
 }
 
@@ -293,51 +302,56 @@ sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indpt
     if (rows <= 0) return SDB_STATUS_SUCCESS;
     cudaStream_t s = ctx->stream;
     SDB_REQUIRE(rows < (int64_t(1) << 31), SDB_STATUS_NOT_SUPPORTED, "sort_rows: too many rows");
-    DevBuf counters, med, lng;
-    SDB_TRY(counters.alloc(3 * sizeof(unsigned), s));
+    DevBuf counters, shortl, med, lng;
+    SDB_TRY(counters.alloc(4 * sizeof(unsigned), s));
+    SDB_TRY(shortl.alloc(size_t(rows) * sizeof(int32_t), s));
     SDB_TRY(med.alloc(size_t(rows) * sizeof(int32_t), s));
     SDB_TRY(lng.alloc(size_t(rows) * sizeof(int32_t), s));
-    SDB_CUDA(cudaMemsetAsync(counters.p, 0, 3 * sizeof(unsigned), s));
-    SDB_LAUNCH(classify_rows_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, indices, med.as<int32_t>(),
-               lng.as<int32_t>(), counters.as<unsigned>());
-    unsigned h[3];
+    SDB_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned), s));
+    SDB_LAUNCH(classify_rows_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, indices,
+               shortl.as<int32_t>(), med.as<int32_t>(), lng.as<int32_t>(), counters.as<unsigned>());
+    unsigned h[4];
     int64_t nnz = 0;
     SDB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     SDB_CUDA(cudaMemcpyAsync(&nnz, indptr + rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     SDB_CUDA(cudaStreamSynchronize(s));
-    trace(s, "sort_rows: classified %lld rows: %u unsorted (%u in shared memory, %u in global memory)", (long long)rows,
-          h[2], h[0], h[1]);
-    if (h[2] == 0 || nnz == 0) return SDB_STATUS_SUCCESS;  // already in order: nothing moves
+    trace(s, "sort_rows: %lld rows, %u unsorted (%u in a warp, %u in shared memory, %u in global memory)",
+          (long long)rows, h[3], h[0], h[1], h[2]);
+    if (h[3] == 0 || nnz == 0) return SDB_STATUS_SUCCESS;  // already in order: nothing moves
 
+    // perm / tmp are row-aligned with the matrix but only the listed (unsorted) rows are ever touched
     DevBuf perm, tmp;
     SDB_TRY(perm.alloc(size_t(nnz) * sizeof(int32_t), s));
-    SDB_LAUNCH(perm_identity_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, perm.as<int32_t>());
-    SDB_LAUNCH(sort_rows_warp_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, indices,
-               perm.as<int32_t>());
     if (h[0] > 0)
-        SDB_LAUNCH(sort_rows_cta_kernel, h[0], kSortThreads, 0, s, med.as<int32_t>(), indptr, indices,
+        SDB_LAUNCH(sort_rows_warp_kernel, blocks_for(int64_t(h[0]) * 32, 256), 256, 0, s, shortl.as<int32_t>(), h[0],
+                   indptr, indices, perm.as<int32_t>());
+    if (h[1] > 0)
+        SDB_LAUNCH(sort_rows_cta_kernel, h[1], kSortThreads, 0, s, med.as<int32_t>(), indptr, indices,
                    perm.as<int32_t>());
-    if (h[1] > 0) {
+    if (h[2] > 0) {
         DevBuf scratch;
         SDB_TRY(scratch.alloc(size_t(nnz) * sizeof(uint64_t), s));
-        SDB_LAUNCH(sort_rows_global_kernel, h[1], 1024, 0, s, lng.as<int32_t>(), indptr, indices,
+        SDB_LAUNCH(sort_rows_global_kernel, h[2], 1024, 0, s, lng.as<int32_t>(), indptr, indices,
                    perm.as<int32_t>(), scratch.as<uint64_t>());
     }
     trace(s, "sort_rows: columns sorted");
-    if (values != nullptr) {
-        const size_t entry_bytes = dtype_size(dtype) * size_t(elems_per_entry);
-        SDB_TRY(tmp.alloc(size_t(nnz) * entry_bytes, s));
-        SDB_LAUNCH(permute_values_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, perm.as<int32_t>(),
-                   static_cast<const uint32_t*>(values), tmp.as<uint32_t>(), int64_t(entry_bytes / 4));
-        SDB_CUDA(cudaMemcpyAsync(values, tmp.p, size_t(nnz) * entry_bytes, cudaMemcpyDeviceToDevice, s));
-    }
-    if (extra != nullptr) {  // a second per-entry payload (one 4-byte word) travels the same way
-        DevBuf tmp2;
-        SDB_TRY(tmp2.alloc(size_t(nnz) * 4, s));
-        SDB_LAUNCH(permute_values_kernel, blocks_for(rows * 32, 256), 256, 0, s, rows, indptr, perm.as<int32_t>(),
-                   reinterpret_cast<const uint32_t*>(extra), tmp2.as<uint32_t>(), int64_t(1));
-        SDB_CUDA(cudaMemcpyAsync(extra, tmp2.p, size_t(nnz) * 4, cudaMemcpyDeviceToDevice, s));
-    }
+    const int32_t* lists[3] = {shortl.as<int32_t>(), med.as<int32_t>(), lng.as<int32_t>()};
+    auto move_payload = [&](void* payload, int64_t words) -> sdb_status {
+        SDB_TRY(tmp.alloc(size_t(nnz) * size_t(words) * 4, s));
+        for (int c = 0; c < 3; ++c) {
+            if (h[c] == 0) continue;
+            SDB_LAUNCH(permute_rows_kernel, blocks_for(int64_t(h[c]) * 32, 256), 256, 0, s, lists[c], h[c], indptr,
+                       perm.as<int32_t>(), static_cast<const uint32_t*>(payload), tmp.as<uint32_t>(), words);
+        }
+        for (int c = 0; c < 3; ++c) {
+            if (h[c] == 0) continue;
+            SDB_LAUNCH(copy_rows_kernel, blocks_for(int64_t(h[c]) * 32, 256), 256, 0, s, lists[c], h[c], indptr,
+                       tmp.as<uint32_t>(), static_cast<uint32_t*>(payload), words);
+        }
+        return SDB_STATUS_SUCCESS;
+    };
+    if (values != nullptr) SDB_TRY(move_payload(values, int64_t(dtype_size(dtype) * size_t(elems_per_entry) / 4)));
+    if (extra != nullptr) SDB_TRY(move_payload(extra, 1));  // a second per-entry payload (one 4-byte word)
     trace(s, "sort_rows: values permuted");
     return SDB_STATUS_SUCCESS;
 }

@@ -105,6 +105,31 @@ __global__ void __launch_bounds__(256) bin_rows_kernel(int64_t rows, const int32
     }
 }
 
+// Ascending bitonic network over pairs[0..n) in shared memory, any n (flip step + half cleaners, no
+// padding needed); `tid`/`team` = this thread's index / size of the cooperating team, `sync` its barrier.
+template <typename Sync>
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* pairs, int n, int tid, int team, Sync sync) {
+    int p2 = 1;
+    while (p2 < n) p2 <<= 1;
+    for (int k = 2; k <= p2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool flip = j == (k >> 1);
+            for (int t = tid; t < (p2 >> 1); t += team) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = flip ? (lo ^ (k - 1)) : (lo | j);
+                if (hi < n) {
+                    const uint64_t a = pairs[lo], c = pairs[hi];
+                    if (a > c) {
+                        pairs[lo] = c;
+                        pairs[hi] = a;
+                    }
+                }
+            }
+            sync();
+        }
+    }
+}
+
 // ------------------------------------------------------------ hash passes
 // One pass over the products of row i; NUMERIC adds values, else only counts.
 // `team` = 32 for a warp-owned table, blockDim.x for a CTA-owned one.
@@ -197,11 +222,13 @@ __global__ void __launch_bounds__(kHashWarps * 32)
     spgemm_warp_kernel(const int32_t* __restrict__ list, unsigned n_list, const int64_t* __restrict__ l_ptr,
                        const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
                        const int32_t* __restrict__ l_pos, const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
-                       const T* __restrict__ r_val, bool upper, int32_t* __restrict__ c_len,
+                       const T* __restrict__ r_val, bool upper, bool sort, int32_t* __restrict__ c_len,
                        const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* all_keys = reinterpret_cast<int32_t*>(smem_raw);
     T* all_vals = reinterpret_cast<T*>(smem_raw + sizeof(int32_t) * kWarpSlots * kHashWarps);
+    // sorted emission: (column, slot) pairs of this warp's row, after the value tables
+    uint64_t* all_pairs = reinterpret_cast<uint64_t*>(smem_raw + (sizeof(int32_t) + sizeof(T)) * kWarpSlots * kHashWarps);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned w = blockIdx.x * kHashWarps + warp;
     if (w >= n_list) return;
@@ -223,6 +250,23 @@ __global__ void __launch_bounds__(kHashWarps * 32)
         return;
     }
     int64_t out = c_ptr[i];
+    if (sort) {
+        uint64_t* pairs = all_pairs + warp * kWarpMax;
+        int n = 0;
+        for (int s = lane; s < kWarpSlots; s += 32) {
+            const int32_t k = keys[s];
+            const unsigned m = __ballot_sync(0xffffffffu, k != kEmpty);
+            if (k != kEmpty) pairs[n + __popc(m & ((1u << lane) - 1))] = (uint64_t(uint32_t(k)) << 32) | uint32_t(s);
+            n += __popc(m);
+        }
+        __syncwarp();
+        bitonic_sort_smem(pairs, n, lane, 32, [] { __syncwarp(); });
+        for (int e = lane; e < n; e += 32) {
+            c_idx[out + e] = int32_t(pairs[e] >> 32);
+            c_val[out + e] = vals[uint32_t(pairs[e])];
+        }
+        return;
+    }
     for (int s = lane; s < kWarpSlots; s += 32) {
         const int32_t k = keys[s];
         const unsigned m = __ballot_sync(0xffffffffu, k != kEmpty);
@@ -240,11 +284,12 @@ __global__ void __launch_bounds__(kCtaThreads)
     spgemm_cta_kernel(const int32_t* __restrict__ list, const int64_t* __restrict__ l_ptr,
                       const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
                       const int32_t* __restrict__ l_pos, const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
-                      const T* __restrict__ r_val, bool upper, int32_t* __restrict__ c_len,
+                      const T* __restrict__ r_val, bool upper, bool sort, int32_t* __restrict__ c_len,
                       const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* keys = reinterpret_cast<int32_t*>(smem_raw);
     T* vals = reinterpret_cast<T*>(smem_raw + sizeof(int32_t) * kCtaSlots);
+    uint64_t* pairs = reinterpret_cast<uint64_t*>(smem_raw + (sizeof(int32_t) + sizeof(T)) * kCtaSlots);  // sort only
     __shared__ int total;
     const int64_t i = list[blockIdx.x];
     for (int s = threadIdx.x; s < kCtaSlots; s += kCtaThreads) {
@@ -280,10 +325,22 @@ __global__ void __launch_bounds__(kCtaThreads)
         if (lane == 0 && m) base = atomicAdd(&total, __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (k != kEmpty) {
-            const int64_t o = out + base + __popc(m & ((1u << lane) - 1));
-            c_idx[o] = k;
-            c_val[o] = vals[s];
+            const int o = base + __popc(m & ((1u << lane) - 1));
+            if (sort) {
+                pairs[o] = (uint64_t(uint32_t(k)) << 32) | uint32_t(s);
+            } else {
+                c_idx[out + o] = k;
+                c_val[out + o] = vals[s];
+            }
         }
+    }
+    if (!sort) return;
+    __syncthreads();
+    const int n = total;
+    bitonic_sort_smem(pairs, n, threadIdx.x, kCtaThreads, [] { __syncthreads(); });
+    for (int e = threadIdx.x; e < n; e += kCtaThreads) {
+        c_idx[out + e] = int32_t(pairs[e] >> 32);
+        c_val[out + e] = vals[uint32_t(pairs[e])];
     }
 }
 
@@ -424,8 +481,8 @@ __global__ void __launch_bounds__(1024)
 }
 
 template <typename T, bool NUMERIC>
-static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, bool upper, const int32_t* sizes,
-                           int32_t* c_len, const int64_t* c_ptr, int32_t* c_idx, T* c_val) {
+static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, bool upper, bool sort,
+                           const int32_t* sizes, int32_t* c_len, const int64_t* c_ptr, int32_t* c_idx, T* c_val) {
     cudaStream_t s = ctx->stream;
     const int64_t rows = l.rows;
     DevBuf lw, lc, lg, counters;
@@ -448,19 +505,21 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
     const int32_t* ri = r.indices;
     const T* rv = static_cast<const T*>(r.values);
     if (h[0] > 0) {
-        const size_t smem = size_t(kHashWarps) * kWarpSlots * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0));
+        const size_t smem = size_t(kHashWarps) * kWarpSlots * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0)) +
+                            (NUMERIC && sort ? size_t(kHashWarps) * kWarpMax * sizeof(uint64_t) : 0);
         SDB_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel<T, NUMERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem)));
         SDB_LAUNCH((spgemm_warp_kernel<T, NUMERIC>), (h[0] + kHashWarps - 1) / kHashWarps, kHashWarps * 32, smem, s,
-                   lw.as<int32_t>(), h[0], lp, li, lv, lq, rp, ri, rv, upper, c_len, c_ptr, c_idx, c_val);
+                   lw.as<int32_t>(), h[0], lp, li, lv, lq, rp, ri, rv, upper, sort, c_len, c_ptr, c_idx, c_val);
         trace(s, "spgemm: warp bin done");
     }
     if (h[1] > 0) {
-        const size_t smem = size_t(kCtaSlots) * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0));
+        const size_t smem = size_t(kCtaSlots) * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0)) +
+                            (NUMERIC && sort ? size_t(kCtaMax) * sizeof(uint64_t) : 0);
         SDB_CUDA(cudaFuncSetAttribute(spgemm_cta_kernel<T, NUMERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem)));
         SDB_LAUNCH((spgemm_cta_kernel<T, NUMERIC>), h[1], kCtaThreads, smem, s, lc.as<int32_t>(), lp, li, lv, lq, rp,
-                   ri, rv, upper, c_len, c_ptr, c_idx, c_val);
+                   ri, rv, upper, sort, c_len, c_ptr, c_idx, c_val);
         trace(s, "spgemm: cta bin done");
     }
     if (h[2] > 0) {
@@ -481,7 +540,8 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
     return SDB_STATUS_SUCCESS;
 }
 
-sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int dtype, bool upper, sdb_mat** out) {
+sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int dtype, bool upper, sdb_mat** out,
+                         bool sort) {
     cudaStream_t s = ctx->stream;
     SDB_REQUIRE(l.cols == r.rows, SDB_STATUS_INVALID_VALUE, "spgemm: inner dimensions %lld and %lld differ",
                 (long long)l.cols, (long long)r.rows);
@@ -494,8 +554,8 @@ sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int d
         SDB_LAUNCH(row_products_kernel, unsigned((rows * 32 + 255) / 256), 256, 0, s, rows, l.indptr, l.indices,
                    upper ? l.pos : nullptr, r.indptr, ub.as<int32_t>());
         SDB_TRY(SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
-            return run_pass<T, false>(ctx, l, r, upper, ub.as<int32_t>(), c_len.as<int32_t>(), nullptr, nullptr,
-                                      nullptr);
+            return run_pass<T, false>(ctx, l, r, upper, false, ub.as<int32_t>(), c_len.as<int32_t>(), nullptr,
+                                      nullptr, nullptr);
         }));
     }
     // row offsets of C, then its size
@@ -510,7 +570,7 @@ sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int d
         SDB_CUDA(cudaMemcpyAsync(c->indptr, c_ptr.p, size_t(rows + 1) * 8, cudaMemcpyDeviceToDevice, s));
         if (nnz == 0) return SDB_STATUS_SUCCESS;
         return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
-            return run_pass<T, true>(ctx, l, r, upper, c_len.as<int32_t>(), nullptr, c->indptr, c->indices,
+            return run_pass<T, true>(ctx, l, r, upper, sort, c_len.as<int32_t>(), nullptr, c->indptr, c->indices,
                                      static_cast<T*>(c->values));
         });
     }();
@@ -736,7 +796,7 @@ static int64_t logical_cols(const sdb_mat* m) { return m->cols * m->block; }
 
 extern "C" {
 
-sdb_status sdb_spgemm(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C) {
+static sdb_status spgemm_impl(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C, bool sort) {
     SDB_REQUIRE(C != nullptr, SDB_STATUS_INVALID_VALUE, "spgemm: null output handle");
     *C = nullptr;
     SDB_TRY(check_pair("spgemm", A, B));
@@ -758,7 +818,7 @@ sdb_status sdb_spgemm(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C) {
         SDB_TRY(csr_view(ctx, A, ta, &l));
         SDB_TRY(csr_view(ctx, B, false, &r));
         sdb_mat* flat = nullptr;
-        SDB_TRY(spgemm_device(ctx, l, r, A->dtype, false, &flat));
+        SDB_TRY(spgemm_device(ctx, l, r, A->dtype, false, &flat, true));
         sdb_status st = sort_rows(ctx, flat->dtype, flat->rows, flat->indptr, flat->indices, flat->values, 1);
         if (st == SDB_STATUS_SUCCESS) st = compress_to_bsr(ctx, flat, A->block, &c);
         free_handle(flat);
@@ -767,20 +827,20 @@ sdb_status sdb_spgemm(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C) {
         // result in A's format: CSC(C) = CSR(C^T) = CSR(B^T) * CSR(op(A)^T)
         SDB_TRY(csr_view(ctx, B, true, &l));
         SDB_TRY(csr_view(ctx, A, !ta, &r));
-        SDB_TRY(spgemm_device(ctx, l, r, A->dtype, false, &c));
+        SDB_TRY(spgemm_device(ctx, l, r, A->dtype, false, &c, sort));
         c->format = SDB_FMT_CSC;
         std::swap(c->rows, c->cols);
     } else {
         SDB_TRY(csr_view(ctx, A, ta, &l));
         SDB_TRY(csr_view(ctx, B, false, &r));
-        SDB_TRY(spgemm_device(ctx, l, r, A->dtype, false, &c));
+        SDB_TRY(spgemm_device(ctx, l, r, A->dtype, false, &c, sort));
     }
     SDB_CUDA(cudaStreamSynchronize(ctx->stream));
     *C = c;
     return SDB_STATUS_SUCCESS;
 }
 
-sdb_status sdb_syrk(int op, const sdb_mat* A, sdb_mat** C) {
+static sdb_status syrk_impl(int op, const sdb_mat* A, sdb_mat** C, bool sort) {
     SDB_REQUIRE(C != nullptr, SDB_STATUS_INVALID_VALUE, "syrk: null output handle");
     *C = nullptr;
     SDB_REQUIRE(A != nullptr, SDB_STATUS_NOT_INITIALIZED, "syrk: null handle");
@@ -795,12 +855,21 @@ sdb_status sdb_syrk(int op, const sdb_mat* A, sdb_mat** C) {
     SDB_TRY(csr_view(ctx, A, true, &at, true));
     // op = TRANSPOSE: A^T A = (A^T) * A;  op = NON_TRANSPOSE: A A^T = A * (A^T)
     sdb_mat* c = nullptr;
-    if (op == SDB_OP_TRANSPOSE) SDB_TRY(spgemm_device(ctx, at, a, A->dtype, true, &c));
-    else SDB_TRY(spgemm_device(ctx, a, at, A->dtype, true, &c));
+    if (op == SDB_OP_TRANSPOSE) SDB_TRY(spgemm_device(ctx, at, a, A->dtype, true, &c, sort));
+    else SDB_TRY(spgemm_device(ctx, a, at, A->dtype, true, &c, sort));
     SDB_CUDA(cudaStreamSynchronize(ctx->stream));
     *C = c;
     return SDB_STATUS_SUCCESS;
 }
+
+sdb_status sdb_spgemm(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C) {
+    return spgemm_impl(op, A, B, C, false);
+}
+sdb_status sdb_spgemm_ordered(int op, const sdb_mat* A, const sdb_mat* B, sdb_mat** C) {
+    return spgemm_impl(op, A, B, C, true);
+}
+sdb_status sdb_syrk(int op, const sdb_mat* A, sdb_mat** C) { return syrk_impl(op, A, C, false); }
+sdb_status sdb_syrk_ordered(int op, const sdb_mat* A, sdb_mat** C) { return syrk_impl(op, A, C, true); }
 
 sdb_status sdb_spgemm_dense_dev(int op, const sdb_mat* A, const sdb_mat* B, int layout, void* dC, int64_t ldc,
                                 void* stream) {

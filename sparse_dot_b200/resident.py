@@ -117,20 +117,16 @@ class ResidentCSR:
         if not isinstance(other, ResidentCSR):
             raise TypeError("matmat takes another ResidentCSR")
         ref = _ct.c_void_p()
-        check(SDB.lib.sdb_spgemm(_lib.OP_N, self.handle.ref, other.handle.ref, _ct.byref(ref)), "sdb_spgemm")
-        out = ResidentCSR(None, _handle=_h.Handle(ref, self.dtype))
-        if reorder_output:
-            _h.order(out.handle)
-        return out
+        fn = "sdb_spgemm_ordered" if reorder_output else "sdb_spgemm"
+        check(getattr(SDB.lib, fn)(_lib.OP_N, self.handle.ref, other.handle.ref, _ct.byref(ref)), fn)
+        return ResidentCSR(None, _handle=_h.Handle(ref, self.dtype))
 
     def gram(self, transpose=False, reorder_output=False):
         """Upper triangle of A^T A (or A A^T) as a new ResidentCSR."""
         ref = _ct.c_void_p()
-        check(SDB.lib.sdb_syrk(_lib.OP_N if transpose else _lib.OP_T, self.handle.ref, _ct.byref(ref)), "sdb_syrk")
-        out = ResidentCSR(None, _handle=_h.Handle(ref, self.dtype))
-        if reorder_output:
-            _h.order(out.handle)
-        return out
+        fn = "sdb_syrk_ordered" if reorder_output else "sdb_syrk"
+        check(getattr(SDB.lib, fn)(_lib.OP_N if transpose else _lib.OP_T, self.handle.ref, _ct.byref(ref)), fn)
+        return ResidentCSR(None, _handle=_h.Handle(ref, self.dtype))
 
     def to_scipy(self):
         meta = _h.info(self.handle)
