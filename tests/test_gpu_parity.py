@@ -662,3 +662,62 @@ def test_resident_operands():
             a.dot(x.astype(np.float64))
         with pytest.raises(ValueError):
             a.dot(x[:100])
+
+
+def test_order_bsr_and_csc_handles():
+    """mkl_sparse_order on BSR (whole blocks move with their column index) and CSC handles."""
+    m1, _ = cs.fixture_pair(np.float64)
+    bsr = m1.tobsr(blocksize=(10, 10))
+    rng = np.random.default_rng(9)
+    shuffled = bsr.copy()
+    for i in range(shuffled.indptr.shape[0] - 1):
+        s0, e0 = shuffled.indptr[i], shuffled.indptr[i + 1]
+        p = rng.permutation(e0 - s0)
+        shuffled.indices[s0:e0] = shuffled.indices[s0:e0][p]
+        shuffled.data[s0:e0] = shuffled.data[s0:e0][p]
+    shuffled.has_sorted_indices = False
+    h, _, _ = H.create(shuffled)
+    with h:
+        H.order(h)
+        got = H.export(h, output_type="bsr_matrix")
+    want = bsr.copy()
+    want.sort_indices()  # tobsr() does not order the block columns itself
+    assert np.array_equal(got.indptr, want.indptr)
+    assert np.array_equal(got.indices, want.indices) and np.array_equal(got.data, want.data)
+    csc = m1.tocsc()
+    sh = csc.copy()
+    for j in range(sh.shape[1]):
+        s0, e0 = sh.indptr[j], sh.indptr[j + 1]
+        sh.indices[s0:e0] = sh.indices[s0:e0][::-1].copy()
+        sh.data[s0:e0] = sh.data[s0:e0][::-1].copy()
+    sh.has_sorted_indices = False
+    h, _, _ = H.create(sh)
+    with h:
+        H.order(h)
+        got = H.export(h, output_type="csc_matrix")
+    assert np.array_equal(got.indices, csc.indices) and np.array_equal(got.data, csc.data)
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("shape_case", ["row", "col"])
+@pytest.mark.parametrize("dtype", REAL)
+def test_one_row_and_one_column_operands(order, shape_case, dtype):
+    """test_sparse_dense.py:293-334: the same method set with a 1-row left operand or a 1-column
+    right operand (arrays that are both C- and F-contiguous; some calls dispatch to the vector path)."""
+    M1, M2 = _pair(dtype)
+    m1 = M1[[0], :] if shape_case == "row" else M1
+    m2 = M2 if shape_case == "row" else M2[:, [0]]
+    m1_d = np.asarray(M1.toarray(), order=order)[[0], :] if shape_case == "row" else np.asarray(M1.toarray(), order=order)
+    m2_d = np.asarray(M2.toarray(), order=order) if shape_case == "row" else np.asarray(M2.toarray(), order=order)[:, [0]]
+    want = m1_d.astype(np.float64) @ m2_d.astype(np.float64)
+    tol = 1.5e-6 if dtype == np.float64 else 1.5e-5  # the reference's assert_array_almost_equal decimals
+    for a, b in ((m1, m2_d), (m1_d, m2), (m1.tocsc(), m2_d), (m1_d, m2.tocsc())):
+        got = sdb.dot_product_mkl(a, b)
+        assert got.shape == want.shape and np.abs(got - want).max() < tol
+        out = np.ones(want.shape, dtype=dtype, order=order)
+        got = sdb.dot_product_mkl(a, b, out=out, out_scalar=3.0)
+        assert got is out and np.abs(got - (want + 3.0)).max() < tol
+    got = sdb.dot_product_mkl(m1, m2)
+    assert sp.issparse(got) and np.abs(got.toarray() - want).max() < tol
+    got = sdb.dot_product_mkl(m1, m2, dense=True)
+    assert np.abs(got - want).max() < tol
