@@ -18,6 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libsdb200.so")
+SHIM_SRC = os.path.join(CSRC, "mkl_shim.cpp")
+SHIM_LIB = os.path.join(HERE, "libsdb200_mkl.so")  # oneMKL symbol names over libsdb200 (see csrc/mkl_shim.cpp)
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3",
@@ -82,7 +84,22 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    build_shim(force)
     return LIB
+
+
+def build_shim(force=False):
+    """libsdb200_mkl.so: plain C++ (g++), links libsdb200.so from its own directory ($ORIGIN)."""
+    if not (force or not os.path.exists(SHIM_LIB)
+            or os.path.getmtime(SHIM_LIB) < max(os.path.getmtime(SHIM_SRC), os.path.getmtime(LIB))):
+        return SHIM_LIB
+    gxx = shutil.which("g++") or "/usr/bin/g++"
+    cmd = [gxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-o", SHIM_LIB, SHIM_SRC,
+           "-L" + HERE, "-l:libsdb200.so", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"shim build failed:\n{r.stdout}\n{r.stderr}")
+    return SHIM_LIB
 
 
 if __name__ == "__main__":
