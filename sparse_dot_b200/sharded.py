@@ -255,3 +255,87 @@ def spmm_sharded(a_csr, x, world_size, rank, allgather="fused", group=None, out=
         plan.synchronize()
         result = plan.read_panel()
     return result
+
+
+# --------------------------------------------------------------------------- SpGEMM / gram sharding
+def spgemm_sharded(a_csr, b_csr, world_size, rank, group=None, reorder_output=False):
+    """C = A @ B with the rows of A split nnz-balanced across ranks and B replicated: every rank multiplies
+    its row block on its GPU (dot_product_mkl -> sdb_spgemm), the blocks are independent CSR row ranges, so
+    the only exchange is an all-gather of the finished blocks, which are stacked (row offsets shifted) on
+    the host.  Every rank returns the full product."""
+    import scipy.sparse as sps
+
+    from .api import dot_product_mkl
+
+    bounds = partition_rows(a_csr.indptr, world_size)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    if hi > lo:
+        block = dot_product_mkl(row_block(a_csr, lo, hi), b_csr, reorder_output=reorder_output)
+    else:
+        block = sps.csr_matrix((0, b_csr.shape[1]), dtype=a_csr.dtype)
+    blocks = _all_gather_obj(block, world_size, group)
+    return stack_row_blocks(blocks, b_csr.shape[1])
+
+
+def stack_row_blocks(blocks, n_cols):
+    """Consecutive CSR row blocks -> one CSR matrix, without touching the entries: data / indices back to
+    back, every block's indptr shifted by the running nnz (int32 index arrays when they fit, scipy's rule)."""
+    import scipy.sparse as sps
+
+    rows = sum(blk.shape[0] for blk in blocks)
+    data = np.concatenate([blk.data for blk in blocks])
+    indices = np.concatenate([blk.indices for blk in blocks])
+    offsets = np.cumsum([0] + [blk.nnz for blk in blocks])
+    indptr = np.concatenate([[0]] + [blk.indptr[1:].astype(np.int64) + offsets[i] for i, blk in enumerate(blocks)])
+    it = np.int32 if indptr[-1] <= np.iinfo(np.int32).max and n_cols <= np.iinfo(np.int32).max else np.int64
+    return sps.csr_matrix((data, indices.astype(it, copy=False), indptr.astype(it)), shape=(rows, n_cols))
+
+
+def gram_dense_sharded(a_csr, world_size, rank, group=None):
+    """Dense upper triangle of A^T A with the ROWS of A split across ranks: A^T A = sum over row blocks of
+    A_s^T A_s, so every rank forms the partial gram of its block on its GPU (sdb_syrkd_dev, device
+    resident) and the partial panels are summed with one all-reduce — NCCL on the device panels when the
+    process group is NCCL, otherwise on host copies.  Every rank returns the full n x n array."""
+    from . import _handles as _h2
+
+    n = a_csr.shape[1]
+    dtype = np.dtype(a_csr.dtype)
+    bounds = partition_rows(a_csr.indptr, world_size)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    panel = _DevBuf(n * n * dtype.itemsize)
+    try:
+        block = row_block(a_csr, lo, hi)
+        zero, one = scalar_pair(0.0), scalar_pair(1.0)
+        if block.nnz > 0:
+            handle, _, _ = _h2.create(block)
+            with handle:
+                # the kernel never writes the strict lower triangle: start from a zero panel
+                host_zero = np.zeros((n, n), dtype=dtype)
+                check(SDB.lib.sdb_memcpy(panel.ptr, host_zero.ctypes.data_as(_ct.c_void_p), host_zero.nbytes, 1),
+                      "sdb_memcpy")
+                check(SDB.lib.sdb_syrkd_dev(_lib.OP_T, handle.ref, one, zero, panel.ptr, _lib.LAYOUT_C, n, None),
+                      "sdb_syrkd_dev")
+                check(SDB.lib.sdb_device_synchronize(), "sdb_device_synchronize")
+        else:
+            host_zero = np.zeros((n, n), dtype=dtype)
+            check(SDB.lib.sdb_memcpy(panel.ptr, host_zero.ctypes.data_as(_ct.c_void_p), host_zero.nbytes, 1),
+                  "sdb_memcpy")
+        if world_size > 1:
+            import torch
+            import torch.distributed as dist
+
+            if dist.get_backend(group) == "nccl":
+                t = torch.as_tensor(_CudaView(panel.ptr.value, (n, n), dtype), device="cuda")
+                dist.all_reduce(t, group=group)
+                torch.cuda.synchronize()
+            else:
+                host = np.empty((n, n), dtype=dtype)
+                check(SDB.lib.sdb_memcpy(host.ctypes.data_as(_ct.c_void_p), panel.ptr, host.nbytes, 2), "sdb_memcpy")
+                t = torch.from_numpy(host)
+                dist.all_reduce(t, group=group)
+                return host
+        out = np.empty((n, n), dtype=dtype)
+        check(SDB.lib.sdb_memcpy(out.ctypes.data_as(_ct.c_void_p), panel.ptr, out.nbytes, 2), "sdb_memcpy")
+        return out
+    finally:
+        panel.free()

@@ -86,3 +86,52 @@ def test_two_rank_fused_allgather_matches_oracle():
     for rank, err in results:
         assert isinstance(err, float), f"rank {rank} failed: {err}"
         assert err <= 1e-5, f"rank {rank}: full panel differs from the oracle ({err:.2e})"
+
+
+def _worker_products(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sparse_dot_b200 as sdb
+        from sparse_dot_b200 import _lib, sharded
+
+        _lib.check(_lib.SDB.lib.sdb_set_device(rank % sdb.device_count()), "sdb_set_device")
+        a = cs.rmat_csr(11, 8, np.float64, seed=1)
+        b = cs.rmat_csr(11, 8, np.float64, seed=2)
+        c = sharded.spgemm_sharded(a, b, world, rank, reorder_output=True)
+        w = orc.c_spgemm(a, b, sort=True)
+        ok_struct = bool(np.array_equal(c.indptr, w.indptr) and np.array_equal(c.indices, w.indices))
+        err = cs.rel_err(c.data, w.data)
+        m1, _ = cs.fixture_pair(np.float64)
+        g = sharded.gram_dense_sharded(m1, world, rank)
+        wg = orc.c_syrkd(m1)
+        gerr = float(np.abs(g - wg).max())
+        q.put((rank, ok_struct, err, gerr))
+    except Exception as e:
+        q.put((rank, repr(e), None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_spgemm_and_gram_sharding():
+    """SURVEY §8e last row: SpGEMM sharded by rows of A (B replicated, blocks concatenated) and the dense
+    gram as an all-reduce of per-row-block partial grams."""
+    import torch.multiprocessing as mp
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_products, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok_struct, err, gerr in results:
+        assert ok_struct is True, f"rank {rank}: {ok_struct}"
+        assert err <= 1e-12 and gerr <= 1e-10, (rank, err, gerr)

@@ -75,3 +75,18 @@ def test_two_rank_row_sharding_assembles_the_full_product():
         assert bounds[0] == 0 and bounds[-1] == 1200
         assert abs(nnz_per[0] - nnz_per[1]) <= 80  # balanced by nnz (within one 40-entry row each side), not by rows
         assert bounds[1] < 600
+
+
+def test_stack_row_blocks_is_exact():
+    """The host-side assembly of a row-sharded sparse product (spgemm_sharded) reproduces the arrays of the
+    unsharded matrix exactly, including empty blocks."""
+    from sparse_dot_b200 import sharded
+    from tests import _cases as cs
+
+    c = cs.rmat_csr(10, 6, np.float64, seed=3)
+    bounds = [0, 100, 100, 700, c.shape[0]]
+    blocks = [sharded.row_block(c, bounds[i], bounds[i + 1]) for i in range(4)]
+    got = sharded.stack_row_blocks(blocks, c.shape[1])
+    assert got.shape == c.shape
+    assert np.array_equal(got.indptr, c.indptr) and np.array_equal(got.indices, c.indices)
+    assert np.array_equal(got.data, c.data)
