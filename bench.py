@@ -130,11 +130,24 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_spmm_runner(a, x, y0, threads=None):
-    """The reference's CPU path for this workload: real oneMKL through the reference's
-    call sequence when reachable (oracle/mkl_ref.py), else the C restatement."""
+    """The reference's CPU path for this workload, best available first: (1) the UNMODIFIED reference
+    package's own dot_product_mkl on real oneMKL (oracle/ref_pkg.py), (2) real oneMKL through the
+    reference's call sequence (oracle/mkl_ref.py), (3) the C restatement (oracle/sdb_oracle.c)."""
     from oracle import mkl_ref
     from oracle import oracle as orc
 
+    ref_pkg, ref_status = try_reference_package()
+    if ref_pkg is not None and not threads:
+        from oracle import ref_pkg as _rp
+
+        y = y0.copy()
+
+        def step():
+            ref_pkg.dot_product_mkl(a, x, out=y, out_scalar=BETA)
+            return y
+
+        return step, "reference", _rp.max_threads(), \
+            "UNMODIFIED sparse_dot_mkl.dot_product_mkl(csr, ndarray, out=, out_scalar=) from baseline/_ref; " + ref_status
     if mkl_ref.available():
         if threads:
             mkl_ref.set_threads(threads)
@@ -162,37 +175,19 @@ def cpu_spmm_runner(a, x, y0, threads=None):
 
 
 def try_reference_package():
-    """The unmodified reference installed under baseline/_ref (pip --no-deps).  It needs libmkl_rt,
-    which this image does not have, so the import is expected to fail; the outcome is reported."""
-    ref = os.path.join(ROOT, "baseline", "_ref")
-    if not os.path.isdir(os.path.join(ref, "sparse_dot_mkl")):
-        return None, "baseline/_ref/sparse_dot_mkl not installed"
-    sys.path.insert(0, ref)
-    try:
-        import sparse_dot_mkl  # noqa: F401
+    """The UNMODIFIED reference (baseline/_ref) on real oneMKL; see oracle/ref_pkg.py."""
+    from oracle import ref_pkg
 
-        return sparse_dot_mkl, "imported"
-    except Exception as e:  # ImportError (no libmkl_rt) or AttributeError (partial MKL in libtorch_cpu)
-        return None, f"{type(e).__name__}: {str(e).splitlines()[0][:160]}"
-    finally:
-        sys.path.remove(ref)
+    return ref_pkg.load()
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ref_pkg, ref_status = try_reference_package()
     a, x, y0 = make_workload(M_ROWS, K_COLS, NNZ_PER_ROW, N_DENSE, seed=0)
-    if ref_pkg is not None:  # a real libmkl_rt is present: time the unmodified package itself
-        y = y0.copy()
-        cores, kind = os.cpu_count(), "reference"
-        what = "unmodified sparse_dot_mkl.dot_product_mkl(csr, ndarray, out=, out_scalar=) from baseline/_ref"
-
-        def step():
-            ref_pkg.dot_product_mkl(a, x, out=y, out_scalar=BETA)
-    else:
-        step, kind, cores, what = cpu_spmm_runner(a, x, y0)
+    step, kind, cores, what = cpu_spmm_runner(a, x, y0)
+    ref_status = what
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()

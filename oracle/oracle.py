@@ -42,6 +42,18 @@ def build(force=False):
     return _SO
 
 
+def build_ref(force=False):
+    """Compile mkl_fwd.c -> oracle/_ref/libmkl_fwd.so (glue for running the unmodified reference on the real
+    oneMKL inside libtorch_cpu.so; see oracle/ref_pkg.py).  Returns the path, or None if it cannot be built."""
+    so = os.path.join(_HERE, "_ref", "libmkl_fwd.so")
+    src = os.path.join(_HERE, "mkl_fwd.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        r = subprocess.run(["make", "-s", "-C", _HERE, "_ref/libmkl_fwd.so"], capture_output=True, text=True)
+        if r.returncode != 0:
+            return None
+    return so
+
+
 _lib = None
 
 

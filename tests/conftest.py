@@ -15,14 +15,20 @@ os.environ.setdefault("MKL_NUM_THREADS", "1")
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     # build (no-op when up to date); nvcc and gcc both work without a GPU
-    from sparse_dot_b200 import build as _build
-
     lib = os.path.join(ROOT, "sparse_dot_b200", "libsdb200.so")
     if not os.path.exists(lib):
+        # by path: importing the package needs the library this builds
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location(
+            "_sdb200_build", os.path.join(ROOT, "sparse_dot_b200", "build.py"))
+        _build = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_build)
         _build.build()
     from oracle import oracle as _oracle
 
     _oracle.build()
+    _oracle.build_ref()
 
 
 def _has_gpu():
