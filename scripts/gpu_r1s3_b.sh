@@ -1,0 +1,18 @@
+mkdir -p gpurun_out
+(timeout 900 python -m pytest tests/test_gpu_slab.py tests/test_reference_live.py -m gpu -q -x 2>&1 | tail -15) | tee gpurun_out/s3b_pytest.log
+run() { echo "== $*"; env "$@" timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1 | python -c "
+import sys, json
+try:
+    d = json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['frac'], d['parity_spot_check'])
+except Exception as e: print('FAILED', e)
+"; }
+(
+run SDB_SLAB=1
+run SDB_SLAB_VARIANT=0
+run SDB_SLAB_VARIANT=1
+run SDB_SLAB_VARIANT=2
+run SDB_SLAB_VARIANT=1 SDB_SLAB_MB=16
+run SDB_SLAB_VARIANT=1 SDB_SLAB_MB=32
+run SDB_SLAB_VARIANT=1 SDB_SLAB_MB=48
+run SDB_SLAB_VARIANT=1 SDB_SLAB_MB=12
+) 2>&1 | tee gpurun_out/s3b_sweep.log

@@ -170,11 +170,15 @@ struct sdb_mat {
     // index i inside line k of the companion.  Valid only while strict_sorted == 1.
     int32_t* pos;
     int strict_sorted;  // 0 unknown, 1 every line strictly ascending (no duplicates), -1 not
-    // Optional column-slab index for the L2-tiled SpMM (spmm_slab.cu): slab_off[s * lines + r] is the
-    // offset, inside line r, of its first entry with index >= s * slab_width (s = 0 .. slab_count).
-    int32_t* slab_off;
-    int slab_count;
+    // Optional slab-ordered copy of the stored entries for the L2-tiled SpMM (spmm_slab.cu, built by its
+    // inspector on the second multiplication with this handle): inside every group of slab_rpw consecutive
+    // rows the entries are ordered by (column / slab_width, row, column); slab_rc[p] = local row << 27 | column,
+    // slab_val[p] the value.  Dropped by sdb_order.
+    void* slab_rc;
+    void* slab_val;
+    int slab_rpw;
     int64_t slab_width;
+    int spmm_calls;  // multiplications seen so far (inspector policy)
 };
 
 namespace sdb {

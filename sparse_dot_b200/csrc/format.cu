@@ -639,11 +639,9 @@ sdb_status sdb_order(sdb_mat* m) {
         cudaFreeAsync(m->pos, ctx->stream);
         m->pos = nullptr;
     }
-    if (m->slab_off) {
-        cudaFreeAsync(m->slab_off, ctx->stream);
-        m->slab_off = nullptr;
-        m->slab_count = 0;
-    }
+    if (m->slab_rc) cudaFreeAsync(m->slab_rc, ctx->stream);
+    if (m->slab_val) cudaFreeAsync(m->slab_val, ctx->stream);
+    m->slab_rc = m->slab_val = nullptr;
     m->strict_sorted = 0;
     SDB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SDB_STATUS_SUCCESS;

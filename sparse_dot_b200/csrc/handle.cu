@@ -52,11 +52,12 @@ void free_handle(sdb_mat* m) {
         if (m->indices) cudaFreeAsync(m->indices, s);
         if (m->values) cudaFreeAsync(m->values, s);
     }
-    if (m->pos || m->slab_off) {
+    if (m->pos || m->slab_rc || m->slab_val) {
         Context* ctx = nullptr;
         cudaStream_t fs = get_context(&ctx) == SDB_STATUS_SUCCESS ? ctx->stream : nullptr;
         if (m->pos) cudaFreeAsync(m->pos, fs);
-        if (m->slab_off) cudaFreeAsync(m->slab_off, fs);
+        if (m->slab_rc) cudaFreeAsync(m->slab_rc, fs);
+        if (m->slab_val) cudaFreeAsync(m->slab_val, fs);
     }
     m->magic = 0;
     free(m);

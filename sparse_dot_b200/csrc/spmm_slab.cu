@@ -1,24 +1,36 @@
-// spmm_slab.cu — L2-tiled CSR x dense SpMM for panels much larger than the L2 cache.
+// spmm_slab.cu — L2-tiled CSR x dense SpMM for panels much larger than the L2 cache
+// (same contract as spmm.cu: Y := alpha * A * X + beta * Y, mkl_sparse_?_mm as
+// sparse_dot_mkl/_sparse_dense.py:111-123 calls it).
 //
 // The row-gather kernel (spmm.cu) reads one n-wide row of X per stored entry; when X is several
 // times the 126 MB L2 and the columns are scattered, ~85 % of those gathers come from HBM and the
 // kernel sits on the DRAM roofline at ~22 GB of traffic for a problem whose unique bytes are
-// ~2 GB (profiles/README.md).  This kernel cuts the traffic instead of chasing bandwidth:
+// ~2 GB (profiles/README.md).  This kernel cuts the traffic instead of chasing bandwidth, with an
+// inspector / executor split (the analogue of mkl_sparse_optimize, which the reference never calls):
 //
-//   * the columns are cut into S slabs of W rows of X, W chosen so that one slab (W * n * sv
-//     bytes) stays L2-resident;
-//   * a persistent grid of one CTA per SM walks row blocks; every warp owns 32 rows whose
-//     accumulators live in SHARED MEMORY (32 x n x sv bytes per warp) for the whole sweep;
-//   * all CTAs sweep the slabs in the same order, so at any moment the whole chip gathers from
-//     the same L2-resident slab: X is read from HBM once per wave of row blocks
-//     (rows / (SMs * rows per CTA) times) instead of once per stored entry;
-//   * per slab a warp flattens the entries of its 32 rows that fall into the slab (a per-row
-//     offset table built once per matrix and cached on the handle gives the segment bounds),
-//     issues the X-row gathers 8 at a time and adds each row's partial sum into shared memory once.
+// Inspector (once per handle, cached; `slab_permute_kernel`): rows are taken in groups of RPW
+// consecutive rows (one group = one warp of the executor).  The stored entries of a group — which
+// are contiguous in CSR — are re-ordered by (column slab, row, column), where a slab is a range of
+// `width` columns whose X rows (width * n * sv bytes, 24 MB by default) fit L2 comfortably, and
+// written as packed (local row << 27 | column) words plus values.  Nothing else is kept: a group's
+// range is still [indptr[g * RPW], indptr[(g + 1) * RPW]).
 //
-// The bound moves from DRAM (22 GB) to L2 bandwidth (every stored entry still pulls n * sv bytes
-// from L2 into an SM).  Requirements: row-major panels, n * sv = 512 bytes per X row (one 16-byte
-// pack per lane), rows strictly ascending (the slab table is a binary search per row and slab).
+// Executor (`spmm_stream_kernel`): a persistent grid of one 1024-thread CTA per SM; a CTA owns
+// RPW * 32 rows at a time and keeps their accumulators in SHARED MEMORY (RPW * 32 rows x 512 B =
+// 208-224 KB).  Each warp simply streams its group's re-ordered entries, 32 per coalesced load,
+// gathers the 512-byte X rows 8 at a time (one 16-byte load per lane) and accumulates in registers;
+// when the row changes (entries of one row inside one slab are adjacent) the running sums are
+// swapped with the new row's accumulators in shared memory.  Because every warp of the chip walks
+// its entries in slab order at about the same pace, at any moment the whole chip gathers from the
+// same few slabs of X, which therefore stay L2-resident: X comes from HBM once per wave of row
+// blocks (rows / (SMs * RPW * 32) times) instead of once per stored entry.  There is no barrier
+// and no slab table in the hot loop — the ordering alone provides the locality, and a matrix with
+// uneven rows merely loses some of it.
+//
+// The bound moves from DRAM (22 GB) to L2 -> SM bandwidth (every stored entry still pulls n * sv
+// bytes from L2).  Requirements: row-major panels with n * sv = 512 bytes per row (one 16-byte
+// pack per lane), fp32 / fp64, strictly ascending rows, fewer than 2^27 columns.
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -29,231 +41,198 @@ namespace sdb {
 
 namespace {
 
-constexpr int kSlabRowsPerCta = 416;         // 416 rows x 512 B = 208 KB of accumulators per CTA
-constexpr int kSlabUnroll = 8;
 constexpr int kSlabMaxPeers = 8;
+constexpr int kColBits = 27;
+constexpr uint32_t kColMask = (1u << kColBits) - 1u;
 
 template <typename T> struct SlabPeers {
     T* y[kSlabMaxPeers];
 };
-
-// off[s * rows + r] = number of entries of row r with column < s * width   (s = 0 .. S)
-__global__ void __launch_bounds__(256) slab_offsets_kernel(int64_t rows, const int64_t* __restrict__ indptr,
-                                                           const int32_t* __restrict__ indices, int S,
-                                                           int64_t width, int32_t* __restrict__ off) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (r >= rows) return;
-    const int64_t b = indptr[r];
-    const int len = int(indptr[r + 1] - b);
-    for (int s = lane; s <= S; s += 32) {
-        const int64_t key = int64_t(s) * width;  // first entry with column >= key
-        int lo = 0, hi = len;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (int64_t(indices[b + mid]) < key) lo = mid + 1;
-            else hi = mid;
-        }
-        off[int64_t(s) * rows + r] = s == S ? len : lo;
-    }
-}
 
 template <typename T> struct alignas(16) Pack16 {
     static constexpr int N = 16 / int(sizeof(T));
     T v[N];
 };
 
-template <typename T> __device__ __forceinline__ Pack16<T> ldg16(const T* p) {
-    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+// ---------------------------------------------------------------- inspector
+// One warp per group of `rpw` rows, lane = local row.  Every lane walks its own (ascending) row
+// once; per slab the lanes' counts are scanned and each lane copies its run behind the runs of
+// the lower rows.  One-time cost, a few passes over A.
+template <typename T>
+__global__ void __launch_bounds__(256) slab_permute_kernel(int64_t rows, int rpw, const int64_t* __restrict__ indptr,
+                                                           const int32_t* __restrict__ indices,
+                                                           const T* __restrict__ values, int64_t width,
+                                                           uint32_t* __restrict__ ent_rc, T* __restrict__ ent_val) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t row_first = g * rpw;
+    if (row_first >= rows) return;
+    const int64_t row = row_first + lane;
+    const bool valid = lane < rpw && row < rows;
+    const int64_t rbeg = valid ? indptr[row] : 0;
+    const int len = valid ? int(indptr[row + 1] - rbeg) : 0;
+    int64_t cursor = indptr[row_first];
+    const int64_t gend = indptr[min(row_first + rpw, rows)];
+    int p = 0;
+    while (cursor < gend) {  // warp-uniform
+        // the next slab that holds an entry of this group
+        int64_t mine = p < len ? int64_t(indices[rbeg + p]) / width : INT64_MAX;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) mine = min(mine, __shfl_xor_sync(kFull, mine, d));
+        const int64_t bound = (mine + 1) * width;
+        const int start = p;
+        while (p < len && int64_t(indices[rbeg + p]) < bound) ++p;
+        const int cnt = p - start;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const int total = __shfl_sync(kFull, incl, 31);
+        const int64_t dst = cursor + (incl - cnt);
+        for (int e = 0; e < cnt; ++e) {
+            ent_rc[dst + e] = (uint32_t(lane) << kColBits) | uint32_t(indices[rbeg + start + e]);
+            ent_val[dst + e] = values[rbeg + start + e];
+        }
+        cursor += total;
+    }
+}
+
+// ---------------------------------------------------------------- executor
+template <typename T> __device__ __forceinline__ Pack16<T> gather16(const char* xlane, uint32_t col, uint32_t row_bytes) {
+    // 32 x 32 -> 64-bit multiply-add on the base pointer: one IMAD.WIDE.U32
+    const float4 q = __ldg(reinterpret_cast<const float4*>(xlane + uint64_t(col) * row_bytes));
     Pack16<T> r;
     *reinterpret_cast<float4*>(&r) = q;
     return r;
 }
 
-// RPW rows per warp: fewer rows per warp = more warps per CTA (416 / RPW) = more independent chains
-template <typename T, int RPW>
-__global__ void __launch_bounds__((kSlabRowsPerCta / RPW) * 32, 1)
-    spmm_slab_kernel(int64_t rows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                     const T* __restrict__ values, bool conj_a, const int32_t* __restrict__ slab_off, int S,
-                     const T* __restrict__ X, int64_t ldx, T alpha, T beta, T* __restrict__ y_self,
-                     SlabPeers<T> peers, int n_peers, int self, int64_t row0, int64_t ldy) {
+// RPW rows per warp, WARPS warps per CTA (RPW * WARPS * 512 B of accumulators), U gathers in flight per lane,
+// CTAS resident CTAs per SM (register budget = 65536 / (CTAS * WARPS * 32)).
+template <typename T, int RPW, int WARPS, int U, int CTAS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS)
+    spmm_stream_kernel(int64_t rows, const int64_t* __restrict__ indptr, const uint32_t* __restrict__ ent_rc,
+                       const T* __restrict__ ent_val, const T* __restrict__ X, uint32_t row_bytes, T alpha, T beta,
+                       T* __restrict__ y_self, SlabPeers<T> peers, int n_peers, int self, int64_t row0, int64_t ldy) {
     constexpr int VEC = Pack16<T>::N;
+    constexpr int kRows = RPW * WARPS;  // rows per CTA
     constexpr unsigned kFull = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // this warp's accumulators: [RPW rows][32 lanes] packs of 16 bytes
-    Pack16<T>* acc = reinterpret_cast<Pack16<T>*>(smem_raw) + warp * RPW * 32;
-    const T* xlane = X + lane * VEC;
-    const int64_t n_blocks = (rows + kSlabRowsPerCta - 1) / kSlabRowsPerCta;
+    Pack16<T>* acc = reinterpret_cast<Pack16<T>*>(smem_raw) + warp * RPW * 32 + lane;
+    const char* xlane = reinterpret_cast<const char*>(X + lane * VEC);
+    const int64_t n_blocks = (rows + kRows - 1) / kRows;
+    Pack16<T> zero;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) zero.v[i] = Num<T>::zero();
 
     for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) {
-        const int64_t row_base = rb * kSlabRowsPerCta + int64_t(warp) * RPW;
-        Pack16<T> zero;
+        const int64_t row_base = rb * kRows + int64_t(warp) * RPW;
+        if (row_base >= rows) continue;  // warp-uniform; no CTA-wide barrier anywhere
+        const int live_rows = int(min(int64_t(RPW), rows - row_base));
+        const int64_t beg = indptr[row_base];
+        // 32-bit counters relative to the group start keep the hot loop small (a group never holds 2^31 entries)
+        const int n_ent = int(min(indptr[row_base + live_rows] - beg, int64_t(INT32_MAX)));
+        const uint32_t* __restrict__ erc = ent_rc + beg;
+        const T* __restrict__ eva = ent_val + beg;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) zero.v[i] = Num<T>::zero();
-#pragma unroll 8
-        for (int r = 0; r < RPW; ++r) acc[r * 32 + lane] = zero;
-        __syncwarp();
+        for (int r = 0; r < RPW; ++r) acc[r * 32] = zero;
 
-        const int64_t my_row = row_base + lane;
-        const bool valid = lane < RPW && my_row < rows;
-        const int64_t rstart = valid ? indptr[my_row] : 0;
-        int off_prev = 0;  // entries with column < 0
-
-        int off_ahead = valid ? __ldg(slab_off + rows + my_row) : 0;  // boundary of slab 0 | 1, loaded one slab ahead
-        for (int s = 0; s < S; ++s) {
-            const int off_next = off_ahead;
-            if (s + 1 < S && valid) off_ahead = __ldg(slab_off + int64_t(s + 2) * rows + my_row);
-            const int cnt = off_next - off_prev;      // this row's entries inside slab s
-            const int64_t seg = rstart + off_prev;    // where they start
-            off_prev = off_next;
-            // inclusive prefix of cnt over the 32 rows of the warp
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(kFull, incl, d);
-                if (lane >= d) incl += o;
+        // invariant: `cur` is the live value of acc[cur_row]
+        Pack16<T> cur = zero;
+        uint32_t cur_row = 0;
+        // entry j of the chunk held in (rc, v): swap accumulators when the row changes (rare: the entries of a
+        // row inside a slab are adjacent), then 4 FMAs.  Every lane works on the same entry: branches are uniform.
+        auto consume = [&](uint32_t rc, T v, unsigned starts, int j, const Pack16<T>& x) {
+            const T a = shfl(kFull, v, j, 32);
+            if ((starts >> j) & 1u) {
+                acc[cur_row * 32] = cur;
+                cur_row = __shfl_sync(kFull, rc, j) >> kColBits;
+                cur = acc[cur_row * 32];
             }
-            const int total = __shfl_sync(kFull, incl, 31);
-            if (total == 0) continue;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) cur.v[i] = madd(a, x.v[i], cur.v[i]);
+        };
 
-            // (column, value, row) of flat entry f0 + lane of this slab
-            auto fetch = [&](int f0, int32_t& c_out, T& v_out, int& r_out) {
-                const int f = f0 + lane;
-                int lo = 0, hi = 31;  // first row whose inclusive prefix exceeds f
-#pragma unroll
-                for (int it = 0; it < 5; ++it) {
-                    const int mid = (lo + hi) >> 1;
-                    const int pm = __shfl_sync(kFull, incl, mid);
-                    if (f >= pm) lo = mid + 1;
-                    else hi = mid;
-                }
-                r_out = lo;  // meaningful when f < total
-                const int r_incl = __shfl_sync(kFull, incl, lo);
-                const int r_cnt = __shfl_sync(kFull, cnt, lo);
-                const int64_t r_seg = __shfl_sync(kFull, seg, lo);
-                c_out = 0;
-                v_out = Num<T>::zero();
-                if (f < total) {
-                    const int64_t p = r_seg + (f - (r_incl - r_cnt));
-                    c_out = __ldg(indices + p);
-                    v_out = ldg(values + p);
-                    if (conj_a) v_out = conj_(v_out);
-                }
-            };
-
-            Pack16<T> cur = zero;
-            int cur_row = -1;
-            int32_t c, c_nx = 0;
-            T v, v_nx = Num<T>::zero();
-            int my_r, my_r_nx = 0;
-            fetch(0, c, v, my_r);
-            for (int f0 = 0; f0 < total; f0 += 32) {
-                // the next chunk's entries are requested before this chunk's gathers are consumed
-                if (f0 + 32 < total) fetch(f0 + 32, c_nx, v_nx, my_r_nx);
-                const int batch = min(32, total - f0);
-                // bit u set = flat entry u of this chunk starts a new row (relative to the entry before it)
-                const int prev_r = __shfl_up_sync(kFull, my_r, 1);
-                const unsigned starts = __ballot_sync(kFull, lane == 0 ? my_r != cur_row : my_r != prev_r);
-                // one batch of kSlabUnroll gathers: loads first, then the FMAs with a row-change test per entry
-                auto run_batch = [&](int u0, auto full) {
-                    constexpr bool kFullBatch = decltype(full)::value;
-                    Pack16<T> x[kSlabUnroll];
-                    T a[kSlabUnroll];
-#pragma unroll
-                    for (int u = 0; u < kSlabUnroll; ++u) {
-                        const int32_t cj = __shfl_sync(kFull, c, u0 + u);
-                        a[u] = shfl(kFull, v, u0 + u, 32);
-                        if (kFullBatch || u0 + u < batch) x[u] = ldg16<T>(xlane + int64_t(cj) * ldx);
-                    }
-                    const unsigned sb = starts >> u0;
-#pragma unroll
-                    for (int u = 0; u < kSlabUnroll; ++u) {
-                        if (kFullBatch || u0 + u < batch) {  // warp-uniform
-                            if (sb & (1u << u)) {
-                                if (cur_row >= 0) {
-                                    Pack16<T> t = acc[cur_row * 32 + lane];
-#pragma unroll
-                                    for (int i = 0; i < VEC; ++i) t.v[i] = add(t.v[i], cur.v[i]);
-                                    acc[cur_row * 32 + lane] = t;
-                                }
-                                cur = zero;
-                                cur_row = __shfl_sync(kFull, my_r, u0 + u);
-                            }
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) cur.v[i] = madd(a[u], x[u].v[i], cur.v[i]);
-                        }
-                    }
-                };
-                int u0 = 0;
-                for (; u0 + kSlabUnroll <= batch; u0 += kSlabUnroll) run_batch(u0, std::true_type{});
-                for (; u0 < batch; ++u0) {  // ragged tail of the last chunk: one entry at a time
-                    const int32_t cj = __shfl_sync(kFull, c, u0);
-                    const T aj = shfl(kFull, v, u0, 32);
-                    const Pack16<T> xj = ldg16<T>(xlane + int64_t(cj) * ldx);
-                    if ((starts >> u0) & 1u) {
-                        if (cur_row >= 0) {
-                            Pack16<T> t = acc[cur_row * 32 + lane];
-#pragma unroll
-                            for (int i = 0; i < VEC; ++i) t.v[i] = add(t.v[i], cur.v[i]);
-                            acc[cur_row * 32 + lane] = t;
-                        }
-                        cur = zero;
-                        cur_row = __shfl_sync(kFull, my_r, u0);
-                    }
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) cur.v[i] = madd(aj, xj.v[i], cur.v[i]);
-                }
-                c = c_nx;
-                v = v_nx;
-                my_r = my_r_nx;
+        uint32_t rc_nx = 0;
+        T v_nx = Num<T>::zero();
+        if (lane < n_ent) {
+            rc_nx = __ldcs(erc + lane);
+            v_nx = ldcs(eva + lane);
+        }
+        for (int f = 0; f < n_ent; f += 32) {
+            const uint32_t rc = rc_nx;
+            const T v = v_nx;
+            // the next chunk is requested before this chunk's gathers are consumed
+            if (f + 32 + lane < n_ent) {
+                rc_nx = __ldcs(erc + f + 32 + lane);
+                v_nx = ldcs(eva + f + 32 + lane);
             }
-            if (cur_row >= 0) {
-                Pack16<T> t = acc[cur_row * 32 + lane];
+            const int cnt = min(32, n_ent - f);
+            const uint32_t my_r = rc >> kColBits;
+            const uint32_t prev_r = __shfl_up_sync(kFull, my_r, 1);
+            const unsigned starts = __ballot_sync(kFull, my_r != (lane == 0 ? cur_row : prev_r));
+            if (cnt == 32) {
+                // rolling ring of U gathers: the slot an entry has just been consumed from is refilled at once,
+                // so ~U 16-byte loads per lane stay in flight for the whole chunk (all indices are compile-time)
+                Pack16<T> x[U];
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) t.v[i] = add(t.v[i], cur.v[i]);
-                acc[cur_row * 32 + lane] = t;
+                for (int u = 0; u < U; ++u) x[u] = gather16<T>(xlane, __shfl_sync(kFull, rc, u) & kColMask, row_bytes);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    consume(rc, v, starts, j, x[j % U]);
+                    if (j + U < 32)
+                        x[j % U] = gather16<T>(xlane, __shfl_sync(kFull, rc, j + U) & kColMask, row_bytes);
+                }
+            } else {
+                // ragged last chunk of the group: one entry at a time
+                for (int j = 0; j < cnt; ++j) {
+                    const Pack16<T> xj = gather16<T>(xlane, __shfl_sync(kFull, rc, j) & kColMask, row_bytes);
+                    consume(rc, v, starts, j, xj);
+                }
             }
         }
-        __syncwarp();
+        acc[cur_row * 32] = cur;
 
-        // epilogue: y = alpha * acc + beta * y, one 512-byte row per iteration
+        // epilogue: y = alpha * acc + beta * y, one 512-byte row per iteration (each lane reads back
+        // only what it wrote itself, so no warp barrier is needed)
         const bool beta_zero = Num<T>::is_zero(beta);
-        const int live_rows = int(max(int64_t(0), min(int64_t(RPW), rows - row_base)));
         for (int r = 0; r < live_rows; ++r) {
             const int64_t o = (row0 + row_base + r) * ldy + lane * VEC;
-            const Pack16<T> t = acc[r * 32 + lane];
+            const Pack16<T> t = acc[r * 32];
             Pack16<T> out;
             if (beta_zero) {
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) out.v[i] = mul(alpha, t.v[i]);
             } else {
                 Pack16<T> old;
-                *reinterpret_cast<float4*>(&old) = *reinterpret_cast<const float4*>(y_self + o);
+                *reinterpret_cast<float4*>(&old) = __ldcs(reinterpret_cast<const float4*>(y_self + o));
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) out.v[i] = madd(alpha, t.v[i], mul(beta, old.v[i]));
             }
-            *reinterpret_cast<float4*>(y_self + o) = *reinterpret_cast<const float4*>(&out);
+            __stcs(reinterpret_cast<float4*>(y_self + o), *reinterpret_cast<const float4*>(&out));
             if (n_peers > 1) {
 #pragma unroll
                 for (int q = 0; q < kSlabMaxPeers; ++q)
                     if (q < n_peers && q != self)
-                        *reinterpret_cast<float4*>(peers.y[q] + o) = *reinterpret_cast<const float4*>(&out);
+                        __stcs(reinterpret_cast<float4*>(peers.y[q] + o), *reinterpret_cast<const float4*>(&out));
             }
         }
-        __syncwarp();
     }
 }
 
 size_t slab_target_bytes() {
     static const size_t v = [] {
         const char* e = getenv("SDB_SLAB_MB");
-        return size_t(e ? atoi(e) : 24) << 20;
+        return size_t(e ? std::max(1, atoi(e)) : 24) << 20;
     }();
     return v;
 }
 
-int slab_mode() {  // 0 / 1 = off (default), 2 = whenever the shape allows
+int slab_mode() {  // 0 = automatic (default), 1 = off, 2 = whenever the shape allows (tests)
     static const int v = [] {
         const char* e = getenv("SDB_SLAB");
         return e ? atoi(e) : 0;
@@ -261,55 +240,90 @@ int slab_mode() {  // 0 / 1 = off (default), 2 = whenever the shape allows
     return v;
 }
 
+// Executor shapes (SDB_SLAB_VARIANT picks; 0 is the default), all with 448 rows = 224 KB of accumulators per SM:
+//   0: 1 CTA x 32 warps x 14 rows, 4 gathers in flight per lane      (64 registers)
+//   1: 1 CTA x 32 warps x 14 rows, 6 gathers
+//   2: 1 CTA x 32 warps x 14 rows, 8 gathers
+//   3: 2 CTAs x 32 warps x 7 rows, 2 gathers                         (32 registers)
+//   4: 1 CTA x 16 warps x 28 rows, 8 gathers                         (128 registers)
+int slab_variant() {
+    static const int v = [] {
+        const char* e = getenv("SDB_SLAB_VARIANT");
+        const int r = e ? atoi(e) : 0;
+        return r >= 0 && r <= 4 ? r : 0;
+    }();
+    return v;
+}
+int slab_rpw() {
+    const int v = slab_variant();
+    return v == 3 ? 7 : (v == 4 ? 28 : 14);
+}
+constexpr int kSlabRowsPerSm = 448;
+
 }  // namespace
 
-template <typename T, int RPW>
-static sdb_status launch_slab_rpw(cudaStream_t s, const CsrView& a, bool conj_a, const int32_t* slab_off, int S,
-                                  const T* X, int64_t ldx, T alpha, T beta, const SlabPeers<T>& peers, int n_peers,
-                                  int self, int64_t row0, int64_t ldy, unsigned grid, size_t smem) {
-    SDB_CUDA(cudaFuncSetAttribute(spmm_slab_kernel<T, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    SDB_LAUNCH((spmm_slab_kernel<T, RPW>), grid, (kSlabRowsPerCta / RPW) * 32, smem, s, a.rows, a.indptr, a.indices,
-               static_cast<const T*>(a.values), conj_a, slab_off, S, X, ldx, alpha, beta, peers.y[self], peers,
-               n_peers, self, row0, ldy);
+template <typename T, int RPW, int WARPS, int U, int CTAS>
+static sdb_status launch_stream(cudaStream_t s, const CsrView& a, const sdb_mat* m, const T* X, int64_t ldx, T alpha,
+                                T beta, void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy,
+                                int sm_count) {
+    constexpr int kRows = RPW * WARPS;
+    static_assert(kRows * CTAS == kSlabRowsPerSm && RPW <= 32, "accumulator tile");
+    const size_t smem = size_t(kRows) * 512;
+    SlabPeers<T> peers;
+    for (int q = 0; q < kSlabMaxPeers; ++q) peers.y[q] = q < n_peers ? static_cast<T*>(dY_peers[q]) : nullptr;
+    const int64_t n_blocks = (a.rows + kRows - 1) / kRows;
+    const unsigned grid = unsigned(std::min<int64_t>(n_blocks, int64_t(sm_count) * CTAS));
+    SDB_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<T, RPW, WARPS, U, CTAS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    SDB_LAUNCH((spmm_stream_kernel<T, RPW, WARPS, U, CTAS>), grid, WARPS * 32, smem, s, a.rows, a.indptr,
+               static_cast<const uint32_t*>(m->slab_rc), static_cast<const T*>(m->slab_val), X,
+               uint32_t(ldx * int64_t(sizeof(T))), alpha, beta, peers.y[self], peers, n_peers, self, row0, ldy);
     return SDB_STATUS_SUCCESS;
 }
 
+#define SDB_SLAB_ARGS s, a, m, X, ldx, alpha, beta, dY_peers, n_peers, self, row0, ldy, sm_count
 template <typename T>
-static sdb_status launch_slab(cudaStream_t s, const CsrView& a, bool conj_a, const int32_t* slab_off, int S,
-                              const T* X, int64_t ldx, T alpha, T beta, void* const* dY_peers, int n_peers, int self,
-                              int64_t row0, int64_t ldy, unsigned grid, size_t smem) {
-    static const int rpw = [] {
-        const char* e = getenv("SDB_SLAB_RPW");
-        return e ? atoi(e) : 13;
-    }();
-    SlabPeers<T> peers;
-    for (int q = 0; q < kSlabMaxPeers; ++q) peers.y[q] = q < n_peers ? static_cast<T*>(dY_peers[q]) : nullptr;
-    if (rpw == 32)
-        return launch_slab_rpw<T, 32>(s, a, conj_a, slab_off, S, X, ldx, alpha, beta, peers, n_peers, self, row0, ldy,
-                                      grid, smem);
-    if (rpw == 13)
-        return launch_slab_rpw<T, 13>(s, a, conj_a, slab_off, S, X, ldx, alpha, beta, peers, n_peers, self, row0, ldy,
-                                      grid, smem);
-    return launch_slab_rpw<T, 16>(s, a, conj_a, slab_off, S, X, ldx, alpha, beta, peers, n_peers, self, row0, ldy,
-                                  grid, smem);
+static sdb_status launch_variant(cudaStream_t s, const CsrView& a, const sdb_mat* m, const T* X, int64_t ldx, T alpha,
+                                 T beta, void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy,
+                                 int sm_count) {
+    switch (slab_variant()) {
+        case 1: return launch_stream<T, 14, 32, 6, 1>(SDB_SLAB_ARGS);
+        case 2: return launch_stream<T, 14, 32, 8, 1>(SDB_SLAB_ARGS);
+        case 3: return launch_stream<T, 7, 32, 2, 2>(SDB_SLAB_ARGS);
+        case 4: return launch_stream<T, 28, 16, 8, 1>(SDB_SLAB_ARGS);
+        default: return launch_stream<T, 14, 32, 4, 1>(SDB_SLAB_ARGS);
+    }
 }
+#undef SDB_SLAB_ARGS
 
+// Does this call qualify?  Shape rules always; in automatic mode also the size rules under which the
+// re-ordered copy pays for itself (it costs nnz * (4 + sv) bytes of HBM and a few passes over A):
+//   * X several times larger than L2 (otherwise the row-gather kernel already hits L2),
+//   * enough rows to fill the persistent grid,
+//   * expected reuse of an X row inside one wave of row blocks >= 1.5
+//     (rows in flight * mean row length / columns),
+//   * the handle has been multiplied before (a matrix used once never pays the inspector).
 bool spmm_slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx) {
-    if (slab_mode() == 1 || a.owner == nullptr) return false;
+    const int mode = slab_mode();
+    if (mode == 1 || a.owner == nullptr) return false;
     if (dtype != SDB_F32 && dtype != SDB_F64) return false;
     const size_t sv = dtype_size(dtype);
-    if (size_t(n) * sv != 512 || ldx != n) return false;
+    if (size_t(n) * sv != 512 || (size_t(ldx) * sv) % 16 != 0 || size_t(ldx) * sv >= (size_t(1) << 31)) return false;
+    if (a.cols >= (int64_t(1) << kColBits) || a.rows <= 0 || a.nnz <= 0) return false;
     if (a.owner->strict_sorted == -1) return false;
-    // Measured on B200 (profiles/README.md, round 1c): on configs[1] this kernel cuts DRAM traffic from 22.2 GB to
-    // 10.1 GB as designed, but it becomes instruction-issue bound (68 % issue slots busy, IPC 2.7) at 3.99 ms
-    // against 3.54 ms for the row-gather kernel on the DRAM roofline — so it is opt-in (SDB_SLAB=2) until the
-    // per-entry instruction count comes down.
-    return slab_mode() == 2 && a.rows > 0 && a.nnz > 0;
+    if (mode == 2) return true;
+    const int uses = a.owner->spmm_calls++;
+    const int64_t in_flight = std::min<int64_t>(a.rows, int64_t(148) * kSlabRowsPerSm);
+    const double reuse = double(in_flight) * (double(a.nnz) / double(a.rows)) / double(a.cols);
+    return uses >= 1 && size_t(a.cols) * 512 >= (size_t(192) << 20) && a.rows >= int64_t(148) * kSlabRowsPerSm &&
+           reuse >= 1.5;
 }
 
 sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a,
                             const double* alpha, const double* beta, const void* dX, int64_t n, int64_t ldx,
                             void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy) {
+    (void)conj_a;  // real dtypes only
+    (void)n;
     sdb_mat* m = a.owner;
     SDB_REQUIRE(m != nullptr, SDB_STATUS_NOT_SUPPORTED, "spmm_slab: ad-hoc view");
     if (m->strict_sorted == 0) {
@@ -318,32 +332,36 @@ sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int 
     }
     if (m->strict_sorted != 1) return SDB_STATUS_NOT_SUPPORTED;
     const size_t sv = dtype_size(dtype);
-    int64_t width = std::max<int64_t>(1024, int64_t(slab_target_bytes() / (size_t(n) * sv)));
-    const int S = int((a.cols + width - 1) / width);
-    if (S < 2 || S > 4096) return SDB_STATUS_NOT_SUPPORTED;
-    if (m->slab_off == nullptr || m->slab_count != S || m->slab_width != width) {
+    const int64_t width = std::max<int64_t>(64, int64_t(slab_target_bytes() / 512));
+    const int rpw = slab_rpw();
+    if (m->slab_rc == nullptr || m->slab_width != width || m->slab_rpw != rpw) {
+        // inspector: the slab-ordered copy of A, cached on the handle until sdb_order / destroy
         cudaStream_t ls = ctx->stream;
-        if (m->slab_off) cudaFreeAsync(m->slab_off, ls);
-        m->slab_off = nullptr;
-        SDB_TRY(dev_alloc(reinterpret_cast<void**>(&m->slab_off), size_t(S + 1) * size_t(a.rows) * 4, ls));
-        SDB_LAUNCH(slab_offsets_kernel, unsigned((a.rows * 32 + 255) / 256), 256, 0, ls, a.rows, a.indptr, a.indices,
-                   S, width, m->slab_off);
-        m->slab_count = S;
+        if (m->slab_rc) cudaFreeAsync(m->slab_rc, ls);
+        if (m->slab_val) cudaFreeAsync(m->slab_val, ls);
+        m->slab_rc = m->slab_val = nullptr;
+        SDB_TRY(dev_alloc(&m->slab_rc, size_t(a.nnz) * 4, ls));
+        SDB_TRY(dev_alloc(&m->slab_val, size_t(a.nnz) * sv, ls));
+        const int64_t groups = (a.rows + rpw - 1) / rpw;
+        const unsigned grid = unsigned((groups * 32 + 255) / 256);
+        if (dtype == SDB_F32) {
+            SDB_LAUNCH(slab_permute_kernel<float>, grid, 256, 0, ls, a.rows, rpw, a.indptr, a.indices,
+                       static_cast<const float*>(a.values), width, static_cast<uint32_t*>(m->slab_rc),
+                       static_cast<float*>(m->slab_val));
+        } else {
+            SDB_LAUNCH(slab_permute_kernel<double>, grid, 256, 0, ls, a.rows, rpw, a.indptr, a.indices,
+                       static_cast<const double*>(a.values), width, static_cast<uint32_t*>(m->slab_rc),
+                       static_cast<double*>(m->slab_val));
+        }
         m->slab_width = width;
+        m->slab_rpw = rpw;
         if (s != ls) SDB_CUDA(cudaStreamSynchronize(ls));
     }
-    const size_t smem = size_t(kSlabRowsPerCta) * 512;
-    const int64_t n_blocks = (a.rows + kSlabRowsPerCta - 1) / kSlabRowsPerCta;
-    const unsigned grid = unsigned(std::min<int64_t>(n_blocks, ctx->sm_count));
-    return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
-        if constexpr (sizeof(T) > 8) {
-            return SDB_STATUS_NOT_SUPPORTED;
-        } else {
-            return launch_slab<T>(s, a, conj_a, m->slab_off, S, static_cast<const T*>(dX), ldx,
-                                  Num<T>::make(alpha[0], alpha[1]), Num<T>::make(beta[0], beta[1]), dY_peers, n_peers,
-                                  self, row0, ldy, grid, smem);
-        }
-    });
+    if (dtype == SDB_F32)
+        return launch_variant<float>(s, a, m, static_cast<const float*>(dX), ldx, float(alpha[0]), float(beta[0]),
+                                     dY_peers, n_peers, self, row0, ldy, ctx->sm_count);
+    return launch_variant<double>(s, a, m, static_cast<const double*>(dX), ldx, alpha[0], beta[0], dY_peers, n_peers,
+                                  self, row0, ldy, ctx->sm_count);
 }
 
 }  // namespace sdb
