@@ -323,6 +323,7 @@ def run_ours(args):
         ev[i + 1].record(stream)
     sync_all()
     launches = sdb.kernel_launches() - launches0
+    kernel_name = sdb.last_spmm_kernel()  # what the timed steps launched (same thread)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
@@ -385,9 +386,9 @@ def run_ours(args):
     achieved = g / (k_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath):  # ncu's DRAM bytes per launch for the kernel that was just timed (None if never captured)
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("kernels", {}).get(kernel_name, {}).get("dram_bytes_per_launch")
         except ValueError:
             traffic = None
 
@@ -412,7 +413,7 @@ def run_ours(args):
         "gflops": 2.0 * nnz * n * world / (ms_per_step * 1e-3) / 1e9,
         "config": workload_config(world, mode),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "spmm_rowmajor_kernel<float,4,32>",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name,
                      "kernel_ms": k_ms, "algorithmic_bytes": g, "unique_bytes": u,
                      "frac_of_8TBs_nominal": achieved / 8000.0,
                      "model": "gather model: (4+4)+128*4 B per nnz, 128*4*2 B per row, 8 B per indptr entry"},

@@ -251,6 +251,12 @@ SDB_API int        sdb_last_error(char* buf, int len);
  * threads); bench.py reports the delta over the timed region. */
 SDB_API int64_t sdb_kernel_launches(void);
 
+/* Name (with template arguments) of the SpMM kernel the most recent sdb_spmm* call on this thread
+ * launched, e.g. "spmm_stream_kernel<float,6,32,2,2>"; empty before the first call.  bench.py labels
+ * its roofline with it.  No reference counterpart (tracing aid, like the reference's print_mkl_debug,
+ * _mkl_interface/_common.py:97-136). */
+SDB_API sdb_status sdb_last_spmm_kernel(char* buf, int len);
+
 /* Device time (ms, CUDA events on the launch stream) the most recent
  * host-pointer entry point on this thread spent in: [0] host->device copies,
  * [1] kernels, [2] device->host copies.  The reference's debug_timer

@@ -7,15 +7,22 @@ without the built library raises ImportError.
 """
 __version__ = "0.1.0"
 
-from .api import (  # noqa: F401
-    dot_product_mkl,
-    dot_product_transpose_mkl,
-    get_version_string,
-    gram_matrix_mkl,
-    set_debug_mode,
-)
-from ._lib import device_count, kernel_launches, last_timing_ms  # noqa: F401
-from .resident import ResidentCSR  # noqa: F401
+import sys as _sys
+
+# `python -m sparse_dot_b200.build` must be able to run when the library is missing or stale: it is the one
+# entry point that does not need it.  Everything else fails loudly on import (no CPU fallback).
+_BUILDING = "sparse_dot_b200.build" in getattr(_sys, "orig_argv", [])
+
+if not _BUILDING:
+    from .api import (  # noqa: F401
+        dot_product_mkl,
+        dot_product_transpose_mkl,
+        get_version_string,
+        gram_matrix_mkl,
+        set_debug_mode,
+    )
+    from ._lib import device_count, kernel_launches, last_spmm_kernel, last_timing_ms  # noqa: F401
+    from .resident import ResidentCSR  # noqa: F401
 
 __all__ = [
     "dot_product_mkl",
@@ -26,5 +33,6 @@ __all__ = [
     "device_count",
     "kernel_launches",
     "last_timing_ms",
+    "last_spmm_kernel",
     "ResidentCSR",
 ]

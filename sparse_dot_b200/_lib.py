@@ -75,6 +75,7 @@ PROTOTYPES = {
     "sdb_version_string": (_i32, [_ct.c_char_p, _i32]),
     "sdb_last_error": (_i32, [_ct.c_char_p, _i32]),
     "sdb_kernel_launches": (_i64, []),
+    "sdb_last_spmm_kernel": (_i32, [_ct.c_char_p, _i32]),
     "sdb_last_timing": (_i32, [_pd]),
 }
 
@@ -152,6 +153,13 @@ def device_count():
 
 def kernel_launches():
     return int(SDB.lib.sdb_kernel_launches())
+
+
+def last_spmm_kernel():
+    """Name of the SpMM kernel the last sdb_spmm* call on this thread launched."""
+    buf = _ct.create_string_buffer(160)
+    check(SDB.lib.sdb_last_spmm_kernel(buf, 160), "sdb_last_spmm_kernel")
+    return buf.value.decode()
 
 
 def last_timing_ms():

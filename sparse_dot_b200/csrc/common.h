@@ -52,8 +52,15 @@ extern std::atomic<int64_t> g_launches;
 // Phase tracing for development (SDB_TRACE=1): synchronises `s` and prints the milliseconds since
 // the previous trace point on this thread.  A no-op (no sync) when the variable is unset.
 void trace(cudaStream_t s, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+// Name of the SpMM kernel the most recent sdb_spmm* call on this thread launched (sdb_last_spmm_kernel).
+void note_spmm_kernel(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+extern thread_local char t_spmm_kernel[128];
 
 // ---------------------------------------------------------------- dtypes
+inline const char* dtype_cname(int dtype) {
+    static const char* const names[4] = {"float", "double", "complex<float>", "complex<double>"};
+    return dtype >= 0 && dtype < 4 ? names[dtype] : "?";
+}
 inline size_t dtype_size(int dtype) {
     switch (dtype) {
         case SDB_F32: return 4;

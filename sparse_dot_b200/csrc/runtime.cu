@@ -31,6 +31,15 @@ sdb_status cuda_fail(cudaError_t e, const char* what, const char* file, int line
     return e == cudaErrorMemoryAllocation ? SDB_STATUS_ALLOC_FAILED : SDB_STATUS_EXECUTION_FAILED;
 }
 
+thread_local char t_spmm_kernel[128] = "";
+
+void note_spmm_kernel(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_spmm_kernel, sizeof(t_spmm_kernel), fmt, ap);
+    va_end(ap);
+}
+
 void trace(cudaStream_t s, const char* fmt, ...) {
     static const bool on = [] {
         const char* e = getenv("SDB_TRACE");
@@ -255,6 +264,12 @@ int sdb_last_error(char* buf, int len) {
 }
 
 int64_t sdb_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+sdb_status sdb_last_spmm_kernel(char* buf, int len) {
+    SDB_REQUIRE(buf != nullptr && len > 0, SDB_STATUS_INVALID_VALUE, "sdb_last_spmm_kernel: null output");
+    snprintf(buf, size_t(len), "%s", sdb::t_spmm_kernel);
+    return SDB_STATUS_SUCCESS;
+}
 
 sdb_status sdb_last_timing(double ms[3]) {
     SDB_REQUIRE(ms != nullptr, SDB_STATUS_INVALID_VALUE, "sdb_last_timing: null output");

@@ -194,6 +194,7 @@ static sdb_status launch_rowmajor(cudaStream_t s, const CsrView& a, bool conj_a,
     const int64_t gy = (n + int64_t(LANES) * VEC - 1) / (int64_t(LANES) * VEC);
     SDB_REQUIRE(gx < (int64_t(1) << 31) && gy < 65536, SDB_STATUS_NOT_SUPPORTED, "spmm: grid too large");
 #define SDB_SPMM_LAUNCH(U, MB)                                                                                  \
+    note_spmm_kernel("spmm_rowmajor_kernel<%s,%d,%d,%d,%d>", dtype_cname(Num<T>::dtype), VEC, LANES, U, MB);                    \
     SDB_LAUNCH((spmm_rowmajor_kernel<T, VEC, LANES, U, MB>), dim3(unsigned(gx), unsigned(gy)), kSpmmWarps * 32, 0, s, \
                a.rows, a.indptr, a.indices, static_cast<const T*>(a.values), conj_a, X, ldx, n, alpha, beta,        \
                out.y[self], out, n_peers, self, row0, ldy)

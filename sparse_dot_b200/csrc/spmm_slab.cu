@@ -109,8 +109,20 @@ template <typename T> __device__ __forceinline__ Pack16<T> gather16(const char* 
     return r;
 }
 
-// RPW rows per warp, WARPS warps per CTA (RPW * WARPS * 512 B of accumulators), U gathers in flight per lane,
-// CTAS resident CTAs per SM (register budget = 65536 / (CTAS * WARPS * 32)).
+// One staged entry: packed (local row << 27 | column) and the value; 8 bytes (fp32) or 16 bytes (fp64), so a
+// warp-uniform read of it is ONE shared-memory wavefront (broadcast) where two shuffles would be two.
+template <typename T> struct alignas(sizeof(T) == 4 ? 8 : 16) StagedEntry {
+    uint32_t rc;
+    T v;
+};
+
+// RPW rows per warp, WARPS warps per CTA (RPW * WARPS * 512 B of accumulators + WARPS * 32 staged entries),
+// U gathers in flight per lane, CTAS resident CTAs per SM (register budget = 65536 / (CTAS * WARPS * 32)).
+//
+// What bounds this kernel is the L1 data pipe (one 128-byte wavefront per clock per SM; ncu:
+// l1tex__data_pipe_lsu_wavefronts), so the hot loop is written to spend as few wavefronts per stored entry as
+// possible: 4 for the 512-byte gather (irreducible), 1 for the staged-entry broadcast, and 8 per row change
+// (store the running sums, load the next row's) amortised over the run of entries a row has inside one slab.
 template <typename T, int RPW, int WARPS, int U, int CTAS>
 __global__ void __launch_bounds__(WARPS * 32, CTAS)
     spmm_stream_kernel(int64_t rows, const int64_t* __restrict__ indptr, const uint32_t* __restrict__ ent_rc,
@@ -119,10 +131,13 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
     constexpr int VEC = Pack16<T>::N;
     constexpr int kRows = RPW * WARPS;  // rows per CTA
     constexpr unsigned kFull = 0xffffffffu;
+    using Ent = StagedEntry<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // this warp's accumulators: [RPW rows][32 lanes] packs of 16 bytes
     Pack16<T>* acc = reinterpret_cast<Pack16<T>*>(smem_raw) + warp * RPW * 32 + lane;
+    // this warp's staging buffer: the 32 entries of the chunk being consumed
+    Ent* stage = reinterpret_cast<Ent*>(smem_raw + size_t(kRows) * 512) + warp * 32;
     const char* xlane = reinterpret_cast<const char*>(X + lane * VEC);
     const int64_t n_blocks = (rows + kRows - 1) / kRows;
     Pack16<T> zero;
@@ -144,17 +159,17 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
         // invariant: `cur` is the live value of acc[cur_row]
         Pack16<T> cur = zero;
         uint32_t cur_row = 0;
-        // entry j of the chunk held in (rc, v): swap accumulators when the row changes (rare: the entries of a
-        // row inside a slab are adjacent), then 4 FMAs.  Every lane works on the same entry: branches are uniform.
-        auto consume = [&](uint32_t rc, T v, unsigned starts, int j, const Pack16<T>& x) {
-            const T a = shfl(kFull, v, j, 32);
-            if ((starts >> j) & 1u) {
+        // one entry: swap accumulators when the row changes (rare: the entries of a row inside a slab are
+        // adjacent), then VEC FMAs.  Every lane works on the same entry, so the branch is warp-uniform.
+        auto consume = [&](const Ent& e, const Pack16<T>& x) {
+            const uint32_t r = e.rc >> kColBits;
+            if (r != cur_row) {
                 acc[cur_row * 32] = cur;
-                cur_row = __shfl_sync(kFull, rc, j) >> kColBits;
-                cur = acc[cur_row * 32];
+                cur_row = r;
+                cur = acc[r * 32];
             }
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) cur.v[i] = madd(a, x.v[i], cur.v[i]);
+            for (int i = 0; i < VEC; ++i) cur.v[i] = madd(e.v, x.v[i], cur.v[i]);
         };
 
         uint32_t rc_nx = 0;
@@ -164,34 +179,42 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
             v_nx = ldcs(eva + lane);
         }
         for (int f = 0; f < n_ent; f += 32) {
-            const uint32_t rc = rc_nx;
-            const T v = v_nx;
+            __syncwarp();  // the previous chunk has been consumed by every lane
+            Ent mine;
+            mine.rc = rc_nx;
+            mine.v = v_nx;
+            stage[lane] = mine;
+            __syncwarp();
             // the next chunk is requested before this chunk's gathers are consumed
             if (f + 32 + lane < n_ent) {
                 rc_nx = __ldcs(erc + f + 32 + lane);
                 v_nx = ldcs(eva + f + 32 + lane);
             }
             const int cnt = min(32, n_ent - f);
-            const uint32_t my_r = rc >> kColBits;
-            const uint32_t prev_r = __shfl_up_sync(kFull, my_r, 1);
-            const unsigned starts = __ballot_sync(kFull, my_r != (lane == 0 ? cur_row : prev_r));
             if (cnt == 32) {
                 // rolling ring of U gathers: the slot an entry has just been consumed from is refilled at once,
                 // so ~U 16-byte loads per lane stay in flight for the whole chunk (all indices are compile-time)
+                Ent e[U];
                 Pack16<T> x[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) x[u] = gather16<T>(xlane, __shfl_sync(kFull, rc, u) & kColMask, row_bytes);
+                for (int u = 0; u < U; ++u) {
+                    e[u] = stage[u];
+                    x[u] = gather16<T>(xlane, e[u].rc & kColMask, row_bytes);
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    consume(rc, v, starts, j, x[j % U]);
-                    if (j + U < 32)
-                        x[j % U] = gather16<T>(xlane, __shfl_sync(kFull, rc, j + U) & kColMask, row_bytes);
+                    consume(e[j % U], x[j % U]);
+                    if (j + U < 32) {
+                        e[j % U] = stage[j + U];
+                        x[j % U] = gather16<T>(xlane, e[j % U].rc & kColMask, row_bytes);
+                    }
                 }
             } else {
                 // ragged last chunk of the group: one entry at a time
                 for (int j = 0; j < cnt; ++j) {
-                    const Pack16<T> xj = gather16<T>(xlane, __shfl_sync(kFull, rc, j) & kColMask, row_bytes);
-                    consume(rc, v, starts, j, xj);
+                    const Ent ej = stage[j];
+                    const Pack16<T> xj = gather16<T>(xlane, ej.rc & kColMask, row_bytes);
+                    consume(ej, xj);
                 }
             }
         }
@@ -240,58 +263,68 @@ int slab_mode() {  // 0 = automatic (default), 1 = off, 2 = whenever the shape a
     return v;
 }
 
-// Executor shapes (SDB_SLAB_VARIANT picks; 0 is the default), all with 448 rows = 224 KB of accumulators per SM:
-//   0: 1 CTA x 32 warps x 14 rows, 4 gathers in flight per lane      (64 registers)
-//   1: 1 CTA x 32 warps x 14 rows, 6 gathers
-//   2: 1 CTA x 32 warps x 14 rows, 8 gathers
-//   3: 2 CTAs x 32 warps x 7 rows, 2 gathers                         (32 registers)
-//   4: 1 CTA x 16 warps x 28 rows, 8 gathers                         (128 registers)
+// Executor shapes (SDB_SLAB_VARIANT picks; 0 is the default); shared memory per SM = accumulators + staging.
+// Measured on configs[1] (profiles/r1_logs/stream_sweep*.log): what matters most is the number of resident warps.
+//   0: 2 CTAs x 32 warps x 6 rows (384 rows / SM), 2 gathers in flight per lane   (32 registers)
+//   1: 2 CTAs x 32 warps x 6 rows,                 3 gathers
+//   2: 2 CTAs x 24 warps x 8 rows (384 rows / SM), 3 gathers                      (40 registers)
+//   3: 2 CTAs x 24 warps x 8 rows,                 4 gathers
+//   4: 3 CTAs x 16 warps x 8 rows (384 rows / SM), 3 gathers                      (40 registers)
+//   5: 1 CTA  x 32 warps x 13 rows (416 rows / SM), 4 gathers                     (64 registers)
 int slab_variant() {
     static const int v = [] {
         const char* e = getenv("SDB_SLAB_VARIANT");
         const int r = e ? atoi(e) : 0;
-        return r >= 0 && r <= 4 ? r : 0;
+        return r >= 0 && r <= 5 ? r : 0;
     }();
     return v;
 }
 int slab_rpw() {
     const int v = slab_variant();
-    return v == 3 ? 7 : (v == 4 ? 28 : 14);
+    return v <= 1 ? 6 : (v <= 4 ? 8 : 13);
 }
-constexpr int kSlabRowsPerSm = 448;
+int slab_rows_per_sm() { return slab_variant() == 5 ? 416 : 384; }
 
 }  // namespace
 
 template <typename T, int RPW, int WARPS, int U, int CTAS>
 static sdb_status launch_stream(cudaStream_t s, const CsrView& a, const sdb_mat* m, const T* X, int64_t ldx, T alpha,
                                 T beta, void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy,
-                                int sm_count) {
+                                int sm_count, int col_chunks) {
     constexpr int kRows = RPW * WARPS;
-    static_assert(kRows * CTAS == kSlabRowsPerSm && RPW <= 32, "accumulator tile");
-    const size_t smem = size_t(kRows) * 512;
-    SlabPeers<T> peers;
-    for (int q = 0; q < kSlabMaxPeers; ++q) peers.y[q] = q < n_peers ? static_cast<T*>(dY_peers[q]) : nullptr;
+    constexpr size_t kSmem = size_t(kRows) * 512 + size_t(WARPS) * 32 * sizeof(StagedEntry<T>);
+    static_assert(RPW <= 32 && (kSmem + 1024) * CTAS <= 233472, "shared memory per SM");
     const int64_t n_blocks = (a.rows + kRows - 1) / kRows;
     const unsigned grid = unsigned(std::min<int64_t>(n_blocks, int64_t(sm_count) * CTAS));
     SDB_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<T, RPW, WARPS, U, CTAS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    SDB_LAUNCH((spmm_stream_kernel<T, RPW, WARPS, U, CTAS>), grid, WARPS * 32, smem, s, a.rows, a.indptr,
-               static_cast<const uint32_t*>(m->slab_rc), static_cast<const T*>(m->slab_val), X,
-               uint32_t(ldx * int64_t(sizeof(T))), alpha, beta, peers.y[self], peers, n_peers, self, row0, ldy);
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmem)));
+    note_spmm_kernel("spmm_stream_kernel<%s,%d,%d,%d,%d>", dtype_cname(Num<T>::dtype), RPW, WARPS, U, CTAS);
+    // panels wider than 512 bytes per row: one sweep per 512-byte column chunk (the accumulator tile is 512 B wide)
+    constexpr int kChunkElems = 512 / int(sizeof(T));
+    for (int c = 0; c < col_chunks; ++c) {
+        SlabPeers<T> peers;
+        for (int q = 0; q < kSlabMaxPeers; ++q)
+            peers.y[q] = q < n_peers ? static_cast<T*>(dY_peers[q]) + int64_t(c) * kChunkElems : nullptr;
+        SDB_LAUNCH((spmm_stream_kernel<T, RPW, WARPS, U, CTAS>), grid, WARPS * 32, kSmem, s, a.rows, a.indptr,
+                   static_cast<const uint32_t*>(m->slab_rc), static_cast<const T*>(m->slab_val),
+                   X + int64_t(c) * kChunkElems, uint32_t(ldx * int64_t(sizeof(T))), alpha, beta, peers.y[self], peers,
+                   n_peers, self, row0, ldy);
+    }
     return SDB_STATUS_SUCCESS;
 }
 
-#define SDB_SLAB_ARGS s, a, m, X, ldx, alpha, beta, dY_peers, n_peers, self, row0, ldy, sm_count
+#define SDB_SLAB_ARGS s, a, m, X, ldx, alpha, beta, dY_peers, n_peers, self, row0, ldy, sm_count, col_chunks
 template <typename T>
 static sdb_status launch_variant(cudaStream_t s, const CsrView& a, const sdb_mat* m, const T* X, int64_t ldx, T alpha,
                                  T beta, void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy,
-                                 int sm_count) {
+                                 int sm_count, int col_chunks) {
     switch (slab_variant()) {
-        case 1: return launch_stream<T, 14, 32, 6, 1>(SDB_SLAB_ARGS);
-        case 2: return launch_stream<T, 14, 32, 8, 1>(SDB_SLAB_ARGS);
-        case 3: return launch_stream<T, 7, 32, 2, 2>(SDB_SLAB_ARGS);
-        case 4: return launch_stream<T, 28, 16, 8, 1>(SDB_SLAB_ARGS);
-        default: return launch_stream<T, 14, 32, 4, 1>(SDB_SLAB_ARGS);
+        case 1: return launch_stream<T, 6, 32, 3, 2>(SDB_SLAB_ARGS);
+        case 2: return launch_stream<T, 8, 24, 3, 2>(SDB_SLAB_ARGS);
+        case 3: return launch_stream<T, 8, 24, 4, 2>(SDB_SLAB_ARGS);
+        case 4: return launch_stream<T, 8, 16, 3, 3>(SDB_SLAB_ARGS);
+        case 5: return launch_stream<T, 13, 32, 4, 1>(SDB_SLAB_ARGS);
+        default: return launch_stream<T, 6, 32, 2, 2>(SDB_SLAB_ARGS);
     }
 }
 #undef SDB_SLAB_ARGS
@@ -308,14 +341,15 @@ bool spmm_slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx) {
     if (mode == 1 || a.owner == nullptr) return false;
     if (dtype != SDB_F32 && dtype != SDB_F64) return false;
     const size_t sv = dtype_size(dtype);
-    if (size_t(n) * sv != 512 || (size_t(ldx) * sv) % 16 != 0 || size_t(ldx) * sv >= (size_t(1) << 31)) return false;
+    if (n <= 0 || (size_t(n) * sv) % 512 != 0 || size_t(n) * sv > 4096) return false;  // 1..8 column chunks of 512 B
+    if ((size_t(ldx) * sv) % 16 != 0 || size_t(ldx) * sv >= (size_t(1) << 31)) return false;
     if (a.cols >= (int64_t(1) << kColBits) || a.rows <= 0 || a.nnz <= 0) return false;
     if (a.owner->strict_sorted == -1) return false;
     if (mode == 2) return true;
     const int uses = a.owner->spmm_calls++;
-    const int64_t in_flight = std::min<int64_t>(a.rows, int64_t(148) * kSlabRowsPerSm);
+    const int64_t in_flight = std::min<int64_t>(a.rows, int64_t(148) * slab_rows_per_sm());
     const double reuse = double(in_flight) * (double(a.nnz) / double(a.rows)) / double(a.cols);
-    return uses >= 1 && size_t(a.cols) * 512 >= (size_t(192) << 20) && a.rows >= int64_t(148) * kSlabRowsPerSm &&
+    return uses >= 1 && size_t(a.cols) * size_t(n) * sv >= (size_t(192) << 20) && a.rows >= int64_t(148) * slab_rows_per_sm() &&
            reuse >= 1.5;
 }
 
@@ -323,7 +357,6 @@ sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int 
                             const double* alpha, const double* beta, const void* dX, int64_t n, int64_t ldx,
                             void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy) {
     (void)conj_a;  // real dtypes only
-    (void)n;
     sdb_mat* m = a.owner;
     SDB_REQUIRE(m != nullptr, SDB_STATUS_NOT_SUPPORTED, "spmm_slab: ad-hoc view");
     if (m->strict_sorted == 0) {
@@ -357,11 +390,12 @@ sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int 
         m->slab_rpw = rpw;
         if (s != ls) SDB_CUDA(cudaStreamSynchronize(ls));
     }
+    const int col_chunks = int(size_t(n) * sv / 512);
     if (dtype == SDB_F32)
         return launch_variant<float>(s, a, m, static_cast<const float*>(dX), ldx, float(alpha[0]), float(beta[0]),
-                                     dY_peers, n_peers, self, row0, ldy, ctx->sm_count);
+                                     dY_peers, n_peers, self, row0, ldy, ctx->sm_count, col_chunks);
     return launch_variant<double>(s, a, m, static_cast<const double*>(dX), ldx, alpha[0], beta[0], dY_peers, n_peers,
-                                  self, row0, ldy, ctx->sm_count);
+                                  self, row0, ldy, ctx->sm_count, col_chunks);
 }
 
 }  // namespace sdb

@@ -1,9 +1,10 @@
 """
-The L2-tiled SpMM kernel (csrc/spmm_slab.cu) is chosen automatically only for panels several
-times the L2 cache; here it is forced (SDB_SLAB=2, tiny slabs via SDB_SLAB_MB) in a subprocess —
-the switches are read once per process — and checked against the CPU oracle on small inputs:
-many slabs, empty rows, rows denser than a warp batch, ragged last row block, beta != 0, fp32
-and fp64, and the two-rank fused all-gather epilogue.
+The L2-tiled SpMM kernel (csrc/spmm_slab.cu: slab-ordered inspector + streaming executor) is chosen
+automatically only for panels several times the L2 cache on a handle that is multiplied repeatedly; here
+it is forced (SDB_SLAB=2, tiny slabs via SDB_SLAB_MB) in a subprocess — the switches are read once per
+process — and checked against the CPU oracle on small inputs: many slabs, empty rows, rows denser than a
+chunk, ragged last row block, beta != 0, fp32 and fp64, panels of 1, 2 and 3 column chunks, every executor
+shape (SDB_SLAB_VARIANT), and the two-rank fused all-gather epilogue.
 """
 import os
 import subprocess
@@ -25,7 +26,8 @@ def _run(code, extra_env=None):
     return r.stdout
 
 
-def test_slab_kernel_matches_oracle():
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+def test_slab_kernel_matches_oracle(variant):
     out = _run("""
         import numpy as np, scipy.sparse as sp
         import sparse_dot_b200 as sdb
@@ -33,7 +35,7 @@ def test_slab_kernel_matches_oracle():
         from oracle import oracle as orc
         from tests import _cases as cs
         before = sdb.kernel_launches()
-        for dtype, n in ((np.float32, 128), (np.float64, 64)):
+        for dtype, n in ((np.float32, 128), (np.float64, 64), (np.float32, 256), (np.float64, 192)):
             a = cs.uniform_rows_csr(5000, 20000, 30, dtype, seed=1).tolil()
             a[7, :] = 0
             a[4999, :] = 0
@@ -57,7 +59,7 @@ def test_slab_kernel_matches_oracle():
                 got = plan.read_panel()
                 want = orc.c_spmm(a, x, alpha=2.0, beta=0.5, y=y0.copy())
                 assert cs.rel_err(got, want, 2 * bound + 0.5 * y0) <= tol, "beta=0.5"
-                info = H.info(plan.handle)
+                assert sdb.last_spmm_kernel().startswith("spmm_stream_kernel"), sdb.last_spmm_kernel()
             # through the public API (fresh handle per call)
             got = sdb.dot_product_mkl(a, x, out=y0.copy(), out_scalar=0.5)
             want = orc.c_spmm(a, x, beta=0.5, y=y0.copy())
@@ -69,8 +71,9 @@ def test_slab_kernel_matches_oracle():
             b.has_sorted_indices = False
             got = sdb.dot_product_mkl(b, x)
             assert cs.rel_err(got, orc.c_spmm(a, x), bound) <= tol, "unsorted fallback"
+            assert sdb.last_spmm_kernel().startswith("spmm_rowmajor_kernel"), sdb.last_spmm_kernel()
         print("OK", sdb.kernel_launches() - before)
-    """)
+    """, extra_env={"SDB_SLAB_VARIANT": str(variant)})
     assert "OK" in out
 
 

@@ -172,7 +172,7 @@ def test_gpu_error_behaviour_matches_reference():
 
     a, b = _dense_pair(np.float64)
     cases = [
-        lambda f: f(a.tocoo(), b),                                            # COO refused (test_sparse_sparse.py:184-188)
+        lambda f: f(a.tocoo(), a.T.tocoo()),                                  # COO refused (test_sparse_sparse.py:184-188)
         lambda f: f(a, b[:-1]),                                               # misaligned (test_mkl.py:143-170)
         lambda f: f(a.astype(np.float32), b),                                 # mixed dtype without cast
         lambda f: f(a, b, out=np.zeros((3, 3))),                              # bad out shape
