@@ -148,7 +148,18 @@ SDB_API sdb_status sdb_spmm_csr_host(int64_t rows, int64_t cols, const void* ind
                                      int64_t ldy);
 
 /* Same operation on DEVICE pointers, stream-ordered on `stream` (a
- * cudaStream_t passed as void*; NULL = the library's own stream). */
+ * cudaStream_t passed as void*; NULL = the library's own stream).
+ *
+ * Inspector / executor (the analogue of mkl_sparse_optimize, which the reference
+ * never calls): when a handle created from HOST arrays is multiplied a second
+ * time by a row-major fp32 / fp64 panel whose rows are a multiple of 512 bytes
+ * and which is several times larger than the L2 cache, the library builds, once,
+ * a column-slab-ordered copy of the stored entries (nnz * (4 + sizeof value)
+ * bytes of HBM, released by sdb_order / sdb_destroy) and switches to the
+ * L2-tiled streaming kernel (csrc/spmm_slab.cu).  Results are the same up to
+ * the order of the floating-point additions inside a row.  SDB_SLAB=1 in the
+ * environment disables this; handles over borrowed device arrays
+ * (sdb_create_csr_dev) never cache a copy. */
 SDB_API sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, int layout,
                                 const void* dX, int64_t n, int64_t ldx,
                                 const double* beta, void* dY, int64_t ldy, void* stream);

@@ -339,6 +339,8 @@ static sdb_status launch_variant(cudaStream_t s, const CsrView& a, const sdb_mat
 bool spmm_slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx) {
     const int mode = slab_mode();
     if (mode == 1 || a.owner == nullptr) return false;
+    // borrowed device arrays (sdb_create_csr_dev) may be rewritten by their owner between calls: never cache a copy
+    if (!a.owner->owns) return false;
     if (dtype != SDB_F32 && dtype != SDB_F64) return false;
     const size_t sv = dtype_size(dtype);
     if (n <= 0 || (size_t(n) * sv) % 512 != 0 || size_t(n) * sv > 4096) return false;  // 1..8 column chunks of 512 B
