@@ -193,7 +193,12 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
             const int cnt = min(32, n_ent - f);
             if (cnt == 32) {
                 // rolling ring of U gathers: the slot an entry has just been consumed from is refilled at once,
-                // so ~U 16-byte loads per lane stay in flight for the whole chunk (all indices are compile-time)
+                // so ~U 16-byte loads per lane stay in flight for the whole chunk (all indices are compile-time).
+                // NOTE for whoever edits this kernel: at 32 registers ptxas's schedule of this loop is sensitive to
+                // unrelated code (an A/B on one box: moving the peer stores of the epilogue out of line made ptxas
+                // pair the refills — two gathers back to back, then two consumes — and the same loop ran 3.91 ms
+                // instead of 2.56 ms).  Check the SASS: the LDG.E.128 of the chunk must be evenly spaced (13
+                // instructions apart), see profiles/README.md round 1e.
                 Ent e[U];
                 Pack16<T> x[U];
 #pragma unroll
