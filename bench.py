@@ -185,6 +185,10 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # all the host threads it can use: torch.distributed.run exports OMP_NUM_THREADS=1 to every rank it spawns,
+    # which would silently make MKL single-threaded under the N > 1 launch (measured: 2167 ms instead of 206 ms)
+    host_threads = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = str(host_threads)
     a, x, y0 = make_workload(M_ROWS, K_COLS, NNZ_PER_ROW, N_DENSE, seed=0)
     step, kind, cores, what = cpu_spmm_runner(a, x, y0)
     ref_status = what

@@ -165,11 +165,18 @@ SDB_API sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, i
                                 const double* beta, void* dY, int64_t ldy, void* stream);
 
 /* Row-sharded SpMM fused with the all-gather of the output panel:
- * this rank owns rows [row0, row0 + A.rows) of the global product; the kernel's
- * epilogue stores every finished row once into EACH of the n_peers full-size
- * row-major output panels (peer-mapped device pointers, ld = ldy, own rank
- * included), so no second pass over Y and no separate collective is needed.
- * beta reads the local panel (dY_peers[self]).  Row-major layout, op = N. */
+ * this rank owns rows [row0, row0 + A.rows) of the global product and the call
+ * leaves them in EACH of the n_peers full-size row-major output panels
+ * (peer-mapped device pointers, ld = ldy, own rank included); once `stream` has
+ * passed the call, this rank's rows are in every panel.  No separate collective
+ * is needed.  beta reads the local panel (dY_peers[self]).  Row-major, op = N.
+ * Two exchange strategies (environment SDB_ALLGATHER):
+ *   "ce" (default)  the shard is cut into a few row chunks; chunk c's kernel
+ *                   writes the local panel and the copy engines push its rows
+ *                   to the peers over NVLink (one stream per peer) while chunk
+ *                   c + 1's kernel runs, so no SM waits for NVLink;
+ *   "stores"        one kernel whose epilogue stores every finished 16-byte
+ *                   slice into every peer panel itself. */
 SDB_API sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A,
                                           const void* dX, int64_t n, int64_t ldx,
                                           const double* beta, void* const* dY_peers,

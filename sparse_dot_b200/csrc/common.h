@@ -89,6 +89,13 @@ struct Context {
     int next_chunk = 0;
     // phase timing of the last host-pointer entry point (ms)
     double last_ms[3] = {0, 0, 0};
+    // chunk-pipelined all-gather (sdb_spmm_dev_allgather): one copy stream per peer, a ring of events
+    static constexpr int kExchangePeers = 8;
+    static constexpr int kExchangeEvents = 32;
+    cudaStream_t xchg_stream[kExchangePeers] = {};
+    cudaEvent_t xchg_event[kExchangeEvents] = {};
+    cudaEvent_t xchg_done[kExchangePeers] = {};
+    int xchg_next_event = 0;
 };
 
 sdb_status get_context(Context** out);
@@ -215,6 +222,10 @@ struct CsrView {
     const int32_t* pos = nullptr;
     // the handle whose arrays these are (nullptr for ad-hoc views): lets kernels cache per-matrix indexes
     sdb_mat* owner = nullptr;
+    // SpMM only: multiply just rows [sub_begin, sub_begin + sub_rows) of the view (sub_rows < 0 = all of them).
+    // Used by the chunk-pipelined all-gather; per-matrix indexes are always built from the whole view.
+    int64_t sub_begin = 0;
+    int64_t sub_rows = -1;
 };
 sdb_status csr_view(Context* ctx, const sdb_mat* m, bool transpose, CsrView* v, bool want_pos = false);
 sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indptr, int32_t* indices,
@@ -234,6 +245,9 @@ sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype
                        void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy);
 // L2-tiled SpMM (spmm_slab.cu): returns SDB_STATUS_NOT_SUPPORTED when the call does not qualify.
 bool spmm_slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx);
+// rows one wave of the streaming kernel's persistent grid covers (0 when the call would not use it): row sub-ranges
+// handed to it must start at a multiple of this
+int64_t spmm_slab_wave_rows(const Context* ctx, const CsrView& a, int dtype, int64_t n, int64_t ldx, bool count_call);
 sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a,
                             const double* alpha, const double* beta, const void* dX, int64_t n, int64_t ldx,
                             void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy);

@@ -18,6 +18,7 @@
 // warp keeps kUnroll * 512 B in flight.  The alpha/beta epilogue is fused and
 // the finished row slice is stored once to every peer panel (n_peers = 1
 // normally; > 1 is the fused all-gather over NVLink peer mappings, §8e).
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.h"
@@ -190,13 +191,16 @@ static sdb_status launch_rowmajor(cudaStream_t s, const CsrView& a, bool conj_a,
                                   T alpha, T beta, const PeerPanels<T>& out, int n_peers, int self, int64_t row0,
                                   int64_t ldy) {
     constexpr int kRowsPerCta = kSpmmWarps * (32 / LANES);
-    const int64_t gx = (a.rows + kRowsPerCta - 1) / kRowsPerCta;
+    const int64_t sub_rows = a.sub_rows < 0 ? a.rows : a.sub_rows;  // row sub-range of the view (default: all)
+    const int64_t* sub_indptr = a.indptr + a.sub_begin;
+    row0 += a.sub_begin;
+    const int64_t gx = (sub_rows + kRowsPerCta - 1) / kRowsPerCta;
     const int64_t gy = (n + int64_t(LANES) * VEC - 1) / (int64_t(LANES) * VEC);
     SDB_REQUIRE(gx < (int64_t(1) << 31) && gy < 65536, SDB_STATUS_NOT_SUPPORTED, "spmm: grid too large");
 #define SDB_SPMM_LAUNCH(U, MB)                                                                                  \
     note_spmm_kernel("spmm_rowmajor_kernel<%s,%d,%d,%d,%d>", dtype_cname(Num<T>::dtype), VEC, LANES, U, MB);                    \
     SDB_LAUNCH((spmm_rowmajor_kernel<T, VEC, LANES, U, MB>), dim3(unsigned(gx), unsigned(gy)), kSpmmWarps * 32, 0, s, \
-               a.rows, a.indptr, a.indices, static_cast<const T*>(a.values), conj_a, X, ldx, n, alpha, beta,        \
+               sub_rows, sub_indptr, a.indices, static_cast<const T*>(a.values), conj_a, X, ldx, n, alpha, beta,    \
                out.y[self], out, n_peers, self, row0, ldy)
     if (LANES == 32 && VEC * sizeof(T) == 16) {
         // full-warp rows (the headline shape): tuning variants selectable for experiments
@@ -327,7 +331,7 @@ sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype
     SDB_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && self >= 0 && self < n_peers, SDB_STATUS_INVALID_VALUE,
                 "spmm: bad peer configuration (%d peers, self %d)", n_peers, self);
     if (a.rows == 0 || n == 0) return SDB_STATUS_SUCCESS;
-    if (n == 1 && n_peers == 1 && row0 == 0) {
+    if (n == 1 && n_peers == 1 && row0 == 0 && a.sub_rows < 0) {
         // one column: the panel layout only decides the element strides
         const bool rm = layout == SDB_LAYOUT_ROW_MAJOR;
         return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
@@ -410,6 +414,36 @@ sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, int layou
     return spmm_device(ctx, s, v, A->dtype, conj_a, alpha, beta, layout, dX, n, ldx, yp, 1, 0, 0, ldy);
 }
 
+// How the finished rows reach the peers (SDB_ALLGATHER): "ce" (default) = chunk-pipelined copy-engine exchange,
+// "stores" = the kernel's epilogue stores every finished 16-byte slice into every peer panel itself.
+static int allgather_strategy() {
+    static const int v = [] {
+        const char* e = getenv("SDB_ALLGATHER");
+        return e && e[0] == 's' ? 1 : 0;
+    }();
+    return v;
+}
+
+static sdb_status ensure_exchange_streams(Context* ctx, int n_peers) {
+    for (int q = 0; q < n_peers; ++q) {
+        if (!ctx->xchg_stream[q]) SDB_CUDA(cudaStreamCreateWithFlags(&ctx->xchg_stream[q], cudaStreamNonBlocking));
+        if (!ctx->xchg_done[q]) SDB_CUDA(cudaEventCreateWithFlags(&ctx->xchg_done[q], cudaEventDisableTiming));
+    }
+    for (int e = 0; e < Context::kExchangeEvents; ++e)
+        if (!ctx->xchg_event[e]) SDB_CUDA(cudaEventCreateWithFlags(&ctx->xchg_event[e], cudaEventDisableTiming));
+    return SDB_STATUS_SUCCESS;
+}
+
+// Row-sharded SpMM + all-gather of the output panel as ONE stream-ordered call.
+//
+// Strategy "ce": the shard's rows are cut into a few chunks (whole waves of the streaming kernel's persistent
+// grid, so no chunk ends in a partial wave except the last); chunk c's kernel writes only the local panel, and
+// as soon as it has finished (event) the N-1 copy engines push its rows into the peers' panels over NVLink on
+// one stream per peer while chunk c+1's kernel runs.  No SM ever waits for NVLink, and only the last chunk's push
+// is exposed.  The caller's stream waits for the pushes at the end, so "the stream has reached this point" still
+// means "my rows are in every panel".
+// Strategy "stores": one kernel, peer stores in its epilogue (fine while the kernel is much longer than the
+// exchange; with the streaming kernel all warps reach their epilogues together and the bursts stall the gathers).
 sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A, const void* dX, int64_t n, int64_t ldx,
                                   const double* beta, void* const* dY_peers, int n_peers, int self, int64_t row0,
                                   int64_t ldy, void* stream) {
@@ -425,8 +459,55 @@ sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A, const v
     SDB_TRY(csr_view(ctx, A, false, &v));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     if (s != ctx->stream) SDB_CUDA(cudaStreamSynchronize(ctx->stream));
-    return spmm_device(ctx, s, v, A->dtype, false, alpha, beta, SDB_LAYOUT_ROW_MAJOR, dX, n, ldx, dY_peers, n_peers,
-                       self, row0, ldy);
+    if (n_peers == 1 || allgather_strategy() == 1 || v.rows == 0 || n == 0)
+        return spmm_device(ctx, s, v, A->dtype, false, alpha, beta, SDB_LAYOUT_ROW_MAJOR, dX, n, ldx, dY_peers,
+                           n_peers, self, row0, ldy);
+
+    SDB_TRY(ensure_exchange_streams(ctx, n_peers));
+    const size_t row_bytes = size_t(n) * dtype_size(A->dtype);
+    const size_t pitch = size_t(ldy) * dtype_size(A->dtype);
+    // chunking: whole waves of the streaming kernel when it will run, else quarters of the shard
+    int64_t chunk = spmm_slab_wave_rows(ctx, v, A->dtype, n, ldx, /*count_call=*/true);
+    if (chunk > 0) {
+        const int64_t waves = (v.rows + chunk - 1) / chunk;
+        chunk *= std::max<int64_t>(1, (waves + 2) / 5);  // about five chunks per step
+    } else {
+        chunk = ((v.rows + 3) / 4 + 63) / 64 * 64;
+    }
+    if (size_t(v.rows) * row_bytes < (size_t(16) << 20)) chunk = v.rows;  // too small to be worth pipelining
+    void* local[1] = {dY_peers[self]};
+    for (int64_t r0 = 0; r0 < v.rows; r0 += chunk) {
+        const int64_t r1 = std::min(v.rows, r0 + chunk);
+        CsrView part = v;
+        if (r0 > 0 || r1 < v.rows) {
+            part.sub_begin = r0;
+            part.sub_rows = r1 - r0;
+        }
+        SDB_TRY(spmm_device(ctx, s, part, A->dtype, false, alpha, beta, SDB_LAYOUT_ROW_MAJOR, dX, n, ldx, local, 1, 0,
+                            row0, ldy));
+        cudaEvent_t done = ctx->xchg_event[ctx->xchg_next_event];
+        ctx->xchg_next_event = (ctx->xchg_next_event + 1) % Context::kExchangeEvents;
+        SDB_CUDA(cudaEventRecord(done, s));
+        const size_t off = size_t(row0 + r0) * pitch;
+        for (int q = 0; q < n_peers; ++q) {
+            if (q == self) continue;
+            cudaStream_t cs = ctx->xchg_stream[q];
+            SDB_CUDA(cudaStreamWaitEvent(cs, done, 0));
+            char* dst = static_cast<char*>(dY_peers[q]) + off;
+            const char* src = static_cast<const char*>(dY_peers[self]) + off;
+            if (pitch == row_bytes)
+                SDB_CUDA(cudaMemcpyAsync(dst, src, size_t(r1 - r0) * row_bytes, cudaMemcpyDeviceToDevice, cs));
+            else
+                SDB_CUDA(cudaMemcpy2DAsync(dst, pitch, src, pitch, row_bytes, size_t(r1 - r0),
+                                           cudaMemcpyDeviceToDevice, cs));
+        }
+    }
+    for (int q = 0; q < n_peers; ++q) {  // the call is complete on `s` once every push has landed
+        if (q == self) continue;
+        SDB_CUDA(cudaEventRecord(ctx->xchg_done[q], ctx->xchg_stream[q]));
+        SDB_CUDA(cudaStreamWaitEvent(s, ctx->xchg_done[q], 0));
+    }
+    return SDB_STATUS_SUCCESS;
 }
 
 sdb_status sdb_spmm(int op, const double* alpha, const sdb_mat* A, int layout, const void* X, int64_t n, int64_t ldx,

@@ -299,7 +299,11 @@ static sdb_status launch_stream(cudaStream_t s, const CsrView& a, const sdb_mat*
     constexpr int kRows = RPW * WARPS;
     constexpr size_t kSmem = size_t(kRows) * 512 + size_t(WARPS) * 32 * sizeof(StagedEntry<T>);
     static_assert(RPW <= 32 && (kSmem + 1024) * CTAS <= 233472, "shared memory per SM");
-    const int64_t n_blocks = (a.rows + kRows - 1) / kRows;
+    const int64_t sub_rows = a.sub_rows < 0 ? a.rows : a.sub_rows;  // row sub-range of the view (default: all)
+    SDB_REQUIRE(a.sub_begin % kRows == 0, SDB_STATUS_INVALID_VALUE, "spmm_slab: sub-range not aligned to the row groups");
+    const int64_t* sub_indptr = a.indptr + a.sub_begin;
+    row0 += a.sub_begin;
+    const int64_t n_blocks = (sub_rows + kRows - 1) / kRows;
     const unsigned grid = unsigned(std::min<int64_t>(n_blocks, int64_t(sm_count) * CTAS));
     SDB_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<T, RPW, WARPS, U, CTAS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmem)));
@@ -310,7 +314,7 @@ static sdb_status launch_stream(cudaStream_t s, const CsrView& a, const sdb_mat*
         SlabPeers<T> peers;
         for (int q = 0; q < kSlabMaxPeers; ++q)
             peers.y[q] = q < n_peers ? static_cast<T*>(dY_peers[q]) + int64_t(c) * kChunkElems : nullptr;
-        SDB_LAUNCH((spmm_stream_kernel<T, RPW, WARPS, U, CTAS>), grid, WARPS * 32, kSmem, s, a.rows, a.indptr,
+        SDB_LAUNCH((spmm_stream_kernel<T, RPW, WARPS, U, CTAS>), grid, WARPS * 32, kSmem, s, sub_rows, sub_indptr,
                    static_cast<const uint32_t*>(m->slab_rc), static_cast<const T*>(m->slab_val),
                    X + int64_t(c) * kChunkElems, uint32_t(ldx * int64_t(sizeof(T))), alpha, beta, peers.y[self], peers,
                    n_peers, self, row0, ldy);
@@ -341,7 +345,20 @@ static sdb_status launch_variant(cudaStream_t s, const CsrView& a, const sdb_mat
 //   * expected reuse of an X row inside one wave of row blocks >= 1.5
 //     (rows in flight * mean row length / columns),
 //   * the handle has been multiplied before (a matrix used once never pays the inspector).
+static bool slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx, bool count_call);
+
 bool spmm_slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx) {
+    // a row sub-range is one piece of a call that has been counted already (spmm_slab_wave_rows)
+    return slab_wanted(a, dtype, n, ldx, a.sub_rows < 0);
+}
+
+int64_t spmm_slab_wave_rows(const Context* ctx, const CsrView& a, int dtype, int64_t n, int64_t ldx, bool count_call) {
+    if (!slab_wanted(a, dtype, n, ldx, count_call)) return 0;
+    if (a.owner->strict_sorted == -1) return 0;
+    return int64_t(ctx->sm_count) * slab_rows_per_sm();
+}
+
+static bool slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx, bool count_call) {
     const int mode = slab_mode();
     if (mode == 1 || a.owner == nullptr) return false;
     // borrowed device arrays (sdb_create_csr_dev) may be rewritten by their owner between calls: never cache a copy
@@ -353,7 +370,7 @@ bool spmm_slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx) {
     if (a.cols >= (int64_t(1) << kColBits) || a.rows <= 0 || a.nnz <= 0) return false;
     if (a.owner->strict_sorted == -1) return false;
     if (mode == 2) return true;
-    const int uses = a.owner->spmm_calls++;
+    const int uses = count_call ? a.owner->spmm_calls++ : a.owner->spmm_calls - 1;
     const int64_t in_flight = std::min<int64_t>(a.rows, int64_t(148) * slab_rows_per_sm());
     const double reuse = double(in_flight) * (double(a.nnz) / double(a.rows)) / double(a.cols);
     return uses >= 1 && size_t(a.cols) * size_t(n) * sv >= (size_t(192) << 20) && a.rows >= int64_t(148) * slab_rows_per_sm() &&

@@ -5,10 +5,12 @@ One process per GPU.  Rank r owns a contiguous block of rows of A (and of Y);
 X is replicated; Y = A @ X needs no reduction, only an all-gather of the dense
 output panel so that every GPU ends up with all of Y.  Three exchange modes:
 
-  fused  the SpMM epilogue stores each finished row once into EVERY rank's full
-         panel through NVLink peer mappings (sdb_spmm_dev_allgather): transfer
-         overlaps the gathers, Y is never re-read.  Peer pointers come from
-         CUDA IPC tokens exchanged over torch.distributed.
+  fused  one library call per step (sdb_spmm_dev_allgather) that leaves this
+         rank's rows in EVERY rank's full panel through NVLink peer mappings
+         (CUDA IPC tokens exchanged over torch.distributed).  Default strategy:
+         the shard is cut into a few row chunks and the copy engines push chunk c
+         to the peers while chunk c + 1's kernel runs; SDB_ALLGATHER=stores makes
+         the kernel's epilogue store into the peer panels itself.
   nccl   kernel into the local block, then ncclAllGather (all_gather_into_tensor)
          — the baseline the fused kernel is compared with.
   none   no exchange (independent shards).
