@@ -170,13 +170,17 @@ SDB_API sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, i
  * (peer-mapped device pointers, ld = ldy, own rank included); once `stream` has
  * passed the call, this rank's rows are in every panel.  No separate collective
  * is needed.  beta reads the local panel (dY_peers[self]).  Row-major, op = N.
- * Two exchange strategies (environment SDB_ALLGATHER):
- *   "ce" (default)  the shard is cut into a few row chunks; chunk c's kernel
+ * Exchange strategies (environment SDB_ALLGATHER overrides the automatic choice:
+ * "ce" up to 4 ranks, "k1" beyond, as measured on one 8-GPU box):
+ *   "ce"            the shard is cut into a few row chunks; chunk c's kernel
  *                   writes the local panel and the copy engines push its rows
  *                   to the peers over NVLink (one stream per peer) while chunk
  *                   c + 1's kernel runs, so no SM waits for NVLink;
  *   "stores"        one kernel whose epilogue stores every finished 16-byte
- *                   slice into every peer panel itself. */
+ *                   slice into every peer panel itself;
+ *   "k1"            "stores" with the row-gather kernel even where the L2-tiled
+ *                   streaming kernel would qualify (its CTAs finish continuously,
+ *                   which spreads the peer stores over the whole kernel). */
 SDB_API sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A,
                                           const void* dX, int64_t n, int64_t ldx,
                                           const double* beta, void* const* dY_peers,

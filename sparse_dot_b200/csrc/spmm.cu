@@ -414,12 +414,18 @@ sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, int layou
     return spmm_device(ctx, s, v, A->dtype, conj_a, alpha, beta, layout, dX, n, ldx, yp, 1, 0, 0, ldy);
 }
 
-// How the finished rows reach the peers (SDB_ALLGATHER): "ce" (default) = chunk-pipelined copy-engine exchange,
-// "stores" = the kernel's epilogue stores every finished 16-byte slice into every peer panel itself.
+// How the finished rows reach the peers (SDB_ALLGATHER overrides the automatic choice): "ce" = chunk-pipelined
+// copy-engine exchange, "stores" = the kernel's epilogue stores every finished 16-byte slice into every peer panel
+// itself, "k1" = the same with the row-gather kernel K1 even where the streaming kernel would qualify.
+enum { kXchgAuto = 0, kXchgCopyEngines = 1, kXchgStores = 2, kXchgStoresRowGather = 3 };
 static int allgather_strategy() {
     static const int v = [] {
         const char* e = getenv("SDB_ALLGATHER");
-        return e && e[0] == 's' ? 1 : 0;
+        if (!e) return int(kXchgAuto);
+        if (e[0] == 'c') return int(kXchgCopyEngines);   // "ce"
+        if (e[0] == 's') return int(kXchgStores);        // "stores"
+        if (e[0] == 'k') return int(kXchgStoresRowGather);  // "k1": epilogue stores, row-gather kernel K1
+        return int(kXchgAuto);
     }();
     return v;
 }
@@ -459,9 +465,17 @@ sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A, const v
     SDB_TRY(csr_view(ctx, A, false, &v));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     if (s != ctx->stream) SDB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (n_peers == 1 || allgather_strategy() == 1 || v.rows == 0 || n == 0)
+    // Automatic choice, from the measurements in DESIGN.md §5: up to 4 ranks the copy engines keep up (N = 2: 2.78,
+    // N = 4: 3.87 ms/step against 3.13 / 4.99 with epilogue stores); at 8 ranks they do not (8.74 ms/step for the
+    // 3.6 GB every rank receives), while the row-gather kernel K1 with epilogue stores — whose CTAs finish
+    // continuously, so its peer stores are spread over the whole kernel — ran the same exchange in 5.52 ms/step.
+    int strategy = allgather_strategy();
+    if (strategy == kXchgAuto) strategy = n_peers <= 4 ? kXchgCopyEngines : kXchgStoresRowGather;
+    if (n_peers == 1 || strategy != kXchgCopyEngines || v.rows == 0 || n == 0) {
+        if (n_peers > 1 && strategy == kXchgStoresRowGather) v.owner = nullptr;  // ad-hoc view: never the streaming kernel
         return spmm_device(ctx, s, v, A->dtype, false, alpha, beta, SDB_LAYOUT_ROW_MAJOR, dX, n, ldx, dY_peers,
                            n_peers, self, row0, ldy);
+    }
 
     SDB_TRY(ensure_exchange_streams(ctx, n_peers));
     const size_t row_bytes = size_t(n) * dtype_size(A->dtype);

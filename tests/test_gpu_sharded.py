@@ -1,7 +1,8 @@
 """
-GPU tests of the row-sharded SpMM: single-rank plan, and a
-two-rank run of the FUSED all-gather epilogue (peer panels mapped with CUDA
-IPC).  The two ranks share cuda:0 when the box has one GPU — peer mapping works
+GPU tests of the row-sharded SpMM: single-rank plan, and
+two-rank runs of the FUSED all-gather (peer panels mapped with CUDA IPC) for
+every exchange strategy (copy-engine chunks, epilogue stores, K1 + stores) and
+both kernels.  The two ranks share cuda:0 when the box has one GPU — peer mapping works
 between processes on the same device — with `gloo` as the process group, so
 the test needs no second GPU; with >= 2 GPUs each rank takes its own.
 """
@@ -43,9 +44,13 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, strategy, slab, rows):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    # read once per process by the library: exchange strategy and kernel selection
+    os.environ["SDB_ALLGATHER"] = strategy
+    os.environ["SDB_SLAB"] = slab
+    os.environ["SDB_SLAB_MB"] = "1"
     import torch.distributed as dist
 
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -55,37 +60,52 @@ def _worker(rank, world, port, q):
 
         dev = rank % sdb.device_count()
         _lib.check(_lib.SDB.lib.sdb_set_device(dev), "sdb_set_device")
-        top = cs.uniform_rows_csr(3000, 2000, 40, np.float32, seed=1)
-        bottom = cs.uniform_rows_csr(7000, 2000, 5, np.float32, seed=2)
+        top = cs.uniform_rows_csr(3 * rows // 10, 2000, 40, np.float32, seed=1)
+        bottom = cs.uniform_rows_csr(rows - 3 * rows // 10, 2000, 5, np.float32, seed=2)
         a = sp.vstack([top, bottom]).tocsr()
         x = np.random.default_rng(3).random((2000, 128), dtype=np.float32)
-        y0 = np.random.default_rng(4).random((10000, 128), dtype=np.float32)
+        y0 = np.random.default_rng(4).random((rows, 128), dtype=np.float32)
         got = sharded.spmm_sharded(a, x, world, rank, allgather="fused", out=y0, out_scalar=0.25)
         want = orc.c_spmm(a, x, beta=0.25, y=y0.copy())
-        q.put((rank, cs.rel_err(got, want)))
+        q.put((rank, cs.rel_err(got, want), sdb.last_spmm_kernel()))
     except Exception as e:  # surface the failure in the parent
-        q.put((rank, repr(e)))
+        q.put((rank, repr(e), ""))
     finally:
         dist.destroy_process_group()
 
 
+# (exchange strategy, SDB_SLAB, global rows, kernel expected): small panels take one chunk, the 300k-row cases are
+# cut into several chunks (copy engines) — with SDB_SLAB=2 into whole waves of the streaming kernel's grid
+CASES = [
+    ("ce", "1", 10_000, "spmm_rowmajor"),
+    ("ce", "1", 300_000, "spmm_rowmajor"),
+    ("ce", "2", 300_000, "spmm_stream"),
+    ("stores", "1", 10_000, "spmm_rowmajor"),
+    ("stores", "2", 300_000, "spmm_stream"),
+    ("k1", "2", 300_000, "spmm_rowmajor"),
+    ("auto", "0", 10_000, "spmm_rowmajor"),
+]
+
+
 @pytest.mark.timeout(300)
-def test_two_rank_fused_allgather_matches_oracle():
+@pytest.mark.parametrize("strategy,slab,rows,kernel", CASES)
+def test_two_rank_fused_allgather_matches_oracle(strategy, slab, rows, kernel):
     import torch.multiprocessing as mp
 
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, strategy, slab, rows)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
-    for rank, err in results:
+    for rank, err, used in results:
         assert isinstance(err, float), f"rank {rank} failed: {err}"
         assert err <= 1e-5, f"rank {rank}: full panel differs from the oracle ({err:.2e})"
+        assert used.startswith(kernel), (rank, used)
 
 
 def _worker_products(rank, world, port, q):
