@@ -89,6 +89,53 @@ def test_c_oracle_agrees_with_the_reference(dtype):
     assert cs.rel_err(orc.c_spmmd(m1, m2), REF.dot_product_mkl(m1, m2, dense=True), _bound(m1, m2)) <= tol
 
 
+def _error_cases():
+    a = sp.random(30, 40, density=0.2, format="csr", random_state=1)
+    b = np.random.default_rng(0).random((40, 5))
+    v = np.random.default_rng(0).random(40)
+    sq = sp.random(12, 12, density=0.3, format="csr", random_state=2)
+    return {
+        "coo x coo": lambda m: m.dot_product_mkl(a.tocoo(), a.T.tocoo()),
+        "misaligned sparse x dense": lambda m: m.dot_product_mkl(a, b[:-1]),
+        "misaligned sparse x sparse": lambda m: m.dot_product_mkl(a, a),
+        "misaligned sparse x vector": lambda m: m.dot_product_mkl(a, v[:-1]),
+        "3-d operand": lambda m: m.dot_product_mkl(a, np.zeros((40, 5, 2))),
+        "mixed precision without cast": lambda m: m.dot_product_mkl(a.astype(np.float32), b),
+        "integer data without cast": lambda m: m.dot_product_mkl(a.astype(np.int32), b),
+        "out: wrong shape": lambda m: m.dot_product_mkl(a, b, out=np.zeros((3, 3))),
+        "out: wrong dtype": lambda m: m.dot_product_mkl(a, b, out=np.zeros((30, 5), dtype=np.float32)),
+        "out: wrong order": lambda m: m.dot_product_mkl(a, b, out=np.zeros((30, 5), order="F")),
+        "out: not contiguous": lambda m: m.dot_product_mkl(a, b, out=np.zeros((30, 10))[:, ::2]),
+        "out with a sparse result": lambda m: m.dot_product_mkl(a, a.T.tocsr(), out=np.zeros((30, 30))),
+        "dense operand not contiguous": lambda m: m.dot_product_mkl(a, np.zeros((40, 10))[:, ::2]),
+        "gram: complex": lambda m: m.gram_matrix_mkl(a.astype(np.complex128)),
+        "gram: CSC without cast": lambda m: m.gram_matrix_mkl(a.tocsc()),
+        "gram: BSR": lambda m: m.gram_matrix_mkl(sq.tobsr((3, 3))),
+        "gram: out with a sparse result": lambda m: m.gram_matrix_mkl(a, out=np.zeros((40, 40))),
+        "empty sparse x dense": lambda m: m.dot_product_mkl(sp.csr_matrix((30, 40)), b),
+        "empty sparse x sparse": lambda m: m.dot_product_mkl(sp.csr_matrix((30, 40)), sp.csr_matrix((40, 7))),
+    }
+
+
+def _outcome(call, module):
+    try:
+        r = call(module)
+        return ("returned", type(r).__name__, tuple(r.shape), str(r.dtype), float(abs(r).sum()))
+    except Exception as e:  # noqa: BLE001
+        return (type(e).__name__, str(e))
+
+
+@pytest.mark.parametrize("name", sorted(_error_cases()))
+def test_validation_paths_behave_like_the_reference(name):
+    """Everything the reference decides BEFORE it touches MKL — refusals and the empty-product shortcut
+    (_common.py:725-955, 1003-1024; sparse_dot.py; _gram_matrix.py:283-310) — needs no GPU in this package
+    either: same exception type AND the same message, or the same kind of empty result."""
+    import sparse_dot_b200 as sdb
+
+    call = _error_cases()[name]
+    assert _outcome(call, sdb) == _outcome(call, REF)
+
+
 # ----------------------------------------------------------------------------- GPU: ours vs the reference, live
 ALL = [np.float32, np.float64, np.complex64, np.complex128]
 
