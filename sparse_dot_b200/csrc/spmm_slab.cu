@@ -130,7 +130,6 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
                        T* __restrict__ y_self, SlabPeers<T> peers, int n_peers, int self, int64_t row0, int64_t ldy) {
     constexpr int VEC = Pack16<T>::N;
     constexpr int kRows = RPW * WARPS;  // rows per CTA
-    constexpr unsigned kFull = 0xffffffffu;
     using Ent = StagedEntry<T>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
