@@ -388,11 +388,24 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     k_ms = float(np.mean(kernel_ms))
     achieved = g / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, l2_to_sm = None, None
     tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-    if os.path.exists(tpath):  # ncu's DRAM bytes per launch for the kernel that was just timed (None if never captured)
+    if os.path.exists(tpath):  # ncu's bytes per launch for the kernel that was just timed (None if never captured)
         try:
-            traffic = json.load(open(tpath)).get("kernels", {}).get(kernel_name, {}).get("dram_bytes_per_launch")
+            captured = json.load(open(tpath)).get("kernels", {}).get(kernel_name, {})
+            traffic = captured.get("dram_bytes_per_launch")
+            l2_bytes = captured.get("l2_to_sm_bytes_per_launch")
+            if l2_bytes:
+                # what binds the streaming kernel: bytes delivered L2 -> L1 (ncu l1tex__m_xbar2l1tex_read_bytes) per
+                # launch over the live launch time, against the ~6300 B/clk L2 throughput the microarchitecture guide
+                # measures, at the SM clock sampled during the timed region
+                mhz = (clocks or {}).get("sm_mhz") or 1900.0
+                peak_l2 = 6300.0 * mhz * 1e6 / 1e9
+                ach_l2 = l2_bytes / (k_ms * 1e-3) / 1e9
+                l2_to_sm = {"bytes_per_launch": l2_bytes, "achieved": ach_l2, "peak_estimate": peak_l2, "unit": "GB/s",
+                            "frac": ach_l2 / peak_l2,
+                            "note": "binding resource of the L2-tiled kernel: every stored entry moves one 512 B X "
+                                    "row from L2 into an SM; half of those rows never reach HBM"}
         except ValueError:
             traffic = None
 
@@ -417,7 +430,7 @@ def run_ours(args):
         "gflops": 2.0 * nnz * n * world / (ms_per_step * 1e-3) / 1e9,
         "config": workload_config(world, mode),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name,
+                     "traffic": traffic, "l2_to_sm": l2_to_sm, "peak_source": peak_src, "kernel": kernel_name,
                      "kernel_ms": k_ms, "algorithmic_bytes": g, "unique_bytes": u,
                      "frac_of_8TBs_nominal": achieved / 8000.0,
                      "model": "gather model: (4+4)+128*4 B per nnz, 128*4*2 B per row, 8 B per indptr entry"},
