@@ -10,22 +10,35 @@ Workload (BASELINE.json configs[1]):  CSR(1M x 1M, 50 nnz/row, fp32) x dense(1M 
     python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a CUDA)
     python bench.py --impl reference --steps K --warmup W    # the reference's MKL path on host cores
 
-N > 1 is launched by torch.distributed.run, one rank per GPU: every rank owns
-one 1M-row block of a (N x 1M)-row product (weak scaling), X is replicated, and
-the SpMM epilogue stores each finished row into every rank's full output panel
-over NVLink peer mappings (the fused all-gather of SURVEY.md §8e);
-`--allgather nccl` runs kernel + ncclAllGather instead, `--allgather none` skips
-the exchange.
+N > 1 is launched by torch.distributed.run, one rank per GPU: every rank owns one 1M-row block of a
+(N x 1M)-row product (weak scaling), X is replicated, and one library call per step leaves the rank's rows
+in every rank's full output panel over NVLink peer mappings (the fused all-gather of SURVEY.md §8e; the
+exchange strategy is picked by timing the candidates during warm-up); `--allgather nccl` runs kernel +
+ncclAllGather instead, `--allgather none` skips the exchange.  After the timed region every rank checks rows
+of EVERY peer's block in its own copy of the panel against a float64 recomputation.
 
-Prints ONE JSON line (rank 0).  `value` times the kernel with operands resident
-in HBM; `e2e` times the public API call (dot_product_mkl on host arrays, H2D and
-D2H inside); `roofline` uses algorithmic (gather-model) bytes, SURVEY.md §8d;
-`cpu_baseline` is the reference's MKL call sequence on this host's cores.
+ONE JSON line (rank 0):
+  value       whole-job gather-model GB/s, operands resident in HBM, CUDA events on the launching stream;
+  e2e         the public call dot_product_mkl(csr, ndarray, out=, out_scalar=) on page-locked host arrays, H2D and
+              D2H inside the timed region; e2e.pageable = the same call on ordinary numpy arrays;
+  roofline    of the dominant kernel: `traffic` = ncu DRAM bytes per launch (profiles/kernel_traffic.json; only
+              when the SASS of that kernel is the one that was profiled), `frac` = traffic / time / measured HBM
+              peak, `effective_*` = the same with the algorithmic (gather-model) bytes of SURVEY.md §8d,
+              `l2_to_sm` = the binding resource of the L2-tiled kernel against an L2 read peak probed in this run;
+  inspector   one-time cost of the handle's slab-ordered copy (ms, extra HBM bytes);
+  legs        N = 1 only: BASELINE configs[2] (SpGEMM R-MAT scale 22, edge factors 1 and 4), configs[3] (dense gram
+              2M x 100k) and the configs[4] BSR-16 variant, each timed with its own roofline;
+  configs4    N = 8 (or --c5): BASELINE configs[4], CSR(8M x 1M, 64 nnz/row) x dense(1M x 256) row-sharded with the
+              all-gather, peer rows verified;
+  cpu_baseline  the unmodified reference (sparse_dot_mkl on real oneMKL) on this host's cores.
 """
 import argparse
 import ctypes
+import hashlib
+import importlib.util
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -37,35 +50,21 @@ import scipy.sparse as sp
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+from tests import _cases as cs  # noqa: E402  (the one generator of the BASELINE recipes, shared with the tests)
+
 M_ROWS = 1_000_000
 K_COLS = 1_000_000
 NNZ_PER_ROW = 50
 N_DENSE = 128
 BETA = 0.5
 DTYPE = np.float32
+T_START = time.perf_counter()
 
 
 # ----------------------------------------------------------------------------- workload
 def make_workload(rows, cols, per_row, n_dense, seed):
-    """BASELINE C2 recipe: exactly `per_row` sorted distinct columns per
-    row, values U[0.5, 1.5) (no cancellation), X and Y uniform random; seeded."""
-    rng = np.random.default_rng(seed)
-    idx = rng.integers(0, cols, size=(rows, per_row), dtype=np.int32)
-    idx.sort(axis=1)
-    for _ in range(6):  # re-draw duplicates
-        dup = np.zeros(idx.shape, dtype=bool)
-        dup[:, 1:] = idx[:, 1:] == idx[:, :-1]
-        n_dup = int(dup.sum())
-        if n_dup == 0:
-            break
-        idx[dup] = rng.integers(0, cols, size=n_dup, dtype=np.int32)
-        idx.sort(axis=1)
-    indptr = np.arange(0, rows * per_row + 1, per_row, dtype=np.int32)
-    data = rng.random(rows * per_row, dtype=np.float32) + np.float32(0.5)
-    a = sp.csr_matrix((data, idx.ravel(), indptr), shape=(rows, cols))
-    x = np.random.default_rng(seed + 2).random((cols, n_dense), dtype=np.float32)
-    y = np.random.default_rng(seed + 3).random((rows, n_dense), dtype=np.float32)
-    return a, x, y
+    """BASELINE C2 / C5 recipe: tests/_cases.c2_workload."""
+    return cs.c2_workload(rows, cols, per_row, n_dense, seed)
 
 
 def algorithmic_bytes(rows, nnz, n_dense, beta_nonzero=True, si=4, sv=4):
@@ -126,6 +125,71 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- ncu traffic, tied to the SASS
+def sass_sha(kernel_substr):
+    """sha1 of the SASS of every function of libsdb200's objects whose name contains `kernel_substr`
+    (addresses and comments stripped), or None when cuobjdump / the objects are not there.  The ncu DRAM
+    bytes in profiles/kernel_traffic.json are only quoted for the SASS they were captured from."""
+    obj_dir = os.path.join(ROOT, "sparse_dot_b200", "csrc", "_obj")
+    try:
+        objs = sorted(f for f in os.listdir(obj_dir) if f.endswith(".o"))
+    except OSError:
+        return None
+    h, found = hashlib.sha1(), False
+    for o in objs:
+        try:
+            out = subprocess.run(["cuobjdump", "-sass", os.path.join(obj_dir, o)], capture_output=True, text=True,
+                                 timeout=120).stdout
+        except (OSError, subprocess.TimeoutExpired):
+            return None
+        keep = False
+        for line in out.splitlines():
+            m = re.match(r"\s*Function : (\S+)", line)
+            if m:
+                keep = kernel_substr in m.group(1)
+                found = found or keep
+                if keep:
+                    h.update(m.group(1).encode())
+                continue
+            if keep:
+                m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
+                if m:
+                    h.update(m.group(1).encode())
+    return h.hexdigest() if found else None
+
+
+def mangled_hint(kernel_name):
+    """'spmm_stream_kernel<float,6,32,2,2>' -> the Itanium-mangled fragment of that instantiation."""
+    m = re.match(r"(\w+)<(.*)>", kernel_name)
+    if not m:
+        return kernel_name
+    base, args = m.group(1), m.group(2).split(",")
+    enc = {"float": "f", "double": "d"}
+    parts = []
+    for a in args:
+        a = a.strip()
+        parts.append(enc[a] if a in enc else f"Li{a}E")
+    return f"{len(base)}{base}I" + "".join(parts) + "E"
+
+
+def captured_traffic(kernel_name):
+    """(entry, note): the ncu capture of `kernel_name` if profiles/kernel_traffic.json has one for this SASS."""
+    path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    try:
+        entry = json.load(open(path)).get("kernels", {}).get(kernel_name)
+    except (OSError, ValueError):
+        return None, "profiles/kernel_traffic.json missing"
+    if not entry:
+        return None, f"no ncu capture of {kernel_name}"
+    want = entry.get("sass_sha1")
+    have = sass_sha(entry.get("sass_match", mangled_hint(kernel_name)))
+    if want and have and want == have:
+        return entry, "ncu capture matches the SASS of this build"
+    if have is None:
+        return None, "cannot hash the SASS here (cuobjdump or objects missing): traffic withheld"
+    return None, f"SASS differs from the profiled build ({have[:12]} vs {str(want)[:12]}): traffic withheld"
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -238,18 +302,50 @@ def pinned_like(arr, lib):
     return out
 
 
-def spot_check(plan, a, x, y0, steps, beta, n_rows=8):
-    """A few rows of what was just timed, recomputed with numpy in float64:
-    after k steps of y <- A x + beta y,  y_k = (1 - beta^k)/(1 - beta) * A x + beta^k * y0."""
-    rows = np.linspace(0, a.shape[0] - 1, n_rows).astype(np.int64)
-    worst = 0.0
+def expected_rows(a, x, y0, rows, steps, beta):
+    """float64 recomputation of panel rows after `steps` passes of y <- A x + beta y:
+    y_k = (1 - beta^k)/(1 - beta) * A x + beta^k * y0."""
+    out = []
     for r in rows:
         s, e = a.indptr[r], a.indptr[r + 1]
         ax = (a.data[s:e].astype(np.float64)[:, None] * x[a.indices[s:e]].astype(np.float64)).sum(axis=0)
-        want = (1.0 - beta ** steps) / (1.0 - beta) * ax + beta ** steps * y0[r].astype(np.float64)
-        got = plan.read_rows(plan.panel_row0 + int(r), 1)[0].astype(np.float64)
-        worst = max(worst, float(np.max(np.abs(got - want) / np.abs(want))))
-    return {"rows_checked": int(n_rows), "max_rel_err": worst, "ok": bool(worst < 1e-5)}
+        out.append((1.0 - beta ** steps) / (1.0 - beta) * ax + beta ** steps * y0[r].astype(np.float64))
+    return out
+
+
+def panel_check(plan, a, x, y0, steps, beta, world, rank, dist, n_rows=8, n_peer_rows=4):
+    """Parity of what was just timed.  Local: `n_rows` rows of this rank's block.  N > 1: every rank also
+    publishes `n_peer_rows` recomputed rows of ITS block and every rank verifies the rows of ALL blocks in
+    its own copy of the panel — a broken exchange cannot report ok."""
+    def worst_of(first_row, want_rows, picks):
+        worst = 0.0
+        for r, want in zip(picks, want_rows):
+            got = plan.read_rows(first_row + int(r), 1)[0].astype(np.float64)
+            worst = max(worst, float(np.max(np.abs(got - want) / np.abs(want))))
+        return worst
+
+    rows = np.linspace(0, a.shape[0] - 1, n_rows).astype(np.int64)
+    local = worst_of(plan.panel_row0, expected_rows(a, x, y0, rows, steps, beta), rows)
+    res = {"rows_checked": int(n_rows), "max_rel_err": local, "ok": bool(local < 1e-5)}
+    if world > 1 and plan.mode != "none":
+        picks = np.linspace(0, a.shape[0] - 1, n_peer_rows + 2).astype(np.int64)[1:-1]
+        mine = (plan.row0, [int(p) for p in picks], expected_rows(a, x, y0, picks, steps, beta))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        worst, checked = 0.0, 0
+        for q, (row0, prows, want_rows) in enumerate(everyone):
+            if q == rank:
+                continue
+            worst = max(worst, worst_of(row0, want_rows, prows))
+            checked += len(prows)
+        import torch
+
+        t = torch.tensor([worst], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res.update({"peer_rows_checked_per_rank": checked, "peer_blocks": world - 1,
+                    "peer_max_rel_err_over_ranks": float(t.item()),
+                    "ok": bool(res["ok"] and float(t.item()) < 1e-5)})
+    return res
 
 
 def bind_to_gpu_numa(gpu_index):
@@ -268,6 +364,46 @@ def bind_to_gpu_numa(gpu_index):
         return len(cpus)
     except Exception:
         return 0
+
+
+def timed_steps(torch, stream, step, steps, sync_all):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record(stream)
+    for i in range(steps):
+        step()
+        ev[i + 1].record(stream)
+    sync_all()
+    return ev[0].elapsed_time(ev[-1]), [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+
+
+def max_over_ranks(torch, dist, world, value):
+    t = torch.tensor([value], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def e2e_leg(sdb, lib, torch, dist, world, a, x, y0, steps, sync_all, pinned):
+    """dot_product_mkl(csr, ndarray, out=, out_scalar=) on host arrays, wall clock, max over ranks."""
+    if pinned:
+        xa, ya = pinned_like(x, lib), pinned_like(y0, lib)
+        ap = sp.csr_matrix((pinned_like(a.data, lib), pinned_like(a.indices, lib), pinned_like(a.indptr, lib)),
+                           shape=a.shape)
+    else:
+        xa, ya, ap = x, y0.copy(), a
+    sdb.dot_product_mkl(ap, xa, out=ya, out_scalar=BETA)  # warm-up (allocator pools, staging rings, copy threads)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sdb.dot_product_mkl(ap, xa, out=ya, out_scalar=BETA)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(torch, dist, world, time.perf_counter() - t0) / steps
+    phases = sdb.last_timing_ms()
+    # what came back, against the closed form after steps + 1 calls (first and last row of the block)
+    rows = np.array([0, a.shape[0] - 1])
+    want = expected_rows(a, x, y0, rows, steps + 1, BETA)
+    err = max(float(np.max(np.abs(ya[r].astype(np.float64) - w) / np.abs(w))) for r, w in zip(rows, want))
+    return dt, phases, err
 
 
 def run_ours(args):
@@ -296,6 +432,12 @@ def run_ours(args):
     x = make_workload(1, cols, 1, n, seed=0)[1] if world > 1 else x  # X is replicated: same on every rank
     nnz = a.nnz
 
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     # ---- operands resident in HBM
     plan = sharded.RowShardedSpMM(a, n, world_size=world, rank=rank, allgather=mode,
                                   group=dist.group.WORLD if world > 1 else None)
@@ -307,59 +449,37 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             plan.run(alpha=1.0, beta=BETA, stream_ptr=stream.cuda_stream)
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
+    # the first three steps, one by one: row-gather kernel, inspector + streaming kernel, streaming kernel
+    _, first_ms = timed_steps(torch, stream, step, 3, sync_all)
+    steps_done = 3
+    inspector_ms = max(0.0, first_ms[1] - first_ms[2])
+    tuned = None
+    if world > 1 and mode == "fused" and not args.no_autotune:
+        tuned = plan.autotune(beta=BETA, stream=stream)
+        steps_done += tuned["steps_run"]
     for _ in range(args.warmup):
         step()
+    steps_done += args.warmup
     sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = sdb.kernel_launches()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record(stream)
-    for i in range(args.steps):
-        step()
-        ev[i + 1].record(stream)
-    sync_all()
+    total_ms, kernel_ms = timed_steps(torch, stream, step, args.steps, sync_all)
+    steps_done += args.steps
     launches = sdb.kernel_launches() - launches0
     kernel_name = sdb.last_spmm_kernel()  # what the timed steps launched (same thread)
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
+    ms_per_step = max_over_ranks(torch, dist, world, total_ms) / args.steps
 
-    # parity spot check of what was just timed (rank-local rows), against the CPU oracle
-    check = spot_check(plan, a, x, y0, steps=args.warmup + args.steps, beta=BETA)
+    # parity of what was just timed: local rows and (N > 1) rows of every peer's block in this rank's panel
+    check = panel_check(plan, a, x, y0, steps_done, BETA, world, rank, dist)
 
-    # ---- end to end through the public API on host arrays (pinned), rank-local shard
+    # ---- end to end through the public API on host arrays, rank-local shard
     e2e = None
     if not args.no_e2e:
-        xa = pinned_like(x, lib)
-        ya = pinned_like(y0, lib)
-        ap = sp.csr_matrix((pinned_like(a.data, lib), pinned_like(a.indices, lib), pinned_like(a.indptr, lib)),
-                           shape=a.shape)
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        sdb.dot_product_mkl(ap, xa, out=ya, out_scalar=BETA)  # warm-up (allocator pools, pinned ring)
-        sync_all()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            sdb.dot_product_mkl(ap, xa, out=ya, out_scalar=BETA)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item()) / e2e_steps
-        phases = sdb.last_timing_ms()
+        dt, phases, err = e2e_leg(sdb, lib, torch, dist, world, a, x, y0, e2e_steps, sync_all, pinned=True)
         g1 = algorithmic_bytes(rows, nnz, n)
         e2e = {
             "value": g1 * world / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3, "steps": e2e_steps,
@@ -367,9 +487,25 @@ def run_ours(args):
             "d2h_bytes_per_step": int(y0.nbytes),
             "host_memory": "pinned (sdb_host_alloc)" + (f", rank bound to {local_cpus} GPU-local cores" if local_cpus else ""),
             "device_spans_ms": {"start_to_last_upload": phases[0], "kernel_sum": phases[1], "whole_call": phases[2]},
+            "max_rel_err": err,
             "api": "sparse_dot_b200.dot_product_mkl(csr, ndarray, out=, out_scalar=) -> sdb_spmm_csr_host "
                    "(3-stream row-chunk pipeline: upload / kernel / download overlap)",
         }
+        dtp, phases_p, err_p = e2e_leg(sdb, lib, torch, dist, world, a, x, y0, e2e_steps, sync_all, pinned=False)
+        e2e["pageable"] = {
+            "value": g1 * world / dtp / 1e9, "unit": "GB/s", "ms_per_step": dtp * 1e3, "steps": e2e_steps,
+            "host_memory": "ordinary (pageable) numpy / scipy arrays, staged through page-locked rings by the "
+                           "library's copy threads", "vs_pinned": dtp / dt, "max_rel_err": err_p,
+            "device_spans_ms": {"start_to_last_upload": phases_p[0], "kernel_sum": phases_p[1],
+                                "whole_call": phases_p[2]},
+        }
+
+    # ---- BASELINE configs[4] across the ranks (N = 8 by default)
+    configs4 = None
+    if world > 1 and mode == "fused" and (args.c5 or world == 8):
+        plan.close()
+        plan = None
+        configs4 = run_configs4(args, torch, dist, sharded, sdb, world, rank, sync_all)
 
     if rank != 0:
         if world > 1:
@@ -387,27 +523,50 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     k_ms = float(np.mean(kernel_ms))
-    achieved = g / (k_ms * 1e-3) / 1e9
-    traffic, l2_to_sm = None, None
-    tpath = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-    if os.path.exists(tpath):  # ncu's bytes per launch for the kernel that was just timed (None if never captured)
+    effective = g / (k_ms * 1e-3) / 1e9
+    captured, traffic_note = captured_traffic(kernel_name)
+    traffic = captured.get("dram_bytes_per_launch") if captured else None
+    # probes of this box, this run: HBM read, L2 -> SM read and the 512-byte-row gather out of L2
+    probes = None
+    if not args.no_probes:
         try:
-            captured = json.load(open(tpath)).get("kernels", {}).get(kernel_name, {})
-            traffic = captured.get("dram_bytes_per_launch")
-            l2_bytes = captured.get("l2_to_sm_bytes_per_launch")
-            if l2_bytes:
-                # what binds the streaming kernel: bytes delivered L2 -> L1 (ncu l1tex__m_xbar2l1tex_read_bytes) per
-                # launch over the live launch time, against the ~6300 B/clk L2 throughput the microarchitecture guide
-                # measures, at the SM clock sampled during the timed region
-                mhz = (clocks or {}).get("sm_mhz") or 1900.0
-                peak_l2 = 6300.0 * mhz * 1e6 / 1e9
-                ach_l2 = l2_bytes / (k_ms * 1e-3) / 1e9
-                l2_to_sm = {"bytes_per_launch": l2_bytes, "achieved": ach_l2, "peak_estimate": peak_l2, "unit": "GB/s",
-                            "frac": ach_l2 / peak_l2,
-                            "note": "binding resource of the L2-tiled kernel: every stored entry moves one 512 B X "
-                                    "row from L2 into an SM; half of those rows never reach HBM"}
-        except ValueError:
-            traffic = None
+            probes = {"hbm_read_gbs": _lib.probe_bandwidth(0, 4 << 30, 3),
+                      "l2_read_gbs": _lib.probe_bandwidth(1, 48 << 20, 3),
+                      "l2_gather512_gbs": _lib.probe_bandwidth(2, 48 << 20, 3),
+                      "how": "sdb_probe_bandwidth (csrc/probe.cu): 16-byte loads, CUDA events; HBM over 4 GiB, L2 "
+                             "over an L2-resident 48 MiB (64 passes per launch, L1 bypassed), gather = whole 512 B rows "
+                             "at random positions of the 48 MiB"}
+        except ValueError as e:
+            probes = {"error": str(e)[:200]}
+    l2_to_sm = None
+    if captured and captured.get("l2_to_sm_bytes_per_launch") and probes and probes.get("l2_gather512_gbs"):
+        l2_bytes = captured["l2_to_sm_bytes_per_launch"]
+        ach_l2 = l2_bytes / (k_ms * 1e-3) / 1e9
+        l2_peak = max(probes["l2_gather512_gbs"], probes["l2_read_gbs"])
+        l2_to_sm = {"bytes_per_launch": l2_bytes, "achieved": ach_l2, "peak": l2_peak, "unit": "GB/s",
+                    "frac": ach_l2 / l2_peak, "peak_source": "probed in this run (the faster of the two L2 probes)",
+                    "note": "binding resource of the L2-tiled kernel: every stored entry moves one 512 B X row from "
+                            "L2 into an SM (ncu l1tex__m_xbar2l1tex_read_bytes); half of those rows never reach HBM"}
+    if traffic:
+        achieved, basis = traffic / (k_ms * 1e-3) / 1e9, "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch"
+    else:
+        achieved, basis = effective, "algorithmic (gather-model) bytes: no ncu capture of this SASS (" + traffic_note + ")"
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "basis": basis, "traffic_note": traffic_note,
+        "effective_achieved": effective, "effective_frac": effective / peak,
+        "effective_frac_of_8TBs_nominal": effective / 8000.0,
+        "l2_to_sm": l2_to_sm, "probes": probes, "peak_source": peak_src, "kernel": kernel_name, "kernel_ms": k_ms,
+        "algorithmic_bytes": g, "unique_bytes": u,
+        "model": "gather model: (4+4)+128*4 B per nnz, 128*4*2 B per row, 8 B per indptr entry",
+    }
+    inspector = {
+        "ms": inspector_ms, "first_three_steps_ms": first_ms,
+        "extra_hbm_bytes": int(nnz * 8) if "stream" in kernel_name else 0,
+        "what": "one-time slab-ordered copy of A built on the handle's second multiplication "
+                "(strict_rows_kernel + slab_permute_kernel), outside the timed region; step 1 runs the row-gather "
+                "kernel, step 2 the inspector + streaming kernel, step 3 onwards the streaming kernel",
+    }
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): a bounded sample = 3 full-workload steps
     cpu = None
@@ -423,28 +582,157 @@ def run_ours(args):
                "gflops": 2.0 * nnz * n / cdt / 1e9,
                "sample": f"{reps} full-workload steps after 1 warm-up ({what})"}
 
+    # ---- the other BASELINE configs on this GPU (N = 1 only)
+    legs = None
+    if world == 1 and not args.no_legs:
+        if plan is not None:
+            plan.close()
+            plan = None
+        del a, x, y0
+        legs = run_legs(args, peak)
+
     line = {
         "metric": "spmm_effective_hbm_gbs", "value": g * world / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "gflops": 2.0 * nnz * n * world / (ms_per_step * 1e-3) / 1e9,
         "config": workload_config(world, mode),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "l2_to_sm": l2_to_sm, "peak_source": peak_src, "kernel": kernel_name,
-                     "kernel_ms": k_ms, "algorithmic_bytes": g, "unique_bytes": u,
-                     "frac_of_8TBs_nominal": achieved / 8000.0,
-                     "model": "gather model: (4+4)+128*4 B per nnz, 128*4*2 B per row, 8 B per indptr entry"},
+        "roofline": roofline,
+        "inspector": inspector,
         "cpu_baseline": cpu,
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "parity_spot_check": check,
+        "exchange": tuned,
+        "configs4": configs4,
+        "legs": legs,
         "version": sdb.get_version_string(),
     }
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_configs4(args, torch, dist, sharded, sdb, world, rank, sync_all):
+    """BASELINE configs[4]: CSR(world x 1M rows x 1M, 64 nnz/row, fp32) x dense(1M x 256), one 1M-row shard per
+    rank, the all-gather of the output panel fused into the step; every rank verifies rows of every block."""
+    rows, cols, per_row, n = 1_000_000, 1_000_000, 64, 256
+    a, _, y0 = make_workload(rows, cols, per_row, n, seed=5 + 10 * rank)
+    x = np.random.default_rng(6).random((cols, n), dtype=np.float32)
+    stream = torch.cuda.Stream()
+    res = {"workload": f"CSR({world * rows}x{cols}, {per_row} nnz/row, fp32) x dense({cols}x{n}), row-sharded x{world}, "
+                       "fused all-gather; BASELINE.json configs[4]", "beta": BETA}
+    # the shard's kernel alone (no exchange)
+    solo = sharded.RowShardedSpMM(a, n, world_size=world, rank=rank, allgather="none", group=dist.group.WORLD)
+    solo.set_x(x)
+    solo.set_local_y(y0)
+
+    def solo_step():
+        with torch.cuda.stream(stream):
+            solo.run(alpha=1.0, beta=BETA, stream_ptr=stream.cuda_stream)
+
+    timed_steps(torch, stream, solo_step, 3, sync_all)
+    t_ms, _ = timed_steps(torch, stream, solo_step, 5, sync_all)
+    res["kernel_only_ms"] = max_over_ranks(torch, dist, world, t_ms) / 5
+    res["kernel"] = sdb.last_spmm_kernel()
+    solo.close()
+
+    plan = sharded.RowShardedSpMM(a, n, world_size=world, rank=rank, allgather="fused", group=dist.group.WORLD)
+    plan.set_x(x)
+    plan.set_local_y(y0)
+
+    def step():
+        with torch.cuda.stream(stream):
+            plan.run(alpha=1.0, beta=BETA, stream_ptr=stream.cuda_stream)
+
+    timed_steps(torch, stream, step, 3, sync_all)
+    done = 3
+    if not args.no_autotune:
+        tuned = plan.autotune(beta=BETA, stream=stream)
+        done += tuned["steps_run"]
+        res["exchange"] = tuned
+    steps = 10
+    t_ms, _ = timed_steps(torch, stream, step, steps, sync_all)
+    done += steps
+    ms = max_over_ranks(torch, dist, world, t_ms) / steps
+    ingress = (world - 1) * rows * n * 4
+    g = algorithmic_bytes(rows, a.nnz, n)
+    res.update({
+        "ms_per_step": ms, "steps": steps, "value_gbs": g * world / (ms * 1e-3) / 1e9,
+        "gflops": 2.0 * a.nnz * n * world / (ms * 1e-3) / 1e9,
+        "ingress_bytes_per_rank": ingress, "ingress_gbs_achieved": ingress / (ms * 1e-3) / 1e9,
+        "step_over_kernel": ms / res["kernel_only_ms"],
+        "parity_spot_check": panel_check(plan, a, x, y0, done, BETA, world, rank, dist),
+    })
+    plan.close()
+    return res
+
+
+def load_run_configs():
+    spec = importlib.util.spec_from_file_location("_run_configs", os.path.join(ROOT, "scripts", "run_configs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def run_legs(args, peak):
+    """The other BASELINE configs on one GPU, each with its own roofline (algorithmic bytes per SURVEY.md §8d over
+    the measured time; `traffic` from profiles/kernel_traffic.json when the SASS matches).  Checks are the
+    size-independent properties of scripts/run_configs.py (checksums, sampled rows, triangle rules)."""
+    rc = load_run_configs()
+    legs, budget_s = {}, args.legs_budget
+
+    def roof(name, gbytes, ms, kernel_key):
+        entry, note = captured_traffic(kernel_key)
+        traffic = entry.get("dram_bytes_per_launch") if entry else None
+        ach = gbytes / (ms * 1e-3)
+        r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+             "basis": "algorithmic bytes", "traffic": traffic, "traffic_note": note}
+        if traffic:
+            r["traffic_gbs"] = traffic / (ms * 1e-3) / 1e9
+            r["traffic_frac"] = r["traffic_gbs"] / peak
+        return r
+
+    wanted = [w.strip() for w in args.legs.split(",") if w.strip()]
+    for name in wanted:
+        if time.perf_counter() - T_START > budget_s:
+            legs[name] = {"skipped": f"time budget of {budget_s} s for the whole bench reached"}
+            continue
+        t0 = time.perf_counter()
+        try:
+            if name in ("spgemm_ef1", "spgemm_ef4"):
+                ef = 1 if name.endswith("1") else 4
+                r = rc.run_c3_resident(22, ef)
+                ms = r["spgemm_ordered_ms"]
+                # numeric (4+4) + symbolic 4 bytes per product, A once per pass, C written once
+                gb = (r["products"] * 12 + 2 * r["nnz_a"] * 8 + r["nnz_c"] * 8) / 1e9
+                r["g_products_per_s_ordered"] = r["products"] / (ms * 1e-3) / 1e9
+                r["roofline"] = roof(name, gb, ms, "spgemm_ordered")
+                r["config"] = f"BASELINE configs[2]: R-MAT scale 22, edge factor {ef}, fp32, sorted sparse output " \
+                              "(sdb_spgemm_ordered = reorder_output=True), result kept in HBM"
+            elif name == "gram":
+                r = rc.run_c4(2_000_000, 100_000, 100)
+                ms = r["syrkd_ms"]
+                gb = (r["nnz"] * 8 + r["n"] * (r["n"] + 1) / 2 * 4) / 1e9
+                r["roofline"] = roof(name, gb, ms, "spgemm_dense_red_kernel<float>")
+                r["config"] = "BASELINE configs[3]: A^T A of CSR(2M x 100k, 100 nnz/row, fp32), dense upper triangle, " \
+                              "device resident"
+            elif name == "bsr16":
+                r = rc.run_c5bsr(62_500, 4, 16, 256)
+                ms = r["spmm_ms"]
+                gb = (r["nnz"] * 4 + r["nnz"] / 256 * (4 + 16 * 256 * 4) + r["rows"] * 256 * 4) / 1e9
+                r["roofline"] = roof(name, gb, ms, r.get("kernel", "spmm_bsr_kernel"))
+                r["config"] = "BASELINE configs[4] BSR variant: 1M x 1M, 62 500 block rows x 4 blocks of 16x16 fp32, " \
+                              "x dense(1M x 256)"
+            else:
+                r = {"skipped": "unknown leg"}
+        except Exception as e:  # a leg must never take the headline down with it
+            r = {"error": f"{type(e).__name__}: {e}"[:300]}
+        r["wall_s"] = time.perf_counter() - t0
+        legs[name] = r
+    return legs
 
 
 def main():
@@ -458,6 +746,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-probes", action="store_true")
+    ap.add_argument("--no-autotune", action="store_true", help="N > 1: keep the library's default exchange strategy")
+    ap.add_argument("--no-legs", action="store_true", help="N = 1: skip the configs[2] / [3] / BSR legs")
+    ap.add_argument("--legs", default="bsr16,spgemm_ef1,gram,spgemm_ef4")
+    ap.add_argument("--legs-budget", type=float, default=400.0, help="seconds after which remaining legs are skipped")
+    ap.add_argument("--c5", action="store_true", help="N > 1: also run BASELINE configs[4] (default at N = 8)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

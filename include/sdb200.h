@@ -116,6 +116,14 @@ SDB_API sdb_status sdb_export(const sdb_mat* m, void* indptr, int indptr_bits,
  * row (CSR) / column (CSC) / block row (BSR), values permuted along. */
 SDB_API sdb_status sdb_order(sdb_mat* m);
 
+/* Drop everything the library has cached on a handle (transposed / expanded companions, cross
+ * positions, the slab-ordered copy of the streaming SpMM, the sortedness flag).  Needed only for handles
+ * over BORROWED device arrays (sdb_create_csr_dev) whose owner rewrites the arrays in place: the caches
+ * hold copies of the values.  Handles may be shared by several host threads for products; triangular
+ * products (sdb_syrk*, sdb_syrkd*), sdb_order and sdb_invalidate must not run concurrently with other
+ * calls on the same handle.  No MKL counterpart (MKL's handles borrow and never cache). */
+SDB_API sdb_status sdb_invalidate(sdb_mat* m);
+
 /* mkl_sparse_convert_csr (_common.py:695-722): CSC or BSR (or CSR) -> new CSR
  * handle; op must be SDB_OP_NON_TRANSPOSE or SDB_OP_TRANSPOSE. */
 SDB_API sdb_status sdb_convert_csr(const sdb_mat* m, int op, sdb_mat** out);
@@ -186,6 +194,13 @@ SDB_API sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A,
                                           const double* beta, void* const* dY_peers,
                                           int n_peers, int self, int64_t row0, int64_t ldy,
                                           void* stream);
+
+/* Choose the exchange strategy of sdb_spmm_dev_allgather at run time (process-wide; overrides
+ * SDB_ALLGATHER): strategy 0 = automatic, 1 = "ce", 2 = "stores", 3 = "k1"; chunks = target number of
+ * row chunks of the "ce" pipeline (0 = default, about five).  RowShardedSpMM.autotune() times the
+ * candidates on the live NVLink topology during warm-up and keeps the fastest.  No reference
+ * counterpart (the reference has no multi-device path). */
+SDB_API sdb_status sdb_set_allgather(int strategy, int chunks);
 
 /* ======================= SpGEMM ==================== */
 
@@ -268,6 +283,14 @@ SDB_API sdb_status sdb_set_device(int device);
 SDB_API sdb_status sdb_get_device(int* device);
 SDB_API sdb_status sdb_version_string(char* buf, int len);
 SDB_API int        sdb_last_error(char* buf, int len);
+
+/* Bandwidth probes measured on the device the numbers are quoted on (bench.py's roofline
+ * denominators): kind 0 = HBM read (sequential 16-byte loads over `bytes`, pick a size much larger than
+ * L2), 1 = L2 -> SM read (same loop over an L2-resident `bytes`, L1 bypassed), 2 = L2 -> SM gather of
+ * whole 512-byte rows at random positions of an L2-resident buffer (the access shape of the SpMM
+ * gathers).  Result in GB/s (1e9 bytes per second), timed with CUDA events over `iters` launches after
+ * one warm-up launch.  No reference counterpart. */
+SDB_API sdb_status sdb_probe_bandwidth(int kind, int64_t bytes, int iters, double* gbs);
 
 /* Number of CUDA kernels this library has launched in this process (all
  * threads); bench.py reports the delta over the timed region. */

@@ -1,0 +1,71 @@
+#!/bin/bash
+# scripts/gpu.sh — the ONE runner for everything that needs the B200 box (replaces the one-shot
+# scripts of round 1).  Run from the repo root, normally through gpurun:
+#
+#   gpurun --timeout 900 -- 'scripts/gpu.sh r2a tests bench launches "ncu:spmm_stream:stream" hashes'
+#
+# Every step logs to gpurun_out/<tag>_<step>.*; a failing step does not stop the following ones.
+# Steps:
+#   tests[=<pytest -k expression>]   pytest -m gpu (whole suite, or the selection)
+#   testfile=<path>                  pytest -m gpu on one file
+#   bench[=<extra bench.py args>]    python bench.py --steps 20 --warmup 5 <extra>   (1 GPU)
+#   benchN=<n>[,<extra args>]        torchrun with n ranks
+#   refarm                           bench.py --impl reference
+#   launches[=<bench args>]          ncu launch list (gpu__time_duration.sum) of a short bench run
+#   ncu=<kernel regex>,<name>[,<skip>[,<python script + args>]]   one `--set full` capture of the top kernel
+#   configs=<run_configs.py args>    scripts/run_configs.py ...
+#   hashes                           SASS hashes of the profiled kernels (ties ncu bytes to this build)
+#   py=<script and args>             python <script and args>
+#   smoke                            __graft_entry__.smoke()
+set -u
+cd "$(dirname "$0")/.."
+TAG=$1; shift
+OUT=gpurun_out
+mkdir -p $OUT
+NCU_COMMON="--clock-control none"
+BENCH_SHORT="bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --no-legs --no-probes"
+for step in "$@"; do
+  name=${step%%=*}; arg=""; [[ "$step" == *=* ]] && arg=${step#*=}
+  echo "=== [$TAG] $step ($(date +%T))"
+  case $name in
+    tests)
+      if [ -n "$arg" ]; then timeout 1500 python -m pytest tests -x -q -m gpu -k "$arg" > $OUT/${TAG}_tests.log 2>&1
+      else timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/${TAG}_tests.log 2>&1; fi
+      tail -5 $OUT/${TAG}_tests.log ;;
+    testfile)
+      timeout 1200 python -m pytest "$arg" -x -q -m gpu > $OUT/${TAG}_testfile_$(basename "$arg" .py).log 2>&1
+      tail -5 $OUT/${TAG}_testfile_$(basename "$arg" .py).log ;;
+    bench)
+      timeout 1500 python bench.py --steps 20 --warmup 5 $arg > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+      tail -c 1500 $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err ;;
+    benchN)
+      n=${arg%%,*}; extra=""; [[ "$arg" == *,* ]] && extra=${arg#*,}
+      timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
+        --master-port 29511 bench.py --gpus $n --steps 20 --warmup 5 $extra \
+        > $OUT/${TAG}_bench_n$n.json 2> $OUT/${TAG}_bench_n$n.err
+      tail -c 2500 $OUT/${TAG}_bench_n$n.json; tail -5 $OUT/${TAG}_bench_n$n.err ;;
+    refarm)
+      timeout 900 python bench.py --impl reference --steps 5 --warmup 3 > $OUT/${TAG}_refarm.json 2> $OUT/${TAG}_refarm.err
+      tail -c 600 $OUT/${TAG}_refarm.json ;;
+    launches)
+      timeout 900 ncu --metrics gpu__time_duration.sum $NCU_COMMON -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+        python ${arg:-$BENCH_SHORT} > $OUT/${TAG}_launches.log 2>&1
+      tail -3 $OUT/${TAG}_launches.csv | cut -c1-300 ;;
+    ncu)
+      IFS=, read -r regex nm skip cmd <<< "$arg"
+      timeout 1200 ncu --set full $NCU_COMMON --import-source on -k "regex:$regex" -s ${skip:-2} -c 1 -f \
+        -o $OUT/${TAG}_$nm python ${cmd:-$BENCH_SHORT} > $OUT/${TAG}_ncu_$nm.log 2>&1
+      tail -2 $OUT/${TAG}_ncu_$nm.log ;;
+    configs)
+      timeout 1500 python scripts/run_configs.py $arg > $OUT/${TAG}_configs.log 2>&1; cat $OUT/${TAG}_configs.log | cut -c1-1200 ;;
+    hashes)
+      python scripts/ncu_traffic.py --hashes > $OUT/${TAG}_sass_hashes.json 2>&1; cat $OUT/${TAG}_sass_hashes.json ;;
+    py)
+      timeout 1500 python $arg > $OUT/${TAG}_py_$(echo "$arg" | tr -c 'A-Za-z0-9' '_' | cut -c1-40).log 2>&1
+      tail -40 $OUT/${TAG}_py_$(echo "$arg" | tr -c 'A-Za-z0-9' '_' | cut -c1-40).log ;;
+    smoke)
+      timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; tail -8 $OUT/${TAG}_smoke.log ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
+echo "=== [$TAG] done ($(date +%T))"

@@ -1,0 +1,139 @@
+#!/usr/bin/env python
+"""
+ncu_traffic.py — keeps profiles/kernel_traffic.json, the table bench.py reads `roofline.traffic` from.
+
+    python scripts/ncu_traffic.py --hashes                       (on the GPU box: SASS sha1 per profiled kernel family)
+    python scripts/ncu_traffic.py --update <tag> <rep> [<rep>..] (here: fold .ncu-rep captures + that run's hashes in)
+
+An entry is only quoted by bench.py while the SASS of the kernel is the one that was profiled: the hash written
+by `--hashes` in the same gpurun call travels back in gpurun_out/<tag>_sass_hashes.json and is stored with the bytes.
+Entries are keyed by the kernel's demangled name without spaces ("spmm_stream_kernel<float,6,32,2,2>"); a family
+entry (key = what `--family` names, e.g. "spgemm_ordered") sums every launch of the capture whose name matches.
+"""
+import argparse
+import csv
+import io
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+TABLE = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+
+# kernel families whose SASS is hashed on the box: substring of the mangled name
+FAMILIES = {
+    "spmm_stream_kernel": "spmm_stream_kernel",
+    "spmm_rowmajor_kernel": "spmm_rowmajor_kernel",
+    "spmm_bsr_kernel": "spmm_bsr_kernel",
+    "spmm_bsr_mma_kernel": "spmm_bsr_mma_kernel",
+    "spgemm_dense_red_kernel": "spgemm_dense_red_kernel",
+    "spgemm_": "spgemm_",
+}
+SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+TSCALE = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "second": 1.0, "msecond": 1e-3, "usecond": 1e-6,
+          "nsecond": 1e-9}
+
+
+def short_name(kernel_name):
+    m = re.search(r"(\w+)\s*<([^()]*)>\s*\(", kernel_name)
+    if m:
+        return m.group(1) + "<" + m.group(2).replace(" ", "") + ">"
+    m = re.search(r"(\w+)\s*\(", kernel_name)
+    return m.group(1) if m else kernel_name
+
+
+def family_of(short):
+    base = short.split("<")[0]
+    return base if base in FAMILIES else ("spgemm_" if base.startswith("spgemm_") else None)
+
+
+def hashes():
+    import bench
+
+    print(json.dumps({fam: bench.sass_sha(sub) for fam, sub in FAMILIES.items()}, indent=1))
+
+
+def read_rep(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+
+    def col(r, key, table):
+        if key not in hdr:
+            return None
+        i = hdr.index(key)
+        try:
+            return float(r[i].replace(",", "")) * table.get(units[i], 1.0)
+        except ValueError:
+            return None
+
+    out = []
+    for r in rows[2:]:
+        out.append({
+            "name": short_name(r[hdr.index("Kernel Name")]),
+            "dram_read": col(r, "dram__bytes_read.sum", SCALE),
+            "dram_write": col(r, "dram__bytes_write.sum", SCALE),
+            "l2_to_sm": col(r, "l1tex__m_xbar2l1tex_read_bytes.sum", SCALE),
+            "seconds": col(r, "gpu__time_duration.sum", TSCALE),
+            "l2_hit_pct": col(r, "lts__t_sector_hit_rate.pct", {}),
+            "warps_active_pct": col(r, "sm__warps_active.avg.pct_of_peak_sustained_active", {}),
+        })
+    return out
+
+
+def update(tag, reps, family_key=None):
+    table = {"note": "", "kernels": {}}
+    if os.path.exists(TABLE):
+        table = json.load(open(TABLE))
+    table["note"] = ("DRAM bytes per launch from ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum), "
+                     "each stored with the sha1 of the SASS it was captured from (scripts/ncu_traffic.py); bench.py quotes "
+                     "an entry only while the SASS of the build matches")
+    hpath = os.path.join(ROOT, "gpurun_out", f"{tag}_sass_hashes.json")
+    sass = json.load(open(hpath)) if os.path.exists(hpath) else {}
+    for rep in reps:
+        launches = read_rep(rep)
+        if family_key:
+            tot = {"dram_bytes_read_per_launch": 0.0, "dram_bytes_write_per_launch": 0.0, "seconds": 0.0, "launches": 0}
+            for k in launches:
+                tot["dram_bytes_read_per_launch"] += k["dram_read"] or 0.0
+                tot["dram_bytes_write_per_launch"] += k["dram_write"] or 0.0
+                tot["seconds"] += k["seconds"] or 0.0
+                tot["launches"] += 1
+            fam = "spgemm_" if family_key.startswith("spgemm") else family_key
+            table["kernels"][family_key] = {
+                "source": f"{os.path.basename(rep)} (sum over the {tot['launches']} launches of the capture)",
+                "dram_bytes_read_per_launch": tot["dram_bytes_read_per_launch"],
+                "dram_bytes_write_per_launch": tot["dram_bytes_write_per_launch"],
+                "dram_bytes_per_launch": tot["dram_bytes_read_per_launch"] + tot["dram_bytes_write_per_launch"],
+                "duration_ms_under_ncu": tot["seconds"] * 1e3,
+                "sass_match": FAMILIES.get(fam, fam), "sass_sha1": sass.get(fam),
+            }
+            continue
+        for k in launches:
+            fam = family_of(k["name"])
+            table["kernels"][k["name"]] = {
+                "source": os.path.basename(rep),
+                "dram_bytes_read_per_launch": k["dram_read"], "dram_bytes_write_per_launch": k["dram_write"],
+                "dram_bytes_per_launch": (k["dram_read"] or 0.0) + (k["dram_write"] or 0.0),
+                "l2_to_sm_bytes_per_launch": k["l2_to_sm"],
+                "duration_ms_under_ncu": (k["seconds"] or 0.0) * 1e3, "l2_hit_rate_pct": k["l2_hit_pct"],
+                "warps_active_pct": k["warps_active_pct"],
+                "sass_match": FAMILIES.get(fam, k["name"].split("<")[0]), "sass_sha1": sass.get(fam),
+            }
+    json.dump(table, open(TABLE, "w"), indent=1)
+    print(json.dumps({k: (v["dram_bytes_per_launch"], v.get("sass_sha1")) for k, v in table["kernels"].items()}, indent=1))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--hashes", action="store_true")
+    ap.add_argument("--update", nargs="+", metavar=("TAG", "REP"))
+    ap.add_argument("--family", default=None, help="store the capture as ONE entry under this key (sum of its launches)")
+    a = ap.parse_args()
+    if a.hashes:
+        hashes()
+    elif a.update:
+        update(a.update[0], a.update[1:], a.family)

@@ -45,11 +45,13 @@ PROTOTYPES = {
                             _ct.POINTER(_i64), _ct.POINTER(_i64), _ct.POINTER(_i32)]),
     "sdb_export": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp]),
     "sdb_order": (_i32, [_vp]),
+    "sdb_invalidate": (_i32, [_vp]),
     "sdb_convert_csr": (_i32, [_vp, _i32, _pvp]),
     "sdb_spmm": (_i32, [_i32, _pd, _vp, _i32, _vp, _i64, _i64, _pd, _vp, _i64]),
     "sdb_spmm_csr_host": (_i32, [_i64, _i64, _vp, _vp, _i32, _vp, _i32, _pd, _vp, _i64, _i64, _pd, _vp, _i64]),
     "sdb_spmm_dev": (_i32, [_i32, _pd, _vp, _i32, _vp, _i64, _i64, _pd, _vp, _i64, _vp]),
     "sdb_spmm_dev_allgather": (_i32, [_pd, _vp, _vp, _i64, _i64, _pd, _pvp, _i32, _i32, _i64, _i64, _vp]),
+    "sdb_set_allgather": (_i32, [_i32, _i32]),
     "sdb_spgemm": (_i32, [_i32, _vp, _vp, _pvp]),
     "sdb_spgemm_ordered": (_i32, [_i32, _vp, _vp, _pvp]),
     "sdb_spgemm_dense": (_i32, [_i32, _vp, _vp, _i32, _vp, _i64]),
@@ -74,6 +76,7 @@ PROTOTYPES = {
     "sdb_get_device": (_i32, [_ct.POINTER(_i32)]),
     "sdb_version_string": (_i32, [_ct.c_char_p, _i32]),
     "sdb_last_error": (_i32, [_ct.c_char_p, _i32]),
+    "sdb_probe_bandwidth": (_i32, [_i32, _i64, _i32, _pd]),
     "sdb_kernel_launches": (_i64, []),
     "sdb_last_spmm_kernel": (_i32, [_ct.c_char_p, _i32]),
     "sdb_last_timing": (_i32, [_pd]),
@@ -160,6 +163,13 @@ def last_spmm_kernel():
     buf = _ct.create_string_buffer(160)
     check(SDB.lib.sdb_last_spmm_kernel(buf, 160), "sdb_last_spmm_kernel")
     return buf.value.decode()
+
+
+def probe_bandwidth(kind, nbytes, iters=5):
+    """GB/s of one of the library's bandwidth probes: 0 HBM read, 1 L2 -> SM read, 2 L2 -> SM 512-byte-row gather."""
+    out = _ct.c_double(0.0)
+    check(SDB.lib.sdb_probe_bandwidth(kind, int(nbytes), int(iters), _ct.byref(out)), "sdb_probe_bandwidth")
+    return out.value
 
 
 def last_timing_ms():

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/sdb200.h"
 
@@ -74,6 +75,15 @@ inline size_t dtype_size(int dtype) {
 // ---------------------------------------------------------------- context
 // One per host thread and device: a non-blocking stream, a ring of pinned
 // staging chunks for pageable<->HBM copies, and CUDA-event phase timers.
+// Page-locked staging slots with one "slot is free again" event each (pipeline.cu).
+struct PinnedRing {
+    static constexpr int kSlots = 8;
+    size_t slot_bytes = 0;
+    void* slot[kSlots] = {};
+    cudaEvent_t free_ev[kSlots] = {};
+    int next = 0;
+};
+
 struct Context {
     int device = -1;
     cudaStream_t stream = nullptr;   // compute + H2D
@@ -87,6 +97,8 @@ struct Context {
     void* chunk[kChunks] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t chunk_free[kChunks] = {nullptr, nullptr, nullptr, nullptr};
     int next_chunk = 0;
+    // staging rings of the pipelined host entry point (pageable operands): uploads / downloads
+    PinnedRing up_ring, dn_ring;
     // phase timing of the last host-pointer entry point (ms)
     double last_ms[3] = {0, 0, 0};
     // chunk-pipelined all-gather (sdb_spmm_dev_allgather): one copy stream per peer, a ring of events
@@ -136,6 +148,8 @@ struct DevBuf {
 // once the bytes are in `dst`.  2-D variants copy `rows` rows of `row_bytes`
 // with independent pitches (dense panels with ld != n).
 bool is_pinned(const void* p);  // page-locked (or managed) host memory: DMA without staging
+void host_copy(void* dst, const void* src, size_t bytes);  // memcpy split over the library's copy threads
+sdb_status ensure_ring(PinnedRing* ring, size_t slot_bytes);
 sdb_status h2d(Context* ctx, void* d_dst, const void* h_src, size_t bytes);
 sdb_status d2h(Context* ctx, void* h_dst, const void* d_src, size_t bytes);
 sdb_status h2d_2d(Context* ctx, void* d_dst, size_t d_pitch, const void* h_src, size_t h_pitch,
@@ -251,7 +265,10 @@ int64_t spmm_slab_wave_rows(const Context* ctx, const CsrView& a, int dtype, int
 sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a,
                             const double* alpha, const double* beta, const void* dX, int64_t n, int64_t ldx,
                             void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy);
+extern std::mutex g_companion_mutex;  // serialises building / dropping the per-handle caches (format.cu)
 sdb_status ensure_strict_flag(Context* ctx, sdb_mat* m);
+// range / monotonicity check of freshly uploaded arrays; also sets strict_sorted (format.cu)
+sdb_status validate_compressed(Context* ctx, sdb_mat* m);
 // Native BSR x dense kernel (spmm_bsr.cu): availability test + launch.
 bool spmm_bsr_supported(const sdb_mat* a, int op, int layout, const void* dX, int64_t n, int64_t ldx, const void* dY,
                         int64_t ldy);

@@ -5,6 +5,8 @@
 //   * BSR -> CSR expansion       (mkl_sparse_convert_csr on a BSR handle;
 //                                 tests/test_mkl.py:251-268)
 // All integer/byte work: HBM-bound, coalesced streams, no tensor cores.
+#include <mutex>
+
 #include "common.h"
 #include "prims.h"
 
@@ -259,6 +261,51 @@ __global__ void __launch_bounds__(256) strict_rows_kernel(int64_t rows, const in
     bool bad = false;
     for (int64_t p = b + 1 + lane; p < e; p += 32) bad |= indices[p] <= indices[p - 1];
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(violations, 1u);
+}
+
+// One pass over freshly uploaded compressed arrays (sdb_create_*): flags[0] counts lines whose offsets or
+// indices are out of range (offsets must be non-decreasing inside [0, nnz], indices inside [0, minor)),
+// flags[1] counts lines that are not strictly ascending.  A malformed scipy matrix thus becomes
+// SDB_STATUS_INVALID_VALUE at create instead of an out-of-bounds access in a later kernel.
+__global__ void __launch_bounds__(256) validate_lines_kernel(int64_t lines, int64_t minor, int64_t nnz,
+                                                             const int64_t* __restrict__ indptr,
+                                                             const int32_t* __restrict__ indices,
+                                                             unsigned* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= lines) return;
+    const int64_t b = indptr[r], e = indptr[r + 1];
+    if (b < 0 || e > nnz || b > e) {
+        if (lane == 0) atomicAdd(&flags[0], 1u);
+        return;
+    }
+    bool range_bad = false, order_bad = false;
+    for (int64_t p = b + lane; p < e; p += 32) {
+        const int32_t c = indices[p];
+        range_bad |= c < 0 || int64_t(c) >= minor;
+        if (p > b) order_bad |= c <= indices[p - 1];
+    }
+    if (__any_sync(0xffffffffu, range_bad) && lane == 0) atomicAdd(&flags[0], 1u);
+    if (__any_sync(0xffffffffu, order_bad) && lane == 0) atomicAdd(&flags[1], 1u);
+}
+
+sdb_status validate_compressed(Context* ctx, sdb_mat* m) {
+    const int64_t lines = major_dim(m);
+    if (lines <= 0) return SDB_STATUS_SUCCESS;
+    cudaStream_t s = ctx->stream;
+    DevBuf f;
+    SDB_TRY(f.alloc(2 * sizeof(unsigned), s));
+    SDB_CUDA(cudaMemsetAsync(f.p, 0, 2 * sizeof(unsigned), s));
+    SDB_LAUNCH(validate_lines_kernel, blocks_for(lines * 32, 256), 256, 0, s, lines, minor_dim(m), m->nnz, m->indptr,
+               m->indices, f.as<unsigned>());
+    unsigned h[2] = {0, 0};
+    SDB_CUDA(cudaMemcpyAsync(h, f.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    SDB_CUDA(cudaStreamSynchronize(s));
+    SDB_REQUIRE(h[0] == 0, SDB_STATUS_INVALID_VALUE,
+                "create: %u line(s) with row offsets that decrease or leave [0, nnz], or indices outside [0, %lld)", h[0],
+                (long long)minor_dim(m));
+    m->strict_sorted = h[1] == 0 ? 1 : -1;
+    return SDB_STATUS_SUCCESS;
 }
 
 // every line strictly ascending (sorted, no duplicate index)?  cached on the handle
@@ -568,8 +615,15 @@ sdb_status compress_to_bsr(Context* ctx, const sdb_mat* csr, int64_t b, sdb_mat*
 }
 
 // ============================================================ CSR view of op(A)
+// Companions (transposed form, BSR expansion, cross positions) are built lazily and cached on the handle; one
+// process-wide mutex serialises building them, so two threads multiplying with the same handle cannot build
+// (or free) a companion twice.  A companion is only ever REPLACED by the positions request of a triangular
+// product (syrk / syrkd): those must not run concurrently with other calls on the same handle (sdb200.h).
+std::mutex g_companion_mutex;
+
 sdb_status csr_view(Context* ctx, const sdb_mat* m_in, bool transpose, CsrView* v, bool want_pos) {
     sdb_mat* m = const_cast<sdb_mat*>(m_in);  // companions are a cache, not a logical mutation
+    std::lock_guard<std::mutex> companion_lock(g_companion_mutex);
     if (m->format == SDB_FMT_BSR) {
         if (!m->expanded) SDB_TRY(expand_bsr(ctx, m, &m->expanded));
         m = m->expanded;
@@ -643,6 +697,26 @@ sdb_status sdb_order(sdb_mat* m) {
     if (m->slab_val) cudaFreeAsync(m->slab_val, ctx->stream);
     m->slab_rc = m->slab_val = nullptr;
     m->strict_sorted = 0;
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_invalidate(sdb_mat* m) {
+    SDB_REQUIRE(m != nullptr, SDB_STATUS_NOT_INITIALIZED, "invalidate: null handle");
+    SDB_REQUIRE(valid(m), SDB_STATUS_INVALID_VALUE, "invalidate: not a live sdb_mat handle");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    std::lock_guard<std::mutex> companion_lock(g_companion_mutex);
+    if (m->transposed) free_handle(m->transposed);
+    if (m->expanded) free_handle(m->expanded);
+    m->transposed = m->expanded = nullptr;
+    if (m->pos) cudaFreeAsync(m->pos, ctx->stream);
+    if (m->slab_rc) cudaFreeAsync(m->slab_rc, ctx->stream);
+    if (m->slab_val) cudaFreeAsync(m->slab_val, ctx->stream);
+    m->pos = nullptr;
+    m->slab_rc = m->slab_val = nullptr;
+    m->strict_sorted = 0;
+    m->spmm_calls = 0;
     SDB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SDB_STATUS_SUCCESS;
 }

@@ -40,6 +40,17 @@ sdb_status new_handle(sdb_mat** out, int format, int dtype, int64_t rows, int64_
 
 void free_handle(sdb_mat* m) {
     if (!m) return;
+    // release on the device the handle lives on, whatever device is current on this thread
+    int cur = -1;
+    const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != m->device && m->device >= 0 &&
+                          cudaSetDevice(m->device) == cudaSuccess;
+    struct Restore {
+        bool on;
+        int dev;
+        ~Restore() {
+            if (on) cudaSetDevice(dev);
+        }
+    } restore{switched, cur};
     if (m->transposed) free_handle(m->transposed);
     if (m->expanded) free_handle(m->expanded);
     if (m->owns) {
@@ -112,6 +123,9 @@ static sdb_status create_compressed(sdb_mat** out, int format, int64_t rows, int
     if (st == SDB_STATUS_SUCCESS) st = upload_index(ctx, indices, index_bits, nnz, nullptr, m->indices);
     if (st == SDB_STATUS_SUCCESS)
         st = h2d(ctx, m->values, values, size_t(nnz) * size_t(block * block) * dtype_size(dtype));
+    // never trust the host arrays: one device pass checks offsets and indices (and notes whether every
+    // line is strictly ascending, which the streaming SpMM and the triangular products want to know)
+    if (st == SDB_STATUS_SUCCESS && nnz > 0) st = validate_compressed(ctx, m);
     if (st == SDB_STATUS_SUCCESS) {
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) st = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);

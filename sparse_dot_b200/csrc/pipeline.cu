@@ -9,7 +9,16 @@
 //   download stream Y rows of chunk c as soon as its kernel has finished
 // With page-locked host buffers all three overlap (full-duplex PCIe); the time
 // is ~ upload bytes / link rate + one chunk's kernel + download.  Pageable
-// buffers take the plain create + sdb_spmm route (staged copies).
+// buffers (ordinary numpy arrays — what the reference's callers pass) run the
+// same pipeline through two rings of page-locked staging slots: the calling
+// thread copies each upload piece into a slot with the library's copy threads
+// (runtime.cu, host_copy) and DMAs it from there, and a helper thread DMAs the
+// finished Y rows into its own ring and copies them out, so host copies, both
+// DMA directions and the kernels all overlap.
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -50,6 +59,132 @@ int64_t index_at(const void* p, int bits, int64_t i) {
     return bits == 32 ? int64_t(static_cast<const int32_t*>(p)[i]) : static_cast<const int64_t*>(p)[i];
 }
 
+constexpr size_t kSlotBytes = size_t(16) << 20;
+
+// Host -> HBM on `s`: straight DMA from page-locked memory, else through the ring in slot-sized pieces
+// (the host copy of piece i + 1 overlaps the DMA of piece i).
+struct Uploader {
+    cudaStream_t s;
+    PinnedRing* ring;
+    sdb_status put(void* d_dst, const void* h_src, size_t bytes, bool pinned) {
+        if (bytes == 0) return SDB_STATUS_SUCCESS;
+        if (pinned) {
+            SDB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s));
+            return SDB_STATUS_SUCCESS;
+        }
+        for (size_t off = 0; off < bytes; off += ring->slot_bytes) {
+            const int k = ring->next;
+            ring->next = (k + 1) % PinnedRing::kSlots;
+            SDB_CUDA(cudaEventSynchronize(ring->free_ev[k]));
+            const size_t len = std::min(ring->slot_bytes, bytes - off);
+            host_copy(ring->slot[k], static_cast<const char*>(h_src) + off, len);
+            SDB_CUDA(cudaMemcpyAsync(static_cast<char*>(d_dst) + off, ring->slot[k], len, cudaMemcpyHostToDevice, s));
+            SDB_CUDA(cudaEventRecord(ring->free_ev[k], s));
+        }
+        return SDB_STATUS_SUCCESS;
+    }
+};
+
+// HBM -> pageable host memory on a helper thread: jobs (device range, host range, "kernel done" event)
+// are cut into slot-sized pieces; up to kSlots - 1 DMAs are in flight on `s` while the thread copies the
+// oldest finished slot out to the caller's array.
+class Downloader {
+  public:
+    struct Job {
+        cudaEvent_t ready;
+        const char* d_src;
+        char* h_dst;
+        size_t bytes;
+    };
+    Downloader(int device, cudaStream_t s, PinnedRing* ring) : device_(device), s_(s), ring_(ring) {}
+    ~Downloader() { finish(); }
+    void start() { th_ = std::thread([this] { run(); }); }
+    void push(const Job& j) {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            q_.push_back(j);
+        }
+        cv_.notify_one();
+    }
+    // no more jobs: wait until everything has been copied out; returns the thread's status
+    sdb_status finish() {
+        if (th_.joinable()) {
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                closed_ = true;
+            }
+            cv_.notify_one();
+            th_.join();
+        }
+        if (status_ != SDB_STATUS_SUCCESS) set_error("%s", err_);
+        return status_;
+    }
+
+  private:
+    struct Piece {
+        int slot;
+        char* h_dst;
+        size_t len;
+    };
+    void fail(cudaError_t e, const char* what) {
+        status_ = e == cudaErrorMemoryAllocation ? SDB_STATUS_ALLOC_FAILED : SDB_STATUS_EXECUTION_FAILED;
+        snprintf(err_, sizeof(err_), "CUDA error %d (%s) in the download thread: %s", int(e), cudaGetErrorString(e),
+                 what);
+    }
+    void run() {
+        cudaError_t e = cudaSetDevice(device_);
+        if (e != cudaSuccess) return fail(e, "cudaSetDevice");
+        std::deque<Piece> inflight;
+        Job cur{};
+        size_t cur_off = 0;
+        bool have = false;
+        while (true) {
+            // issue DMAs while slots are free and work is queued
+            while (int(inflight.size()) < PinnedRing::kSlots - 1) {
+                if (!have) {
+                    std::unique_lock<std::mutex> lk(m_);
+                    if (q_.empty()) {
+                        if (!inflight.empty()) break;  // something to copy out meanwhile
+                        cv_.wait(lk, [&] { return !q_.empty() || closed_; });
+                        if (q_.empty()) return;  // closed and drained
+                    }
+                    cur = q_.front();
+                    q_.pop_front();
+                    cur_off = 0;
+                    have = true;
+                    lk.unlock();
+                    if ((e = cudaStreamWaitEvent(s_, cur.ready, 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
+                }
+                const int k = ring_->next;
+                ring_->next = (k + 1) % PinnedRing::kSlots;
+                const size_t len = std::min(ring_->slot_bytes, cur.bytes - cur_off);
+                if ((e = cudaMemcpyAsync(ring_->slot[k], cur.d_src + cur_off, len, cudaMemcpyDeviceToHost, s_)) !=
+                    cudaSuccess)
+                    return fail(e, "cudaMemcpyAsync");
+                if ((e = cudaEventRecord(ring_->free_ev[k], s_)) != cudaSuccess) return fail(e, "cudaEventRecord");
+                inflight.push_back({k, cur.h_dst + cur_off, len});
+                cur_off += len;
+                if (cur_off >= cur.bytes) have = false;
+            }
+            if (inflight.empty()) continue;
+            const Piece p = inflight.front();
+            inflight.pop_front();
+            if ((e = cudaEventSynchronize(ring_->free_ev[p.slot])) != cudaSuccess) return fail(e, "cudaEventSynchronize");
+            host_copy(p.h_dst, ring_->slot[p.slot], p.len);
+        }
+    }
+    int device_;
+    cudaStream_t s_;
+    PinnedRing* ring_;
+    std::thread th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<Job> q_;
+    bool closed_ = false;
+    sdb_status status_ = SDB_STATUS_SUCCESS;
+    char err_[256] = "";
+};
+
 }  // namespace
 
 extern "C" sdb_status sdb_spmm_csr_host(int64_t rows, int64_t cols, const void* indptr, const void* indices,
@@ -67,11 +202,10 @@ extern "C" sdb_status sdb_spmm_csr_host(int64_t rows, int64_t cols, const void* 
                 "spmm_csr_host: indptr must start at 0");
     const bool beta_zero = beta[0] == 0.0 && beta[1] == 0.0;
     const bool packed = ldx == n && ldy == n;
-    const bool pipelined = index_bits == 32 && packed && nnz > 0 && rows > 0 && n > 0 && is_pinned(X) &&
-                           is_pinned(Y) && is_pinned(indices) && is_pinned(values) &&
+    const bool pipelined = index_bits == 32 && packed && nnz > 0 && rows > 0 && n > 0 &&
                            size_t(nnz) * (4 + es) + size_t(rows + cols) * size_t(n) * es > (size_t(32) << 20);
     if (!pipelined) {
-        // small or pageable operands: the plain triple
+        // small operands (or 64-bit host indices / padded panels): the plain triple
         sdb_mat* a = nullptr;
         SDB_TRY(sdb_create_csr(&a, rows, cols, indptr, indices, index_bits, values, dtype));
         sdb_status st = sdb_spmm(SDB_OP_NON_TRANSPOSE, alpha, a, SDB_LAYOUT_ROW_MAJOR, X, n, ldx, beta, Y, ldy);
@@ -91,6 +225,13 @@ extern "C" sdb_status sdb_spmm_csr_host(int64_t rows, int64_t cols, const void* 
     SDB_TRY(d_x.alloc(size_t(cols) * size_t(n) * es, s0));
     SDB_TRY(d_y.alloc(size_t(rows) * size_t(n) * es, s0));
     StreamJoin join{s_up, s_dn, s0};
+    // page-locked arrays are DMA'd in place, pageable ones go through the staging rings
+    const bool pin_x = is_pinned(X), pin_y = is_pinned(Y), pin_i = is_pinned(indices), pin_v = is_pinned(values);
+    if (!(pin_x && pin_y && pin_i && pin_v)) SDB_TRY(ensure_ring(&ctx->up_ring, kSlotBytes));
+    if (!pin_y) SDB_TRY(ensure_ring(&ctx->dn_ring, kSlotBytes));
+    Uploader up{s_up, &ctx->up_ring};
+    Downloader down(ctx->device, s_dn, &ctx->dn_ring);  // destroyed (joined) before the streams are drained
+    if (!pin_y) down.start();
     cudaEvent_t e_start, e_alloc, e_end, e_last_up;
     SDB_TRY(pool.get(&e_start, true));
     SDB_TRY(pool.get(&e_alloc));
@@ -105,7 +246,7 @@ extern "C" sdb_status sdb_spmm_csr_host(int64_t rows, int64_t cols, const void* 
     SDB_CUDA(cudaStreamWaitEvent(s_dn, e_alloc, 0));
 
     // X first: every chunk needs all of it
-    SDB_CUDA(cudaMemcpyAsync(d_x.p, X, size_t(cols) * size_t(n) * es, cudaMemcpyHostToDevice, s_up));
+    SDB_TRY(up.put(d_x.p, X, size_t(cols) * size_t(n) * es, pin_x));
 
     // row chunks of ~kChunkBytes of upload each
     constexpr size_t kChunkBytes = size_t(48) << 20;
@@ -128,16 +269,14 @@ extern "C" sdb_status sdb_spmm_csr_host(int64_t rows, int64_t cols, const void* 
         const int64_t r1 = lo;
         const int64_t p0 = hp[r0], p1 = hp[r1];
         if (p1 > p0) {
-            SDB_CUDA(cudaMemcpyAsync(d_idx.as<int32_t>() + p0, static_cast<const int32_t*>(indices) + p0,
-                                     size_t(p1 - p0) * 4, cudaMemcpyHostToDevice, s_up));
-            SDB_CUDA(cudaMemcpyAsync(static_cast<char*>(d_val.p) + size_t(p0) * es,
-                                     static_cast<const char*>(values) + size_t(p0) * es, size_t(p1 - p0) * es,
-                                     cudaMemcpyHostToDevice, s_up));
+            SDB_TRY(up.put(d_idx.as<int32_t>() + p0, static_cast<const int32_t*>(indices) + p0, size_t(p1 - p0) * 4,
+                           pin_i));
+            SDB_TRY(up.put(static_cast<char*>(d_val.p) + size_t(p0) * es,
+                           static_cast<const char*>(values) + size_t(p0) * es, size_t(p1 - p0) * es, pin_v));
         }
         const size_t y_off = size_t(r0) * size_t(n) * es, y_len = size_t(r1 - r0) * size_t(n) * es;
         if (!beta_zero)
-            SDB_CUDA(cudaMemcpyAsync(static_cast<char*>(d_y.p) + y_off, static_cast<const char*>(Y) + y_off, y_len,
-                                     cudaMemcpyHostToDevice, s_up));
+            SDB_TRY(up.put(static_cast<char*>(d_y.p) + y_off, static_cast<const char*>(Y) + y_off, y_len, pin_y));
         cudaEvent_t e_up, e_k0, e_k1;
         SDB_TRY(pool.get(&e_up));
         SDB_TRY(pool.get(&e_k0, true));
@@ -156,12 +295,17 @@ extern "C" sdb_status sdb_spmm_csr_host(int64_t rows, int64_t cols, const void* 
         SDB_TRY(spmm_device(ctx, s0, v, dtype, false, alpha, beta, SDB_LAYOUT_ROW_MAJOR, d_x.p, n, n, yp, 1, 0, 0, n));
         SDB_CUDA(cudaEventRecord(e_k1, s0));
         kernel_events.emplace_back(e_k0, e_k1);
-        SDB_CUDA(cudaStreamWaitEvent(s_dn, e_k1, 0));
-        SDB_CUDA(cudaMemcpyAsync(static_cast<char*>(Y) + y_off, static_cast<char*>(d_y.p) + y_off, y_len,
-                                 cudaMemcpyDeviceToHost, s_dn));
+        if (pin_y) {
+            SDB_CUDA(cudaStreamWaitEvent(s_dn, e_k1, 0));
+            SDB_CUDA(cudaMemcpyAsync(static_cast<char*>(Y) + y_off, static_cast<char*>(d_y.p) + y_off, y_len,
+                                     cudaMemcpyDeviceToHost, s_dn));
+        } else if (y_len > 0) {
+            down.push({e_k1, static_cast<const char*>(d_y.p) + y_off, static_cast<char*>(Y) + y_off, y_len});
+        }
         r0 = r1;
     }
     SDB_CUDA(cudaEventRecord(e_last_up, s_up));
+    SDB_TRY(down.finish());  // pageable Y: every row has been copied out to the caller's array
     // join: frees below are ordered on s0 after everything else
     cudaEvent_t e_dn;
     SDB_TRY(pool.get(&e_dn));

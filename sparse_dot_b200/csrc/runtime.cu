@@ -1,7 +1,9 @@
 // runtime.cu — host runtime of libsdb200: error plumbing, per-thread context,
 // stream-ordered memory, pinned staging copies, phase timers and the small
 // host-only ABI entry points (version string, device selection, row partitioner).
+#include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdlib>
 #include <mutex>
@@ -94,6 +96,19 @@ static sdb_status ensure_staging(Context* c) {
     return SDB_STATUS_SUCCESS;
 }
 
+sdb_status ensure_ring(PinnedRing* ring, size_t slot_bytes) {
+    if (ring->slot[0] && ring->slot_bytes >= slot_bytes) return SDB_STATUS_SUCCESS;
+    for (int i = 0; i < PinnedRing::kSlots; ++i) {
+        if (ring->slot[i]) cudaFreeHost(ring->slot[i]);
+        ring->slot[i] = nullptr;
+        SDB_CUDA(cudaHostAlloc(&ring->slot[i], slot_bytes, cudaHostAllocDefault));
+        if (!ring->free_ev[i]) SDB_CUDA(cudaEventCreateWithFlags(&ring->free_ev[i], cudaEventDisableTiming));
+    }
+    ring->slot_bytes = slot_bytes;
+    ring->next = 0;
+    return SDB_STATUS_SUCCESS;
+}
+
 sdb_status dev_alloc(void** p, size_t bytes, cudaStream_t s) {
     *p = nullptr;
     cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, s);
@@ -117,27 +132,118 @@ bool is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-// memcpy split over a few host threads: one core moves ~10 GB/s, PCIe 5 wants ~55.
-static void fast_memcpy(void* dst, const void* src, size_t bytes) {
-    constexpr size_t kMin = size_t(4) << 20;
-    unsigned hw = std::thread::hardware_concurrency();
-    int nt = int(bytes / kMin);
-    if (nt > 8) nt = 8;
-    if (hw && nt > int(hw)) nt = int(hw);
-    if (nt <= 1) {
-        memcpy(dst, src, bytes);
-        return;
+// ---------------------------------------------------------------- host copy pool
+// Pageable host memory cannot be DMA'd; it is staged through page-locked ring buffers, and one core
+// moves only ~10 GB/s where PCIe 5 wants ~55.  A small persistent pool of worker threads (created on
+// first use, SDB_COPY_THREADS overrides the count) splits every large copy; the calling thread
+// takes pieces too.  Several threads may submit copies at the same time (the upload and download
+// sides of sdb_spmm_csr_host do).
+namespace {
+
+class CopyPool {
+  public:
+    static CopyPool& get() {
+        static CopyPool* pool = new CopyPool();  // never destroyed: workers may outlive static destruction
+        return *pool;
     }
-    std::vector<std::thread> th;
-    size_t per = (bytes / nt + 63) & ~size_t(63);
-    for (int t = 0; t < nt; ++t) {
-        size_t off = size_t(t) * per;
-        if (off >= bytes) break;
-        size_t len = bytes - off < per ? bytes - off : per;
-        th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    void copy(void* dst, const void* src, size_t bytes) {
+        constexpr size_t kPiece = size_t(2) << 20;
+        if (bytes < 2 * kPiece || workers_ == 0) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        Job job;
+        job.dst = static_cast<char*>(dst);
+        job.src = static_cast<const char*>(src);
+        job.bytes = bytes;
+        // about two pieces per thread, multiples of 4 KiB
+        size_t piece = bytes / (size_t(workers_ + 1) * 2);
+        piece = std::max(kPiece, (piece + 4095) & ~size_t(4095));
+        job.piece = piece;
+        job.n_pieces = (bytes + piece - 1) / piece;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            jobs_.push_back(&job);
+        }
+        cv_.notify_all();
+        run_pieces(&job);  // the submitter works too
+        std::unique_lock<std::mutex> lk(m_);
+        job.done_cv.wait(lk, [&] { return job.finished == job.n_pieces; });
     }
-    for (auto& x : th) x.join();
-}
+
+  private:
+    struct Job {
+        char* dst;
+        const char* src;
+        size_t bytes, piece, n_pieces;
+        size_t next = 0;      // guarded by m_
+        size_t finished = 0;  // guarded by m_
+        std::condition_variable done_cv;
+    };
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = hw > 1 ? int(hw) - 1 : 0;
+        if (n > 15) n = 15;
+        if (const char* e = getenv("SDB_COPY_THREADS")) n = std::max(0, std::min(63, atoi(e) - 1));
+        workers_ = n;
+        for (int i = 0; i < n; ++i) std::thread([this] { worker(); }).detach();
+    }
+    // Hand out the next piece of `job` (m_ held).  A job leaves the queue when its last piece is handed
+    // out, so nobody can pick it up afterwards; it may be destroyed by its submitter as soon as the last
+    // `finished` increment has been published.
+    size_t claim(Job* job) {
+        const size_t idx = job->next++;
+        if (job->next == job->n_pieces) {
+            for (size_t i = 0; i < jobs_.size(); ++i)
+                if (jobs_[i] == job) {
+                    jobs_.erase(jobs_.begin() + long(i));
+                    break;
+                }
+        }
+        return idx;
+    }
+    void copy_piece(Job* job, size_t idx) {
+        const size_t off = idx * job->piece;
+        memcpy(job->dst + off, job->src + off, std::min(job->piece, job->bytes - off));
+        std::lock_guard<std::mutex> lk(m_);
+        if (++job->finished == job->n_pieces) job->done_cv.notify_all();  // `job` must not be touched after this
+    }
+    // the submitter's share: pieces of its own job only (the job is alive: it lives on this thread's stack)
+    void run_pieces(Job* job) {
+        while (true) {
+            size_t idx;
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (job->next >= job->n_pieces) return;
+                idx = claim(job);
+            }
+            copy_piece(job, idx);
+        }
+    }
+    void worker() {
+        while (true) {
+            Job* job;
+            size_t idx;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return !jobs_.empty(); });
+                job = jobs_.front();  // still has at least one piece, or it would have left the queue
+                idx = claim(job);
+            }
+            copy_piece(job, idx);
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::vector<Job*> jobs_;
+    int workers_ = 0;
+};
+
+}  // namespace
+
+void host_copy(void* dst, const void* src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
+
+static void fast_memcpy(void* dst, const void* src, size_t bytes) { host_copy(dst, src, bytes); }
 
 sdb_status h2d(Context* ctx, void* d_dst, const void* h_src, size_t bytes) {
     if (bytes == 0) return SDB_STATUS_SUCCESS;

@@ -418,15 +418,19 @@ sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, int layou
 // copy-engine exchange, "stores" = the kernel's epilogue stores every finished 16-byte slice into every peer panel
 // itself, "k1" = the same with the row-gather kernel K1 even where the streaming kernel would qualify.
 enum { kXchgAuto = 0, kXchgCopyEngines = 1, kXchgStores = 2, kXchgStoresRowGather = 3 };
+// process-wide; sdb_set_allgather overrides the environment (RowShardedSpMM.autotune measures the strategies on
+// the live topology during warm-up and keeps the fastest)
+static std::atomic<int> g_xchg_strategy{-1};
+static std::atomic<int> g_xchg_chunks{0};  // target number of row chunks of the "ce" pipeline (0 = about five)
 static int allgather_strategy() {
-    static const int v = [] {
-        const char* e = getenv("SDB_ALLGATHER");
-        if (!e) return int(kXchgAuto);
-        if (e[0] == 'c') return int(kXchgCopyEngines);   // "ce"
-        if (e[0] == 's') return int(kXchgStores);        // "stores"
-        if (e[0] == 'k') return int(kXchgStoresRowGather);  // "k1": epilogue stores, row-gather kernel K1
-        return int(kXchgAuto);
-    }();
+    int v = g_xchg_strategy.load(std::memory_order_relaxed);
+    if (v >= 0) return v;
+    const char* e = getenv("SDB_ALLGATHER");
+    v = kXchgAuto;
+    if (e && e[0] == 'c') v = kXchgCopyEngines;      // "ce"
+    if (e && e[0] == 's') v = kXchgStores;           // "stores"
+    if (e && e[0] == 'k') v = kXchgStoresRowGather;  // "k1": epilogue stores, row-gather kernel K1
+    g_xchg_strategy.store(v, std::memory_order_relaxed);
     return v;
 }
 
@@ -482,11 +486,14 @@ sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A, const v
     const size_t pitch = size_t(ldy) * dtype_size(A->dtype);
     // chunking: whole waves of the streaming kernel when it will run, else quarters of the shard
     int64_t chunk = spmm_slab_wave_rows(ctx, v, A->dtype, n, ldx, /*count_call=*/true);
+    const int want_chunks = g_xchg_chunks.load(std::memory_order_relaxed);
     if (chunk > 0) {
         const int64_t waves = (v.rows + chunk - 1) / chunk;
-        chunk *= std::max<int64_t>(1, (waves + 2) / 5);  // about five chunks per step
+        const int64_t target = want_chunks > 0 ? want_chunks : 5;  // about five chunks per step by default
+        chunk *= std::max<int64_t>(1, (waves + target / 2) / target);
     } else {
-        chunk = ((v.rows + 3) / 4 + 63) / 64 * 64;
+        const int64_t target = want_chunks > 0 ? want_chunks : 4;
+        chunk = ((v.rows + target - 1) / target + 63) / 64 * 64;
     }
     if (size_t(v.rows) * row_bytes < (size_t(16) << 20)) chunk = v.rows;  // too small to be worth pipelining
     void* local[1] = {dY_peers[self]};
@@ -521,6 +528,14 @@ sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A, const v
         SDB_CUDA(cudaEventRecord(ctx->xchg_done[q], ctx->xchg_stream[q]));
         SDB_CUDA(cudaStreamWaitEvent(s, ctx->xchg_done[q], 0));
     }
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_set_allgather(int strategy, int chunks) {
+    SDB_REQUIRE(strategy >= kXchgAuto && strategy <= kXchgStoresRowGather && chunks >= 0 && chunks <= 64,
+                SDB_STATUS_INVALID_VALUE, "sdb_set_allgather: strategy 0..3, chunks 0..64");
+    g_xchg_strategy.store(strategy, std::memory_order_relaxed);
+    g_xchg_chunks.store(chunks, std::memory_order_relaxed);
     return SDB_STATUS_SUCCESS;
 }
 

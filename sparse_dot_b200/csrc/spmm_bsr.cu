@@ -203,6 +203,7 @@ static sdb_status launch_bsr_s(cudaStream_t s, const sdb_mat* a, const T* X, int
     const int64_t gy = (n + CW - 1) / CW;
     SDB_REQUIRE(a->rows < (int64_t(1) << 31) && gy < 65536, SDB_STATUS_NOT_SUPPORTED, "spmm_bsr: grid too large");
     const dim3 grid(unsigned(a->rows), unsigned(gy));
+    note_spmm_kernel("spmm_bsr_kernel<%s,%d,%d,%d>", dtype_cname(Num<T>::dtype), B, CW, kBsrStages);
     if (a->block_layout == SDB_LAYOUT_COL_MAJOR) {
         SDB_CUDA(cudaFuncSetAttribute(spmm_bsr_kernel<T, B, CW, true, kBsrStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem)));

@@ -370,10 +370,11 @@ static bool slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx, boo
     if (a.owner->strict_sorted == -1) return false;
     if (mode == 2) return true;
     const int uses = count_call ? a.owner->spmm_calls++ : a.owner->spmm_calls - 1;
-    const int64_t in_flight = std::min<int64_t>(a.rows, int64_t(148) * slab_rows_per_sm());
-    const double reuse = double(in_flight) * (double(a.nnz) / double(a.rows)) / double(a.cols);
-    return uses >= 1 && size_t(a.cols) * size_t(n) * sv >= (size_t(192) << 20) && a.rows >= int64_t(148) * slab_rows_per_sm() &&
-           reuse >= 1.5;
+    Context* ctx = nullptr;
+    const int sms = get_context(&ctx) == SDB_STATUS_SUCCESS ? ctx->sm_count : 148;
+    const int64_t wave = int64_t(sms) * slab_rows_per_sm();  // rows one wave of the persistent grid holds
+    const double reuse = double(std::min<int64_t>(a.rows, wave)) * (double(a.nnz) / double(a.rows)) / double(a.cols);
+    return uses >= 1 && size_t(a.cols) * size_t(n) * sv >= (size_t(192) << 20) && a.rows >= wave && reuse >= 1.5;
 }
 
 sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a,
@@ -382,6 +383,7 @@ sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int 
     (void)conj_a;  // real dtypes only
     sdb_mat* m = a.owner;
     SDB_REQUIRE(m != nullptr, SDB_STATUS_NOT_SUPPORTED, "spmm_slab: ad-hoc view");
+    std::unique_lock<std::mutex> cache_lock(g_companion_mutex);  // the inspector's output is a per-handle cache
     if (m->strict_sorted == 0) {
         // the check runs on the library stream; the caller's stream must not race with it
         SDB_TRY(ensure_strict_flag(ctx, m));
@@ -413,6 +415,7 @@ sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int 
         m->slab_rpw = rpw;
         if (s != ls) SDB_CUDA(cudaStreamSynchronize(ls));
     }
+    cache_lock.unlock();
     const int col_chunks = int(size_t(n) * sv / 512);
     if (dtype == SDB_F32)
         return launch_variant<float>(s, a, m, static_cast<const float*>(dX), ldx, float(alpha[0]), float(beta[0]),

@@ -201,6 +201,53 @@ class RowShardedSpMM:
             local = self._torch_panel[self.row0:self.row0 + self.rows_local]
             dist.all_gather_into_tensor(self._torch_panel, local, group=self.group)
 
+    # ------------------------------------------------------------------ exchange strategy
+    STRATEGIES = {"auto": 0, "ce": 1, "stores": 2, "k1": 3}
+
+    @staticmethod
+    def set_exchange(strategy="auto", chunks=0):
+        """Process-wide exchange strategy of the fused mode (sdb_set_allgather): 'auto', 'ce' (copy engines push
+        row chunks while the next chunk's kernel runs; ``chunks`` = how many), 'stores' (the kernel's epilogue
+        stores into the peer panels), 'k1' (the same with the row-gather kernel)."""
+        check(SDB.lib.sdb_set_allgather(RowShardedSpMM.STRATEGIES[strategy], int(chunks)), "sdb_set_allgather")
+
+    def autotune(self, beta=0.0, stream=None, candidates=None, reps=3):
+        """Time the exchange strategies on the live topology (device time, max over ranks) and keep the fastest.
+        Which one wins depends on the rank count, the panel width and how the kernel's time compares with
+        the NVLink time of the step, so it is measured instead of guessed.  Every candidate computes the same
+        product, so the steps count as ordinary steps (``steps_run`` of them are executed).  Collective: every
+        rank must call it."""
+        import torch
+        import torch.distributed as dist
+
+        if self.mode != "fused" or self.world == 1:
+            return {"chosen": None, "steps_run": 0}
+        if candidates is None:
+            candidates = [("ce", 5), ("ce", 10), ("ce", 20), ("stores", 0), ("k1", 0)]
+        stream = stream or torch.cuda.current_stream()
+        timings, steps_run = [], 0
+        for strategy, chunks in candidates:
+            self.set_exchange(strategy, chunks)
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                self.run(alpha=1.0, beta=beta, stream_ptr=stream.cuda_stream)  # untimed: first use of this path
+                e0.record(stream)
+                for _ in range(reps):
+                    self.run(alpha=1.0, beta=beta, stream_ptr=stream.cuda_stream)
+                e1.record(stream)
+            torch.cuda.synchronize()
+            steps_run += reps + 1
+            t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            timings.append({"strategy": strategy, "chunks": chunks, "ms_per_step": float(t.item()),
+                            "kernel": _lib.last_spmm_kernel()})
+        best = min(timings, key=lambda r: r["ms_per_step"])  # identical on every rank (all-reduced times)
+        self.set_exchange(best["strategy"], best["chunks"])
+        dist.barrier(group=self.group)
+        return {"chosen": best, "candidates": timings, "steps_run": steps_run}
+
     def synchronize(self):
         check(SDB.lib.sdb_device_synchronize(), "sdb_device_synchronize")
         if self.world > 1:

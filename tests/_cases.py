@@ -58,6 +58,15 @@ def uniform_rows_csr(m, k, per_row, dtype, seed):
     return a
 
 
+def c2_workload(rows, cols, per_row, n_dense, seed, dtype=np.float32):
+    """The BASELINE configs[1] / configs[4] SpMM workload: A = uniform_rows_csr, X and Y0 uniform
+    random panels.  The ONE generator of this recipe: bench.py, scripts/run_configs.py and the tests use it."""
+    a = uniform_rows_csr(rows, cols, per_row, dtype, seed)
+    x = np.random.default_rng(seed + 2).random((cols, n_dense), dtype=np.float32).astype(dtype, copy=False)
+    y = np.random.default_rng(seed + 3).random((rows, n_dense), dtype=np.float32).astype(dtype, copy=False)
+    return a, x, y
+
+
 def rmat_csr(scale, edge_factor, dtype, seed, abcd=(0.57, 0.19, 0.19, 0.05)):
     """Graph500 R-MAT (BASELINE C3 recipe): duplicates summed, values U[0.5,1.5)."""
     rng = np.random.default_rng(seed)

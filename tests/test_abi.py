@@ -86,3 +86,24 @@ def test_compute_fails_loudly_without_gpu():
         sdb.dot_product_mkl(a, b)
     with pytest.raises(ValueError):
         sdb.gram_matrix_mkl(a)
+
+
+def test_allgather_switch_validates_its_arguments():
+    """sdb_set_allgather is host-only state: usable (and checked) without a GPU."""
+    lib = _lib.SDB.lib
+    assert lib.sdb_set_allgather(1, 10) == 0
+    assert lib.sdb_set_allgather(0, 0) == 0
+    assert lib.sdb_set_allgather(9, 0) == 3 and lib.sdb_set_allgather(1, -1) == 3
+
+
+def test_bench_helpers():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.mangled_hint("spmm_stream_kernel<float,6,32,2,2>") == "18spmm_stream_kernelIfLi6ELi32ELi2ELi2EE"
+    sha = bench.sass_sha("spmm_stream_kernel")
+    assert sha is None or len(sha) == 40
+    # gather-model bytes of BASELINE configs[1] (SURVEY.md section 8d): 27.03 GB with beta != 0
+    assert abs(bench.algorithmic_bytes(1_000_000, 50_000_000, 128) - 27.032e9) < 1e7

@@ -1,0 +1,130 @@
+"""Round-2 additions, through the C-ABI on the GPU: the pageable-memory host pipeline, create-time
+validation, cache invalidation for borrowed arrays, the bandwidth probes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import sparse_dot_b200 as sdb
+from oracle import oracle as orc
+from sparse_dot_b200 import _handles as H
+from sparse_dot_b200 import _lib
+from tests import _cases as cs
+
+pytestmark = pytest.mark.gpu
+lib = _lib.SDB.lib
+
+
+def _pinned_like(arr):
+    p = C.c_void_p()
+    _lib.check(lib.sdb_host_alloc(C.byref(p), arr.nbytes), "sdb_host_alloc")
+    buf = (C.c_char * arr.nbytes).from_address(p.value)
+    out = np.frombuffer(buf, dtype=arr.dtype).reshape(arr.shape)
+    out[...] = arr
+    return out, p
+
+
+# ===================================================== sdb_spmm_csr_host on ordinary (pageable) numpy arrays
+@pytest.mark.parametrize("beta", [0.0, 0.5])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pageable_pipeline_matches_oracle(dtype, beta):
+    """Large enough (> 32 MiB of operands) to take the row-chunk pipeline; every array is pageable, so uploads go
+    through the staging ring and the result comes back through the download thread (_sparse_dense.py:34-132)."""
+    a, x, y0 = cs.c2_workload(70_000, 60_000, 40, 128, seed=3, dtype=dtype)
+    if beta == 0.0:
+        got = sdb.dot_product_mkl(a, x)
+        want = orc.c_spmm(a, x)
+    else:
+        got = sdb.dot_product_mkl(a, x, out=y0.copy(), out_scalar=beta)
+        want = orc.c_spmm(a, x, beta=beta, y=y0.copy())
+    assert cs.rel_err(got, want) <= cs.TOL[np.dtype(dtype)]
+    t = sdb.last_timing_ms()
+    assert t[2] > 0.0  # the pipelined call reports its spans
+
+
+def test_mixed_pinned_and_pageable_operands():
+    """X page-locked, A and Y pageable: each array takes its own route inside one call."""
+    a, x, y0 = cs.c2_workload(70_000, 60_000, 40, 128, seed=4)
+    xp, handle = _pinned_like(x)
+    try:
+        got = sdb.dot_product_mkl(a, xp, out=y0.copy(), out_scalar=2.0)
+        want = orc.c_spmm(a, x, beta=2.0, y=y0.copy())
+        assert cs.rel_err(got, want) <= 1e-5
+    finally:
+        lib.sdb_host_free(handle)
+
+
+def test_pageable_pipeline_repeated_calls_reuse_the_rings():
+    a, x, y0 = cs.c2_workload(70_000, 60_000, 40, 128, seed=5)
+    y = y0.copy()
+    for _ in range(3):
+        sdb.dot_product_mkl(a, x, out=y, out_scalar=0.5)
+    want = y0.copy()
+    for _ in range(3):
+        want = orc.c_spmm(a, x, beta=0.5, y=want)
+    assert cs.rel_err(y, want) <= 1e-5
+
+
+# ===================================================== create never trusts the host arrays
+def test_malformed_matrix_is_a_value_error_not_a_crash():
+    m1, _ = cs.fixture_pair(np.float64)
+    bad = m1.copy()
+    bad.indices[7] = bad.shape[1] + 5  # column out of range
+    with pytest.raises(ValueError, match="sdb_create_csr returned 3"):
+        H.create(bad)
+    bad = m1.copy()
+    bad.indices[3] = -1
+    with pytest.raises(ValueError, match="sdb_create_csr returned 3"):
+        H.create(bad)
+    bad = m1.copy()
+    bad.indptr[5], bad.indptr[6] = bad.indptr[6] + 3, bad.indptr[5]  # offsets decrease
+    with pytest.raises(ValueError, match="sdb_create_csr returned 3"):
+        H.create(bad)
+    # the context is still healthy afterwards
+    x = np.random.default_rng(0).random((m1.shape[1], 8))
+    assert cs.rel_err(sdb.dot_product_mkl(m1, x), orc.c_spmm(m1, x), orc.value_bound(abs(m1), abs(x))) <= 1e-12
+
+
+# ===================================================== borrowed device arrays + sdb_invalidate
+def test_invalidate_drops_cached_copies_of_borrowed_arrays():
+    import torch
+
+    m1, _ = cs.fixture_pair(np.float32)
+    ip = torch.from_numpy(m1.indptr.astype(np.int64)).cuda()
+    ix = torch.from_numpy(m1.indices.astype(np.int32)).cuda()
+    va = torch.from_numpy(m1.data).cuda()
+    ref = C.c_void_p()
+    _lib.check(lib.sdb_create_csr_dev(C.byref(ref), m1.shape[0], m1.shape[1], m1.nnz, C.c_void_p(ip.data_ptr()),
+                                      C.c_void_p(ix.data_ptr()), C.c_void_p(va.data_ptr()), _lib.F32),
+               "sdb_create_csr_dev")
+    h = H.Handle(ref, np.float32)
+    x = np.random.default_rng(1).random((m1.shape[0], 16), dtype=np.float32)
+    xt = torch.from_numpy(x).cuda()
+    yt = torch.empty((m1.shape[1], 16), dtype=torch.float32, device="cuda")
+    one, zero = _lib.scalar_pair(1.0), _lib.scalar_pair(0.0)
+
+    def at_times_x():
+        _lib.check(lib.sdb_spmm_dev(_lib.OP_T, one, h.ref, _lib.LAYOUT_C, C.c_void_p(xt.data_ptr()), 16, 16, zero,
+                                    C.c_void_p(yt.data_ptr()), 16, None), "sdb_spmm_dev")
+        _lib.check(lib.sdb_device_synchronize(), "sync")
+        return yt.cpu().numpy()
+
+    with h:
+        want = orc.c_spmm(m1.T.tocsr(), x)
+        assert cs.rel_err(at_times_x(), want, orc.value_bound(abs(m1.T.tocsr()), abs(x))) <= 1e-5
+        va.mul_(2.0)  # the owner rewrites the values in place: the cached transposed copy is now stale
+        torch.cuda.synchronize()
+        _lib.check(lib.sdb_invalidate(h.ref), "sdb_invalidate")
+        assert cs.rel_err(at_times_x(), 2.0 * want, 2.0 * orc.value_bound(abs(m1.T.tocsr()), abs(x))) <= 1e-5
+
+
+# ===================================================== bandwidth probes (bench.py's roofline denominators)
+def test_bandwidth_probes_are_sane():
+    hbm = _lib.probe_bandwidth(0, 1 << 30, 2)
+    l2 = _lib.probe_bandwidth(1, 32 << 20, 2)
+    gather = _lib.probe_bandwidth(2, 32 << 20, 2)
+    assert 1000.0 < hbm < 9000.0, hbm
+    assert l2 > hbm and gather > hbm, (hbm, l2, gather)
+    with pytest.raises(ValueError):
+        _lib.probe_bandwidth(7, 1 << 30, 1)
