@@ -284,11 +284,20 @@ SDB_API sdb_status sdb_get_device(int* device);
 SDB_API sdb_status sdb_version_string(char* buf, int len);
 SDB_API int        sdb_last_error(char* buf, int len);
 
+/* Run-time switches (process-wide), each also readable from the environment at first use:
+ *   "bsr_mma"       SDB_BSR_MMA        BSR x dense on the tensor cores (DMMA fp64, 3xTF32 fp32): -1 automatic, 0 off, 1 on
+ *   "spgemm_wide"   SDB_SPGEMM_WIDE    wide SpGEMM rows: 0 automatic, 1 full-sweep bitmap, 2 bitmap with summary
+ *   "dense_mode"    SDB_DENSE_MODE     dense-output products: 0 automatic, 1 shared-memory tiles, 2 global reductions
+ *   "dense_threads" SDB_DENSE_THREADS  threads per CTA of the global-reduction kernel (0 = default)
+ * Unknown names return SDB_STATUS_INVALID_VALUE.  No reference counterpart (tuning aid for tests and sweeps). */
+SDB_API sdb_status sdb_set_option(const char* name, int value);
+
 /* Bandwidth probes measured on the device the numbers are quoted on (bench.py's roofline
  * denominators): kind 0 = HBM read (sequential 16-byte loads over `bytes`, pick a size much larger than
  * L2), 1 = L2 -> SM read (same loop over an L2-resident `bytes`, L1 bypassed), 2 = L2 -> SM gather of
  * whole 512-byte rows at random positions of an L2-resident buffer (the access shape of the SpMM
- * gathers).  Result in GB/s (1e9 bytes per second), timed with CUDA events over `iters` launches after
+ * gathers), 3 = the host side of the pageable-memory pipeline: pageable -> page-locked copies in 16 MiB
+ * slots by the library's copy threads (no GPU involved).  Result in GB/s (1e9 bytes per second), timed with CUDA events over `iters` launches after
  * one warm-up launch.  No reference counterpart. */
 SDB_API sdb_status sdb_probe_bandwidth(int kind, int64_t bytes, int iters, double* gbs);
 

@@ -16,6 +16,7 @@
 #   configs=<run_configs.py args>    scripts/run_configs.py ...
 #   hashes                           SASS hashes of the profiled kernels (ties ncu bytes to this build)
 #   py=<script and args>             python <script and args>
+#   envpy=<label>,<VAR=VAL ..>,<script and args>   the same with environment variables set
 #   smoke                            __graft_entry__.smoke()
 set -u
 cd "$(dirname "$0")/.."
@@ -63,6 +64,9 @@ for step in "$@"; do
     py)
       timeout 1500 python $arg > $OUT/${TAG}_py_$(echo "$arg" | tr -c 'A-Za-z0-9' '_' | cut -c1-40).log 2>&1
       tail -40 $OUT/${TAG}_py_$(echo "$arg" | tr -c 'A-Za-z0-9' '_' | cut -c1-40).log ;;
+    envpy)   # envpy=<label>,<VAR=VAL[ VAR=VAL..]>,<script and args>
+      IFS=, read -r label envs cmd <<< "$arg"
+      env $envs timeout 1500 python $cmd > $OUT/${TAG}_envpy_$label.log 2>&1; tail -25 $OUT/${TAG}_envpy_$label.log | cut -c1-1500 ;;
     smoke)
       timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; tail -8 $OUT/${TAG}_smoke.log ;;
     *) echo "unknown step $step" ;;

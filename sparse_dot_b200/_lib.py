@@ -76,6 +76,7 @@ PROTOTYPES = {
     "sdb_get_device": (_i32, [_ct.POINTER(_i32)]),
     "sdb_version_string": (_i32, [_ct.c_char_p, _i32]),
     "sdb_last_error": (_i32, [_ct.c_char_p, _i32]),
+    "sdb_set_option": (_i32, [_ct.c_char_p, _i32]),
     "sdb_probe_bandwidth": (_i32, [_i32, _i64, _i32, _pd]),
     "sdb_kernel_launches": (_i64, []),
     "sdb_last_spmm_kernel": (_i32, [_ct.c_char_p, _i32]),
@@ -163,6 +164,11 @@ def last_spmm_kernel():
     buf = _ct.create_string_buffer(160)
     check(SDB.lib.sdb_last_spmm_kernel(buf, 160), "sdb_last_spmm_kernel")
     return buf.value.decode()
+
+
+def set_option(name, value):
+    """Run-time switch of the library (sdb200.h, sdb_set_option): 'bsr_mma', 'spgemm_wide', 'dense_mode', ..."""
+    check(SDB.lib.sdb_set_option(name.encode(), int(value)), "sdb_set_option")
 
 
 def probe_bandwidth(kind, nbytes, iters=5):

@@ -57,6 +57,18 @@ void trace(cudaStream_t s, const char* fmt, ...) __attribute__((format(printf, 2
 void note_spmm_kernel(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
 extern thread_local char t_spmm_kernel[128];
 
+// ---------------------------------------------------------------- run-time options
+// Small integer switches, each initialised from an environment variable on first use and settable at run time
+// through sdb_set_option (tests and sweeps flip them inside one process).  -1 / 0 mean "automatic".
+enum Option {
+    kOptBsrMma = 0,     // "bsr_mma"       SDB_BSR_MMA        BSR x dense on tensor cores: -1 auto, 0 off, 1 on
+    kOptSpgemmWide,     // "spgemm_wide"   SDB_SPGEMM_WIDE    wide SpGEMM rows: 0 auto, 1 full-sweep bitmap, 2 summary
+    kOptDenseMode,      // "dense_mode"    SDB_DENSE_MODE     dense-output products: 0 auto, 1 shared tiles, 2 global reductions
+    kOptDenseThreads,   // "dense_threads" SDB_DENSE_THREADS  threads per CTA of the global-reduction kernel (0 = 1024)
+    kOptCount
+};
+int get_option(Option o);
+
 // ---------------------------------------------------------------- dtypes
 inline const char* dtype_cname(int dtype) {
     static const char* const names[4] = {"float", "double", "complex<float>", "complex<double>"};
@@ -272,6 +284,10 @@ sdb_status validate_compressed(Context* ctx, sdb_mat* m);
 // Native BSR x dense kernel (spmm_bsr.cu): availability test + launch.
 bool spmm_bsr_supported(const sdb_mat* a, int op, int layout, const void* dX, int64_t n, int64_t ldx, const void* dY,
                         int64_t ldy);
+// tensor-core variant (spmm_bsr_mma.cu): block sizes 8 / 16 / 32, n a multiple of 8
+bool spmm_bsr_mma_supported(const sdb_mat* a, int64_t n);
+sdb_status spmm_bsr_mma_device(cudaStream_t s, const sdb_mat* a, const double* alpha, const double* beta,
+                               const void* dX, int64_t n, int64_t ldx, void* dY, int64_t ldy, int stages);
 sdb_status spmm_bsr_device(cudaStream_t s, const sdb_mat* a, const double* alpha, const double* beta, const void* dX,
                            int64_t n, int64_t ldx, void* dY, int64_t ldy);
 }  // namespace sdb

@@ -16,6 +16,7 @@
 // finished Y rows into its own ring and copies them out, so host copies, both
 // DMA directions and the kernels all overlap.
 #include <condition_variable>
+#include <cstdlib>
 #include <deque>
 #include <mutex>
 #include <thread>
@@ -59,7 +60,16 @@ int64_t index_at(const void* p, int bits, int64_t i) {
     return bits == 32 ? int64_t(static_cast<const int32_t*>(p)[i]) : static_cast<const int64_t*>(p)[i];
 }
 
-constexpr size_t kSlotBytes = size_t(16) << 20;
+// staging slot size (SDB_STAGE_SLOT_MB, default 16 MiB): large enough to amortise the hand-off to the copy
+// threads, small enough that eight of them pipeline well behind a 48 MiB row chunk
+size_t slot_bytes() {
+    static const size_t v = [] {
+        const char* e = getenv("SDB_STAGE_SLOT_MB");
+        const int mb = e ? atoi(e) : 16;
+        return size_t(mb >= 1 && mb <= 256 ? mb : 16) << 20;
+    }();
+    return v;
+}
 
 // Host -> HBM on `s`: straight DMA from page-locked memory, else through the ring in slot-sized pieces
 // (the host copy of piece i + 1 overlaps the DMA of piece i).
@@ -227,8 +237,8 @@ extern "C" sdb_status sdb_spmm_csr_host(int64_t rows, int64_t cols, const void* 
     StreamJoin join{s_up, s_dn, s0};
     // page-locked arrays are DMA'd in place, pageable ones go through the staging rings
     const bool pin_x = is_pinned(X), pin_y = is_pinned(Y), pin_i = is_pinned(indices), pin_v = is_pinned(values);
-    if (!(pin_x && pin_y && pin_i && pin_v)) SDB_TRY(ensure_ring(&ctx->up_ring, kSlotBytes));
-    if (!pin_y) SDB_TRY(ensure_ring(&ctx->dn_ring, kSlotBytes));
+    if (!(pin_x && pin_y && pin_i && pin_v)) SDB_TRY(ensure_ring(&ctx->up_ring, slot_bytes()));
+    if (!pin_y) SDB_TRY(ensure_ring(&ctx->dn_ring, slot_bytes()));
     Uploader up{s_up, &ctx->up_ring};
     Downloader down(ctx->device, s_dn, &ctx->dn_ring);  // destroyed (joined) before the streams are drained
     if (!pin_y) down.start();

@@ -6,6 +6,10 @@
 //                           L2-resident buffer, one 16-byte read-only load per lane — the access
 //                           shape of the SpMM gathers (spmm.cu / spmm_slab.cu), whose ceiling it is
 // No reference counterpart (the reference has no device); test/bench infrastructure of the product.
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+
 #include "common.h"
 
 namespace sdb {
@@ -62,11 +66,45 @@ __global__ void __launch_bounds__(kProbeThreads) probe_gather_kernel(const char*
 
 using namespace sdb;
 
+// kind 3: the host side of the pageable-memory pipeline — pageable -> page-locked copies in 16 MiB slots by
+// the library's copy threads (runtime.cu), no GPU involved (falls back to plain memory without a device)
+static sdb_status probe_host_copy(int64_t bytes, int iters, double* gbs) {
+    constexpr size_t kSlot = size_t(16) << 20;
+    char* src = static_cast<char*>(malloc(size_t(bytes)));
+    SDB_REQUIRE(src != nullptr, SDB_STATUS_ALLOC_FAILED, "probe: out of host memory");
+    memset(src, 1, size_t(bytes));
+    void* slots[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool pinned = true;
+    for (auto& p : slots)
+        if (cudaHostAlloc(&p, kSlot, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            pinned = false;
+            p = malloc(kSlot);
+            memset(p, 0, kSlot);
+        }
+    host_copy(slots[0], src, kSlot);  // starts the pool
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int it = 0; it < iters; ++it) {
+        int k = 0;
+        for (size_t off = 0; off < size_t(bytes); off += kSlot, k = (k + 1) & 3)
+            host_copy(slots[k], src + off, std::min(kSlot, size_t(bytes) - off));
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    *gbs = double(iters) * double(bytes) / sec / 1e9;
+    for (auto& p : slots) {
+        if (pinned) cudaFreeHost(p);
+        else free(p);
+    }
+    free(src);
+    return SDB_STATUS_SUCCESS;
+}
+
 extern "C" sdb_status sdb_probe_bandwidth(int kind, int64_t bytes, int iters, double* gbs) {
     SDB_REQUIRE(gbs != nullptr, SDB_STATUS_INVALID_VALUE, "probe: null output");
-    SDB_REQUIRE(kind >= 0 && kind <= 2, SDB_STATUS_INVALID_VALUE, "probe: kind must be 0, 1 or 2");
+    SDB_REQUIRE(kind >= 0 && kind <= 3, SDB_STATUS_INVALID_VALUE, "probe: kind must be 0..3");
     SDB_REQUIRE(bytes >= (int64_t(1) << 20) && iters >= 1, SDB_STATUS_INVALID_VALUE, "probe: bad size / iterations");
     *gbs = 0.0;
+    if (kind == 3) return probe_host_copy(bytes, iters, gbs);
     Context* ctx;
     SDB_TRY(get_context(&ctx));
     cudaStream_t s = ctx->stream;

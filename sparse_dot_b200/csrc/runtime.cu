@@ -60,6 +60,33 @@ void trace(cudaStream_t s, const char* fmt, ...) {
     last = std::chrono::steady_clock::now();
 }
 
+// ---------------------------------------------------------------- options
+namespace {
+struct OptionSlot {
+    const char* name;
+    const char* env;
+    int fallback;
+    std::atomic<int> value;
+    std::atomic<bool> set;
+};
+OptionSlot g_options[kOptCount] = {
+    {"bsr_mma", "SDB_BSR_MMA", -1, {0}, {false}},
+    {"spgemm_wide", "SDB_SPGEMM_WIDE", 0, {0}, {false}},
+    {"dense_mode", "SDB_DENSE_MODE", 0, {0}, {false}},
+    {"dense_threads", "SDB_DENSE_THREADS", 0, {0}, {false}},
+};
+}  // namespace
+
+int get_option(Option o) {
+    OptionSlot& s = g_options[o];
+    if (!s.set.load(std::memory_order_acquire)) {
+        const char* e = getenv(s.env);
+        s.value.store(e ? atoi(e) : s.fallback, std::memory_order_relaxed);
+        s.set.store(true, std::memory_order_release);
+    }
+    return s.value.load(std::memory_order_relaxed);
+}
+
 // ---------------------------------------------------------------- context
 static thread_local Context t_ctx[16];
 
@@ -147,7 +174,11 @@ class CopyPool {
         return *pool;
     }
     void copy(void* dst, const void* src, size_t bytes) {
-        constexpr size_t kPiece = size_t(2) << 20;
+        static const size_t kPiece = [] {  // smallest piece handed to a thread (SDB_COPY_PIECE_KB, default 1 MiB)
+            const char* e = getenv("SDB_COPY_PIECE_KB");
+            const int kb = e ? atoi(e) : 1024;
+            return size_t(kb >= 64 && kb <= (1 << 20) ? kb : 1024) << 10;
+        }();
         if (bytes < 2 * kPiece || workers_ == 0) {
             memcpy(dst, src, bytes);
             return;
@@ -156,8 +187,8 @@ class CopyPool {
         job.dst = static_cast<char*>(dst);
         job.src = static_cast<const char*>(src);
         job.bytes = bytes;
-        // about two pieces per thread, multiples of 4 KiB
-        size_t piece = bytes / (size_t(workers_ + 1) * 2);
+        // about one piece per thread, multiples of 4 KiB
+        size_t piece = bytes / size_t(workers_ + 1);
         piece = std::max(kPiece, (piece + 4095) & ~size_t(4095));
         job.piece = piece;
         job.n_pieces = (bytes + piece - 1) / piece;
@@ -367,6 +398,18 @@ int sdb_last_error(char* buf, int len) {
         buf[len - 1] = '\0';
     }
     return int(strlen(t_err));
+}
+
+sdb_status sdb_set_option(const char* name, int value) {
+    SDB_REQUIRE(name != nullptr, SDB_STATUS_INVALID_VALUE, "sdb_set_option: null name");
+    for (auto& s : g_options)
+        if (strcmp(s.name, name) == 0) {
+            s.value.store(value, std::memory_order_relaxed);
+            s.set.store(true, std::memory_order_release);
+            return SDB_STATUS_SUCCESS;
+        }
+    set_error("sdb_set_option: unknown option '%s'", name);
+    return SDB_STATUS_INVALID_VALUE;
 }
 
 int64_t sdb_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -8,9 +8,12 @@
 // fill) so the result is allocated exactly once between them.  Rows are binned
 // by an upper bound of their work (symbolic) / by their exact length (numeric):
 //   warp bin   per-warp hash table in shared memory (kWarpSlots slots)
-//   CTA bin    one CTA, one shared-memory hash table (kCtaSlots slots)
-//   wide bin   one CTA, dense accumulator + bitmap in global memory (L2
-//              resident), emitted in ascending column order
+//   small bin  one 128-thread CTA, 2048-slot shared-memory hash table
+//   CTA bin    one 512-thread CTA, 8192-slot shared-memory hash table
+//   wide bin   one CTA, bitmap of the column range in global memory (L2 resident) with a
+//              word-level summary in shared memory, emitted in ascending column order
+// (teams and tables are sized to the rows they serve: a row's fixed costs — clearing and scanning its
+// table — are proportional to the table, so a 300-product row must not pay for an 8192-slot one)
 // MKL's structural convention is kept: an entry exists for every structural
 // product even if the values cancel to 0.0 (SURVEY §8c parity hazard 2), and
 // columns inside a row are unordered until sdb_order.
@@ -26,9 +29,11 @@
 namespace sdb {
 
 constexpr int kWarpSlots = 512, kWarpSlotsLog2 = 9, kWarpMax = 256;
+constexpr int kSmallSlots = 2048, kSmallSlotsLog2 = 11, kSmallMax = 1024, kSmallThreads = 128;
 constexpr int kCtaSlots = 8192, kCtaSlotsLog2 = 13, kCtaMax = 4096;
 constexpr int kHashWarps = 8;  // warps per CTA in the warp-bin kernels
 constexpr int kCtaThreads = 512;
+constexpr int kBins = 4;  // warp, small, CTA, wide
 constexpr int32_t kEmpty = -1;
 
 __device__ __forceinline__ uint32_t hash_slot(int32_t col, int log2size) {
@@ -74,10 +79,12 @@ __global__ void __launch_bounds__(256) row_products_kernel(int64_t rows, const i
     if (lane == 0) ub[i] = int32_t(min(acc, int64_t(INT32_MAX)));
 }
 
-// rows with size 0 get c_len = 0 here; the others go to one of three lists
+// rows with size 0 get c_len = 0 here; the others go to one of kBins lists
+struct BinLists {
+    int32_t* list[kBins];
+};
 __global__ void __launch_bounds__(256) bin_rows_kernel(int64_t rows, const int32_t* __restrict__ size,
-                                                       int32_t* __restrict__ zero_len, int32_t* __restrict__ list_w,
-                                                       int32_t* __restrict__ list_c, int32_t* __restrict__ list_g,
+                                                       int32_t* __restrict__ zero_len, BinLists lists,
                                                        unsigned* __restrict__ counters) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -87,21 +94,18 @@ __global__ void __launch_bounds__(256) bin_rows_kernel(int64_t rows, const int32
         if (v == 0) {
             if (zero_len) zero_len[i] = 0;
         } else {
-            bin = v <= kWarpMax ? 0 : (v <= kCtaMax ? 1 : 2);
+            bin = v <= kWarpMax ? 0 : (v <= kSmallMax ? 1 : (v <= kCtaMax ? 2 : 3));
         }
     }
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {  // warp-aggregated append
+    for (int b = 0; b < kBins; ++b) {  // warp-aggregated append
         const unsigned m = __ballot_sync(0xffffffffu, bin == b);
         if (m == 0) continue;
         unsigned base = 0;
         const int leader = __ffs(m) - 1;
         if (lane == leader) base = atomicAdd(&counters[b], unsigned(__popc(m)));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (bin == b) {
-            int32_t* list = b == 0 ? list_w : (b == 1 ? list_c : list_g);
-            list[base + __popc(m & ((1u << lane) - 1))] = int32_t(i);
-        }
+        if (bin == b) lists.list[b][base + __popc(m & ((1u << lane) - 1))] = int32_t(i);
     }
 }
 
@@ -131,38 +135,49 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* pairs, int n, int ti
 }
 
 // ------------------------------------------------------------ hash passes
-// One pass over the products of row i; NUMERIC adds values, else only counts.
-// `team` = 32 for a warp-owned table, blockDim.x for a CTA-owned one.
+// One pass over the products of row i by ONE warp that owns the table; NUMERIC adds values, else only
+// counts.  The lanes walk one R row at a time (warp-uniform trip count).  When the R rows are strictly
+// ascending (`distinct`) the lanes of one step hold distinct columns, hence distinct slots, so the value
+// update is a plain read-modify-write ordered by the __syncwarp() that ends the step; only the key insert
+// needs an atomic (fp32 / fp64 shared-memory atomicAdd is a compare-and-swap loop).
 template <typename T, bool NUMERIC, int SLOTS, int LOG2>
-__device__ __forceinline__ int hash_row(int64_t i, int tid, int team, const int64_t* __restrict__ l_ptr,
-                                        const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
-                                        const int32_t* __restrict__ l_pos, const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
-                                        const T* __restrict__ r_val, bool upper, int32_t* keys, T* vals) {
+__device__ __forceinline__ int hash_row_warp(int64_t i, int lane, const int64_t* __restrict__ l_ptr,
+                                             const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
+                                             const int32_t* __restrict__ l_pos, const int64_t* __restrict__ r_ptr,
+                                             const int32_t* __restrict__ r_idx, const T* __restrict__ r_val, bool upper,
+                                             bool distinct, int32_t* keys, T* vals) {
     int added = 0;
-    const int lane = tid & 31;
-    const int nwarps = team >> 5, warp = tid >> 5;
-    // every warp of the team takes L entries in turn; its lanes stride the R row
-    for (int64_t p0 = l_ptr[i] + int64_t(warp) * 32; p0 < l_ptr[i + 1]; p0 += int64_t(nwarps) * 32) {
+    const int64_t l_end = l_ptr[i + 1];
+    for (int64_t p0 = l_ptr[i]; p0 < l_end; p0 += 32) {
         const int64_t mine = p0 + lane;
         int64_t rb = 0, re = 0;
         T a = Num<T>::zero();
-        if (mine < l_ptr[i + 1]) {
+        if (mine < l_end) {
             const int32_t k = l_idx[mine];
             rb = r_ptr[k] + (l_pos ? l_pos[mine] : 0);
             re = r_ptr[k + 1];
             if (NUMERIC) a = l_val[mine];
         }
-        const int cnt = int(min(int64_t(32), l_ptr[i + 1] - p0));
+        const int cnt = int(min(int64_t(32), l_end - p0));
         for (int j = 0; j < cnt; ++j) {
             const int64_t qb = __shfl_sync(0xffffffffu, rb, j), qe = __shfl_sync(0xffffffffu, re, j);
             T aj = Num<T>::zero();
             if (NUMERIC) aj = shfl(0xffffffffu, a, j, 32);
-            for (int64_t q = qb + lane; q < qe; q += 32) {
-                const int32_t col = r_idx[q];
-                if (upper && int64_t(col) < i) continue;
-                uint32_t slot;
-                added += hash_insert<SLOTS, LOG2>(keys, col, &slot);
-                if (NUMERIC) atomic_add(vals + slot, mul(aj, r_val[q]));
+            for (int64_t q0 = qb; q0 < qe; q0 += 32) {  // warp-uniform
+                const int64_t q = q0 + lane;
+                if (q < qe) {
+                    const int32_t col = r_idx[q];
+                    if (!(upper && int64_t(col) < i)) {
+                        uint32_t slot;
+                        added += hash_insert<SLOTS, LOG2>(keys, col, &slot);
+                        if (NUMERIC) {
+                            const T prod = mul(aj, r_val[q]);
+                            if (distinct) vals[slot] = add(vals[slot], prod);
+                            else atomic_add(vals + slot, prod);
+                        }
+                    }
+                }
+                if (NUMERIC) __syncwarp();  // the next step may touch the same slot from another lane
             }
         }
     }
@@ -174,18 +189,19 @@ __device__ __forceinline__ int hash_row(int64_t i, int tid, int team, const int6
 // round-robin and their lanes stride the R row.  f(col, a, q) is called once per product.
 constexpr int kStageEntries = 256;
 constexpr int kLongRRow = 512;  // R rows longer than this are shared by all warps of the CTA
-template <typename T> struct LStage {
+template <typename T, int kStageEntries = 256> struct LStage {
     int64_t rb[kStageEntries];
     int64_t re[kStageEntries];
     T a[kStageEntries];
 };
 
-template <typename T, bool NEED_VAL, typename F>
+template <typename T, bool NEED_VAL, int kStageEntries, typename F>
 __device__ __forceinline__ void for_each_product_cta(int64_t i, const int64_t* __restrict__ l_ptr,
                                                      const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
                                                      const int32_t* __restrict__ l_pos,
                                                      const int64_t* __restrict__ r_ptr,
-                                                     const int32_t* __restrict__ r_idx, LStage<T>& st, F f) {
+                                                     const int32_t* __restrict__ r_idx,
+                                                     LStage<T, kStageEntries>& st, F f) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int64_t l_end = l_ptr[i + 1];
     for (int64_t base = l_ptr[i]; base < l_end; base += kStageEntries) {
@@ -222,7 +238,7 @@ __global__ void __launch_bounds__(kHashWarps * 32)
     spgemm_warp_kernel(const int32_t* __restrict__ list, unsigned n_list, const int64_t* __restrict__ l_ptr,
                        const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
                        const int32_t* __restrict__ l_pos, const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
-                       const T* __restrict__ r_val, bool upper, bool sort, int32_t* __restrict__ c_len,
+                       const T* __restrict__ r_val, bool upper, bool sort, bool distinct, int32_t* __restrict__ c_len,
                        const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* all_keys = reinterpret_cast<int32_t*>(smem_raw);
@@ -240,8 +256,8 @@ __global__ void __launch_bounds__(kHashWarps * 32)
         if (NUMERIC) vals[s] = Num<T>::zero();
     }
     __syncwarp();
-    int added = hash_row<T, NUMERIC, kWarpSlots, kWarpSlotsLog2>(i, lane, 32, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx,
-                                                                r_val, upper, keys, vals);
+    int added = hash_row_warp<T, NUMERIC, kWarpSlots, kWarpSlotsLog2>(i, lane, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx,
+                                                                     r_val, upper, distinct, keys, vals);
     __syncwarp();
     if (!NUMERIC) {
 #pragma unroll
@@ -279,8 +295,11 @@ __global__ void __launch_bounds__(kHashWarps * 32)
     }
 }
 
-template <typename T, bool NUMERIC>
-__global__ void __launch_bounds__(kCtaThreads)
+// One CTA of THREADS threads per row, one shared-memory table of SLOTS slots (rows of at most SLOTS / 2
+// entries), L entries staged STAGE at a time.  Instantiated for the small bin (128 threads, 2048 slots) and the
+// CTA bin (512 threads, 8192 slots).
+template <typename T, bool NUMERIC, int SLOTS, int LOG2, int THREADS, int STAGE>
+__global__ void __launch_bounds__(THREADS)
     spgemm_cta_kernel(const int32_t* __restrict__ list, const int64_t* __restrict__ l_ptr,
                       const int32_t* __restrict__ l_idx, const T* __restrict__ l_val,
                       const int32_t* __restrict__ l_pos, const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
@@ -288,25 +307,25 @@ __global__ void __launch_bounds__(kCtaThreads)
                       const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t* keys = reinterpret_cast<int32_t*>(smem_raw);
-    T* vals = reinterpret_cast<T*>(smem_raw + sizeof(int32_t) * kCtaSlots);
-    uint64_t* pairs = reinterpret_cast<uint64_t*>(smem_raw + (sizeof(int32_t) + sizeof(T)) * kCtaSlots);  // sort only
+    T* vals = reinterpret_cast<T*>(smem_raw + sizeof(int32_t) * SLOTS);
+    uint64_t* pairs = reinterpret_cast<uint64_t*>(smem_raw + (sizeof(int32_t) + sizeof(T)) * SLOTS);  // sort only
     __shared__ int total;
     const int64_t i = list[blockIdx.x];
-    for (int s = threadIdx.x; s < kCtaSlots; s += kCtaThreads) {
+    for (int s = threadIdx.x; s < SLOTS; s += THREADS) {
         keys[s] = kEmpty;
         if (NUMERIC) vals[s] = Num<T>::zero();
     }
     if (threadIdx.x == 0) total = 0;
     __syncthreads();
-    __shared__ LStage<T> stage;
+    __shared__ LStage<T, STAGE> stage;
     int added = 0;
-    for_each_product_cta<T, NUMERIC>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
-                                     [&](int32_t col, T a, int64_t q) {
-                                         if (upper && int64_t(col) < i) return;
-                                         uint32_t slot;
-                                         added += hash_insert<kCtaSlots, kCtaSlotsLog2>(keys, col, &slot);
-                                         if (NUMERIC) atomic_add(vals + slot, mul(a, r_val[q]));
-                                     });
+    for_each_product_cta<T, NUMERIC, STAGE>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
+                                            [&](int32_t col, T a, int64_t q) {
+                                                if (upper && int64_t(col) < i) return;
+                                                uint32_t slot;
+                                                added += hash_insert<SLOTS, LOG2>(keys, col, &slot);
+                                                if (NUMERIC) atomic_add(vals + slot, mul(a, r_val[q]));
+                                            });
     if (!NUMERIC) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) added += __shfl_xor_sync(0xffffffffu, added, d);
@@ -318,7 +337,7 @@ __global__ void __launch_bounds__(kCtaThreads)
     __syncthreads();
     const int64_t out = c_ptr[i];
     const int lane = threadIdx.x & 31;
-    for (int s = threadIdx.x; s < kCtaSlots; s += kCtaThreads) {
+    for (int s = threadIdx.x; s < SLOTS; s += THREADS) {
         const int32_t k = keys[s];
         const unsigned m = __ballot_sync(0xffffffffu, k != kEmpty);
         int base = 0;
@@ -337,8 +356,8 @@ __global__ void __launch_bounds__(kCtaThreads)
     if (!sort) return;
     __syncthreads();
     const int n = total;
-    bitonic_sort_smem(pairs, n, threadIdx.x, kCtaThreads, [] { __syncthreads(); });
-    for (int e = threadIdx.x; e < n; e += kCtaThreads) {
+    bitonic_sort_smem(pairs, n, threadIdx.x, THREADS, [] { __syncthreads(); });
+    for (int e = threadIdx.x; e < n; e += THREADS) {
         c_idx[out + e] = int32_t(pairs[e] >> 32);
         c_val[out + e] = vals[uint32_t(pairs[e])];
     }
@@ -380,7 +399,7 @@ __global__ void __launch_bounds__(1024)
     for (unsigned li = blockIdx.x; li < n_list; li += gridDim.x) {
         const int64_t i = list[li];
         // ---- 1. membership
-        for_each_product_cta<T, false>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
+        for_each_product_cta<T, false, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
                                        [&](int32_t col, T, int64_t) {
                                            if (upper && int64_t(col) < i) return;
                                            atomicOr(&bm[col >> 5], 1u << (col & 31));
@@ -461,7 +480,7 @@ __global__ void __launch_bounds__(1024)
             continue;
         }
         // ---- 4. values: every product is added at its column's rank
-        for_each_product_cta<T, true>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
+        for_each_product_cta<T, true, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
                                       [&](int32_t col, T a, int64_t q) {
                                           if (upper && int64_t(col) < i) return;
                                           const int w = col >> 5;
@@ -480,23 +499,206 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
+
+// Wide rows, second formulation (the default): the same bitmap, but every pass after the first touches only the
+// bitmap words the row has set.  The first version swept the whole column range (cols / 8 bytes of bitmap plus
+// as much again of per-word ranks) three times per row whatever the row held; at 4M columns and two CTAs per SM
+// those slices no longer fit L2 and the bin ran at the speed of the sweeps' DRAM traffic (38 000 rows x 2.5 MB at
+// R-MAT scale 22).  Here a word-level SUMMARY of the bitmap lives in shared memory — bit b of summary[g] says
+// bitmap word 32 g + b is non-zero — together with two per-group prefix arrays, and
+//   1. the products are walked: atomicOr on the bitmap word (global, fire-and-forget) and, only while the
+//      summary bit is still clear, an atomicOr on the summary (shared);
+//   2. a warp takes a group of 32 words at a time (lane = word; the set words of a group share a 128-byte
+//      line): populations per group -> block-wide exclusive scans -> entry / set-word offsets per group;
+//      [symbolic stops here: c_len, then only the set words are cleared]
+//   3. second walk of the non-empty groups: the k-th set word's output rank goes into a COMPACT array
+//      (k = group offset + popc of the lower summary bits), columns are written in ascending order;
+//   4. the products are walked again: rank = compact_rank[k] + popc(lower bits of the word) and the product is
+//      atomically added at c_val[row start + rank];
+//   5. the set words and the summary are cleared.
+// Per row the global traffic is proportional to the words it sets, not to the column count.  The result rows
+// come out sorted.  Shared memory: 12 bytes per 1024 columns (up to ~17M columns; beyond, the first version runs).
 template <typename T, bool NUMERIC>
-static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, bool upper, bool sort,
+__global__ void __launch_bounds__(1024)
+    spgemm_wide2_kernel(const int32_t* __restrict__ list, unsigned n_list, int64_t words_padded, int n_groups,
+                        const int64_t* __restrict__ l_ptr, const int32_t* __restrict__ l_idx,
+                        const T* __restrict__ l_val, const int32_t* __restrict__ l_pos,
+                        const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
+                        const T* __restrict__ r_val, bool upper, unsigned* __restrict__ bitmaps,
+                        int32_t* __restrict__ word_ranks, int32_t* __restrict__ c_len,
+                        const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* summary = reinterpret_cast<unsigned*>(smem_raw);           // [n_groups]
+    int* grp_ent = reinterpret_cast<int*>(summary + n_groups);           // [n_groups] entries before group g
+    int* grp_wrd = grp_ent + n_groups;                                   // [n_groups] set words before group g
+    __shared__ int warp_ent[32], warp_wrd[32];
+    __shared__ LStage<T, 256> stage;
+    unsigned* bm = bitmaps + int64_t(blockIdx.x) * words_padded;
+    int32_t* wr = NUMERIC ? word_ranks + int64_t(blockIdx.x) * words_padded : nullptr;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int g = tid; g < n_groups; g += blockDim.x) summary[g] = 0u;
+    __syncthreads();
+    // groups handled by one thread in the block-wide scans (contiguous, so the scan is over ascending columns)
+    const int per_thread = (n_groups + int(blockDim.x) - 1) / int(blockDim.x);
+    for (unsigned li = blockIdx.x; li < n_list; li += gridDim.x) {
+        const int64_t i = list[li];
+        // ---- 1. membership
+        for_each_product_cta<T, false, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
+                                            [&](int32_t col, T, int64_t) {
+                                                if (upper && int64_t(col) < i) return;
+                                                const int w = col >> 5;
+                                                atomicOr(&bm[w], 1u << (col & 31));
+                                                const unsigned sb = 1u << (w & 31);
+                                                volatile unsigned* sp = summary + (w >> 5);
+                                                if (!(*sp & sb)) atomicOr(summary + (w >> 5), sb);
+                                            });
+        __syncthreads();
+        // ---- 2. populations per group
+        for (int g = warp; g < n_groups; g += nwarps) {
+            const unsigned sm = summary[g];
+            int c = 0;
+            if (sm) {
+                const unsigned word = (sm >> lane) & 1u ? __ldcg(bm + int64_t(g) * 32 + lane) : 0u;
+                c = __popc(word);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+            }
+            if (lane == 0) {
+                grp_ent[g] = c;
+                grp_wrd[g] = __popc(sm);
+            }
+        }
+        __syncthreads();
+        // block-wide exclusive scans of both arrays: thread-local run, warp scan, scan of the warp totals
+        int e_sum = 0, w_sum = 0;
+        const int g0 = tid * per_thread, g1 = min(n_groups, g0 + per_thread);
+        for (int g = g0; g < g1; ++g) {
+            e_sum += grp_ent[g];
+            w_sum += grp_wrd[g];
+        }
+        int e_inc = e_sum, w_inc = w_sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int eo = __shfl_up_sync(0xffffffffu, e_inc, d), wo = __shfl_up_sync(0xffffffffu, w_inc, d);
+            if (lane >= d) {
+                e_inc += eo;
+                w_inc += wo;
+            }
+        }
+        if (lane == 31) {
+            warp_ent[warp] = e_inc;
+            warp_wrd[warp] = w_inc;
+        }
+        __syncthreads();
+        int e_before = 0, w_before = 0, e_total = 0;
+        for (int x = 0; x < nwarps; ++x) {
+            const int te = warp_ent[x], tw = warp_wrd[x];
+            if (x < warp) {
+                e_before += te;
+                w_before += tw;
+            }
+            e_total += te;
+        }
+        int e_run = e_before + e_inc - e_sum, w_run = w_before + w_inc - w_sum;
+        for (int g = g0; g < g1; ++g) {
+            const int ce = grp_ent[g], cw = grp_wrd[g];
+            grp_ent[g] = e_run;
+            grp_wrd[g] = w_run;
+            e_run += ce;
+            w_run += cw;
+        }
+        __syncthreads();
+        if (!NUMERIC) {
+            if (tid == 0) c_len[i] = e_total;
+        } else {
+            // ---- 3. ranks of the set words (compact) and ordered emission
+            const int64_t out0 = c_ptr[i];
+            for (int g = warp; g < n_groups; g += nwarps) {
+                const unsigned sm = summary[g];
+                if (!sm) continue;
+                const bool mine = (sm >> lane) & 1u;
+                const int64_t w = int64_t(g) * 32 + lane;
+                unsigned word = mine ? __ldcg(bm + w) : 0u;
+                const int c = __popc(word);
+                int incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                if (mine) {
+                    int rank = grp_ent[g] + incl - c;
+                    wr[grp_wrd[g] + __popc(sm & lt_mask)] = rank;
+                    while (word) {
+                        const int bit = __ffs(word) - 1;
+                        word &= word - 1;
+                        c_idx[out0 + rank] = int32_t((w << 5) + bit);
+                        c_val[out0 + rank] = Num<T>::zero();
+                        ++rank;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- 4. values: every product is added at its column's rank
+            for_each_product_cta<T, true, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
+                                               [&](int32_t col, T a, int64_t q) {
+                                                   if (upper && int64_t(col) < i) return;
+                                                   const int w = col >> 5, g = w >> 5;
+                                                   const unsigned sm = summary[g];
+                                                   const int k = grp_wrd[g] + __popc(sm & ((1u << (w & 31)) - 1u));
+                                                   const unsigned below = __ldcg(bm + w) & ((1u << (col & 31)) - 1u);
+                                                   const int rank = __ldcg(wr + k) + __popc(below);
+                                                   atomic_add(c_val + out0 + rank, mul(a, r_val[q]));
+                                               });
+            __syncthreads();
+        }
+        // ---- 5. clear the set words and the summary
+        for (int g = warp; g < n_groups; g += nwarps) {
+            const unsigned sm = summary[g];
+            if (!sm) continue;
+            if ((sm >> lane) & 1u) bm[int64_t(g) * 32 + lane] = 0u;
+            __syncwarp();
+            if (lane == 0) summary[g] = 0u;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, bool NUMERIC, int SLOTS, int LOG2, int THREADS, int STAGE, int MAXLEN>
+static sdb_status launch_cta_bin(cudaStream_t s, unsigned n_rows, const int32_t* list, const int64_t* lp,
+                                 const int32_t* li, const T* lv, const int32_t* lq, const int64_t* rp,
+                                 const int32_t* ri, const T* rv, bool upper, bool sort, int32_t* c_len,
+                                 const int64_t* c_ptr, int32_t* c_idx, T* c_val) {
+    const size_t smem = size_t(SLOTS) * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0)) +
+                        (NUMERIC && sort ? size_t(MAXLEN) * sizeof(uint64_t) : 0);
+    auto kernel = spgemm_cta_kernel<T, NUMERIC, SLOTS, LOG2, THREADS, STAGE>;
+    SDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    SDB_LAUNCH(kernel, n_rows, THREADS, smem, s, list, lp, li, lv, lq, rp, ri, rv, upper, sort, c_len, c_ptr, c_idx,
+               c_val);
+    return SDB_STATUS_SUCCESS;
+}
+
+template <typename T, bool NUMERIC>
+static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, bool upper, bool sort, bool distinct,
                            const int32_t* sizes, int32_t* c_len, const int64_t* c_ptr, int32_t* c_idx, T* c_val) {
     cudaStream_t s = ctx->stream;
     const int64_t rows = l.rows;
-    DevBuf lw, lc, lg, counters;
-    SDB_TRY(lw.alloc(size_t(rows) * 4, s));
-    SDB_TRY(lc.alloc(size_t(rows) * 4, s));
-    SDB_TRY(lg.alloc(size_t(rows) * 4, s));
-    SDB_TRY(counters.alloc(3 * sizeof(unsigned), s));
-    SDB_CUDA(cudaMemsetAsync(counters.p, 0, 3 * sizeof(unsigned), s));
-    SDB_LAUNCH(bin_rows_kernel, unsigned((rows + 255) / 256), 256, 0, s, rows, sizes, NUMERIC ? nullptr : c_len,
-               lw.as<int32_t>(), lc.as<int32_t>(), lg.as<int32_t>(), counters.as<unsigned>());
-    unsigned h[3];
+    DevBuf list_buf[kBins], counters;
+    BinLists lists;
+    for (int b = 0; b < kBins; ++b) {
+        SDB_TRY(list_buf[b].alloc(size_t(rows) * 4, s));
+        lists.list[b] = list_buf[b].as<int32_t>();
+    }
+    SDB_TRY(counters.alloc(kBins * sizeof(unsigned), s));
+    SDB_CUDA(cudaMemsetAsync(counters.p, 0, kBins * sizeof(unsigned), s));
+    SDB_LAUNCH(bin_rows_kernel, unsigned((rows + 255) / 256), 256, 0, s, rows, sizes, NUMERIC ? nullptr : c_len, lists,
+               counters.as<unsigned>());
+    unsigned h[kBins];
     SDB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     SDB_CUDA(cudaStreamSynchronize(s));
-    trace(s, "spgemm %s: bins warp %u, cta %u, wide %u", NUMERIC ? "numeric" : "symbolic", h[0], h[1], h[2]);
+    trace(s, "spgemm %s: bins warp %u, small %u, cta %u, wide %u", NUMERIC ? "numeric" : "symbolic", h[0], h[1], h[2],
+          h[3]);
     const int64_t* lp = l.indptr;
     const int32_t* li = l.indices;
     const T* lv = static_cast<const T*>(l.values);
@@ -510,32 +712,45 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
         SDB_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel<T, NUMERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem)));
         SDB_LAUNCH((spgemm_warp_kernel<T, NUMERIC>), (h[0] + kHashWarps - 1) / kHashWarps, kHashWarps * 32, smem, s,
-                   lw.as<int32_t>(), h[0], lp, li, lv, lq, rp, ri, rv, upper, sort, c_len, c_ptr, c_idx, c_val);
+                   lists.list[0], h[0], lp, li, lv, lq, rp, ri, rv, upper, sort, distinct, c_len, c_ptr, c_idx, c_val);
         trace(s, "spgemm: warp bin done");
     }
     if (h[1] > 0) {
-        const size_t smem = size_t(kCtaSlots) * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0)) +
-                            (NUMERIC && sort ? size_t(kCtaMax) * sizeof(uint64_t) : 0);
-        SDB_CUDA(cudaFuncSetAttribute(spgemm_cta_kernel<T, NUMERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(smem)));
-        SDB_LAUNCH((spgemm_cta_kernel<T, NUMERIC>), h[1], kCtaThreads, smem, s, lc.as<int32_t>(), lp, li, lv, lq, rp,
-                   ri, rv, upper, sort, c_len, c_ptr, c_idx, c_val);
-        trace(s, "spgemm: cta bin done");
+        SDB_TRY((launch_cta_bin<T, NUMERIC, kSmallSlots, kSmallSlotsLog2, kSmallThreads, 64, kSmallMax>(
+            s, h[1], lists.list[1], lp, li, lv, lq, rp, ri, rv, upper, sort, c_len, c_ptr, c_idx, c_val)));
+        trace(s, "spgemm: small bin done");
     }
     if (h[2] > 0) {
+        SDB_TRY((launch_cta_bin<T, NUMERIC, kCtaSlots, kCtaSlotsLog2, kCtaThreads, 256, kCtaMax>(
+            s, h[2], lists.list[2], lp, li, lv, lq, rp, ri, rv, upper, sort, c_len, c_ptr, c_idx, c_val)));
+        trace(s, "spgemm: cta bin done");
+    }
+    if (h[3] > 0) {
         const int64_t n_cols = r.cols;
         const int64_t words = (((n_cols + 31) >> 5) + kPieceWords - 1) / kPieceWords * kPieceWords;  // padded
         // resident CTAs: bounded by the list, two per SM, and ~2 GiB of scratch
         const int64_t per_cta = words * 4 * (NUMERIC ? 2 : 1);
-        int64_t ctas = std::min<int64_t>(h[2], 2 * int64_t(ctx->sm_count));
+        int64_t ctas = std::min<int64_t>(h[3], 2 * int64_t(ctx->sm_count));
         ctas = std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t(2) << 30) / std::max<int64_t>(per_cta, 1)));
         DevBuf bm, ranks;
         SDB_TRY(bm.alloc(size_t(ctas * words) * 4, s));
         SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(ctas * words) * 4, s));
         if (NUMERIC) SDB_TRY(ranks.alloc(size_t(ctas * words) * 4, s));
-        SDB_LAUNCH((spgemm_wide_kernel<T, NUMERIC>), unsigned(ctas), 1024, 0, s, lg.as<int32_t>(), h[2], words, lp, li,
-                   lv, lq, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx, c_val);
-        trace(s, "spgemm: wide bin done (%lld CTAs)", (long long)ctas);
+        // summary formulation while its shared-memory index fits beside two CTAs per SM (SDB_SPGEMM_WIDE=1: first version)
+        const int forced = get_option(kOptSpgemmWide);
+        const int64_t n_groups = words / 32;
+        const size_t smem2 = size_t(n_groups) * 12;
+        if (forced != 1 && smem2 <= size_t(96) * 1024) {
+            auto kernel = spgemm_wide2_kernel<T, NUMERIC>;
+            SDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem2, 48 * 1024))));
+            SDB_LAUNCH(kernel, unsigned(ctas), 1024, smem2, s, lists.list[3], h[3], words, int(n_groups), lp, li, lv, lq,
+                       rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx, c_val);
+            trace(s, "spgemm: wide bin (summary) done (%lld CTAs)", (long long)ctas);
+        } else {
+            SDB_LAUNCH((spgemm_wide_kernel<T, NUMERIC>), unsigned(ctas), 1024, 0, s, lists.list[3], h[3], words, lp, li,
+                       lv, lq, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx, c_val);
+            trace(s, "spgemm: wide bin done (%lld CTAs)", (long long)ctas);
+        }
     }
     return SDB_STATUS_SUCCESS;
 }
@@ -546,6 +761,12 @@ sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int d
     SDB_REQUIRE(l.cols == r.rows, SDB_STATUS_INVALID_VALUE, "spgemm: inner dimensions %lld and %lld differ",
                 (long long)l.cols, (long long)r.rows);
     const int64_t rows = l.rows;
+    // R rows strictly ascending (no duplicate column inside a row): the warp bin then adds values without atomics
+    bool distinct = false;
+    if (r.owner != nullptr) {
+        if (r.owner->strict_sorted == 0) SDB_TRY(ensure_strict_flag(ctx, r.owner));
+        distinct = r.owner->strict_sorted == 1;
+    }
     DevBuf ub, c_len;
     SDB_TRY(ub.alloc(size_t(rows + 1) * 4, s));
     SDB_TRY(c_len.alloc(size_t(rows + 1) * 4, s));
@@ -554,7 +775,7 @@ sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int d
         SDB_LAUNCH(row_products_kernel, unsigned((rows * 32 + 255) / 256), 256, 0, s, rows, l.indptr, l.indices,
                    upper ? l.pos : nullptr, r.indptr, ub.as<int32_t>());
         SDB_TRY(SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
-            return run_pass<T, false>(ctx, l, r, upper, false, ub.as<int32_t>(), c_len.as<int32_t>(), nullptr,
+            return run_pass<T, false>(ctx, l, r, upper, false, false, ub.as<int32_t>(), c_len.as<int32_t>(), nullptr,
                                       nullptr, nullptr);
         }));
     }
@@ -570,8 +791,8 @@ sdb_status spgemm_device(Context* ctx, const CsrView& l, const CsrView& r, int d
         SDB_CUDA(cudaMemcpyAsync(c->indptr, c_ptr.p, size_t(rows + 1) * 8, cudaMemcpyDeviceToDevice, s));
         if (nnz == 0) return SDB_STATUS_SUCCESS;
         return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
-            return run_pass<T, true>(ctx, l, r, upper, sort, c_len.as<int32_t>(), nullptr, c->indptr, c->indices,
-                                     static_cast<T*>(c->values));
+            return run_pass<T, true>(ctx, l, r, upper, sort, distinct, c_len.as<int32_t>(), nullptr, c->indptr,
+                                     c->indices, static_cast<T*>(c->values));
         });
     }();
     if (st != SDB_STATUS_SUCCESS) {
@@ -746,16 +967,15 @@ sdb_status spgemm_dense_device(Context* ctx, cudaStream_t s, const CsrView& l, c
     const bool col_major = layout == SDB_LAYOUT_COL_MAJOR;
     SDB_REQUIRE(ldc >= (col_major ? m : n), SDB_STATUS_INVALID_VALUE, "dense product: ldc too small");
     // accumulate in shared-memory column tiles (small rows) or directly in the L2-resident output row
-    static const int forced_mode = [] {
-        const char* e = getenv("SDB_DENSE_MODE");
-        return e ? atoi(e) : 0;  // 1 = shared-memory tiles, 2 = global reductions
-    }();
+    const int forced_mode = get_option(kOptDenseMode);  // 1 = shared-memory tiles, 2 = global reductions
     // measured (profiles/r1_logs/dense_modes.log): one shared-memory tile beats global reductions 1.8x at
     // n = 10k; once a row needs several tiles (n = 100k fp32) the single-pass global variant wins 1.3x
     const bool use_red = forced_mode ? forced_mode == 2 : size_t(n) * dtype_size(dtype) > size_t(200) * 1024;
     if (use_red) {
         return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
-            SDB_LAUNCH(spgemm_dense_red_kernel<T>, unsigned(m), 1024, 0, s, n, l.indptr, l.indices,
+            int threads = get_option(kOptDenseThreads);
+            threads = threads >= 64 && threads <= 1024 ? threads / 32 * 32 : 1024;
+            SDB_LAUNCH(spgemm_dense_red_kernel<T>, unsigned(m), threads, 0, s, n, l.indptr, l.indices,
                        static_cast<const T*>(l.values), upper ? l.pos : nullptr, r.indptr, r.indices,
                        static_cast<const T*>(r.values), upper, zero_lower, Num<T>::make(alpha[0], alpha[1]),
                        Num<T>::make(beta[0], beta[1]), static_cast<T*>(dC), ldc, col_major);

@@ -19,6 +19,7 @@
 #include <cstdlib>
 
 #include "common.h"
+#include "tma.cuh"
 #include "types.cuh"
 
 namespace sdb {
@@ -26,38 +27,7 @@ namespace sdb {
 namespace {
 
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-}
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
+using namespace tma;
 
 template <typename T> struct Vec16;  // 16-byte vector of T
 template <> struct Vec16<float> {
@@ -203,7 +173,8 @@ static sdb_status launch_bsr_s(cudaStream_t s, const sdb_mat* a, const T* X, int
     const int64_t gy = (n + CW - 1) / CW;
     SDB_REQUIRE(a->rows < (int64_t(1) << 31) && gy < 65536, SDB_STATUS_NOT_SUPPORTED, "spmm_bsr: grid too large");
     const dim3 grid(unsigned(a->rows), unsigned(gy));
-    note_spmm_kernel("spmm_bsr_kernel<%s,%d,%d,%d>", dtype_cname(Num<T>::dtype), B, CW, kBsrStages);
+    note_spmm_kernel("spmm_bsr_kernel<%s,%d,%d,%d,%d>", dtype_cname(Num<T>::dtype), B, CW,
+                     a->block_layout == SDB_LAYOUT_COL_MAJOR ? 1 : 0, kBsrStages);
     if (a->block_layout == SDB_LAYOUT_COL_MAJOR) {
         SDB_CUDA(cudaFuncSetAttribute(spmm_bsr_kernel<T, B, CW, true, kBsrStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem)));
@@ -220,15 +191,13 @@ static sdb_status launch_bsr_s(cudaStream_t s, const sdb_mat* a, const T* X, int
 
 // Ring depth: short block rows (a handful of blocks) finish before a deep ring pays off and a shallow
 // ring lets more CTAs share the SM; long block rows want the deeper prefetch.
+static int ring_depth(const sdb_mat* a);
+constexpr bool kBsrMmaByDefault = false;  // flipped by measurement
+
 template <typename T, int B, int CW>
 static sdb_status launch_bsr(cudaStream_t s, const sdb_mat* a, const T* X, int64_t ldx, int64_t n, T alpha, T beta,
                              T* Y, int64_t ldy) {
-    static const int forced = [] {
-        const char* e = getenv("SDB_BSR_STAGES");
-        return e ? atoi(e) : 0;
-    }();
-    const double mean_blocks = a->rows > 0 ? double(a->nnz) / double(a->rows) : 0.0;
-    const int stages = forced ? forced : (mean_blocks <= 6.0 ? 2 : 4);
+    const int stages = ring_depth(a);
     if (stages <= 2) return launch_bsr_s<T, B, CW, 2>(s, a, X, ldx, n, alpha, beta, Y, ldy);
     if (stages == 3) return launch_bsr_s<T, B, CW, 3>(s, a, X, ldx, n, alpha, beta, Y, ldy);
     return launch_bsr_s<T, B, CW, 4>(s, a, X, ldx, n, alpha, beta, Y, ldy);
@@ -255,8 +224,21 @@ bool spmm_bsr_supported(const sdb_mat* a, int op, int layout, const void* dX, in
     return a->rows > 0;
 }
 
+static int ring_depth(const sdb_mat* a) {
+    static const int forced = [] {
+        const char* e = getenv("SDB_BSR_STAGES");
+        return e ? atoi(e) : 0;
+    }();
+    const double mean_blocks = a->rows > 0 ? double(a->nnz) / double(a->rows) : 0.0;
+    return forced ? forced : (mean_blocks <= 6.0 ? 2 : 4);
+}
+
 sdb_status spmm_bsr_device(cudaStream_t s, const sdb_mat* a, const double* alpha, const double* beta, const void* dX,
                            int64_t n, int64_t ldx, void* dY, int64_t ldy) {
+    // tensor cores (spmm_bsr_mma.cu) when switched on and the shape is covered; see DESIGN.md K2 for the measurements
+    const int mma = get_option(kOptBsrMma);
+    if ((mma == 1 || (mma < 0 && kBsrMmaByDefault)) && spmm_bsr_mma_supported(a, n))
+        return spmm_bsr_mma_device(s, a, alpha, beta, dX, n, ldx, dY, ldy, ring_depth(a));
 #define SDB_BSR_CASE(T, B)                                                                                    \
     return pick_cw<T, B>(s, a, static_cast<const T*>(dX), ldx, n, Num<T>::make(alpha[0], alpha[1]),           \
                          Num<T>::make(beta[0], beta[1]), static_cast<T*>(dY), ldy)

@@ -128,3 +128,92 @@ def test_bandwidth_probes_are_sane():
     assert l2 > hbm and gather > hbm, (hbm, l2, gather)
     with pytest.raises(ValueError):
         _lib.probe_bandwidth(7, 1 << 30, 1)
+
+
+# ===================================================== BSR x dense on tensor cores (DMMA / 3xTF32) vs the oracle
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("b", [8, 16, 32])
+@pytest.mark.parametrize("n", [8, 40, 128, 264])
+def test_bsr_tensor_core_kernel(dtype, b, n):
+    """_common.py:327-384 create_bsr -> _sparse_dense.py:111-123 mm, with the tensor-core kernel forced on:
+    every block size it covers, chunk widths with dead n-tiles (n = 40, 264), beta != 0, both block layouts."""
+    rng = np.random.default_rng(b * 1000 + n)
+    dense = sp.random(6 * b, 5 * b, density=0.02, format="csr", dtype=np.float64, random_state=b + n)
+    a = (dense + sp.eye(6 * b, 5 * b, format="csr")).tobsr(blocksize=(b, b)).astype(dtype)
+    a.data[:] = (rng.random(a.data.shape) + 0.5).astype(dtype)
+    x = rng.random((a.shape[1], n)).astype(dtype)
+    y0 = rng.random((a.shape[0], n)).astype(dtype)
+    want = orc.c_spmm(a.tocsr(), x, beta=0.5, y=y0.copy())
+    want0 = orc.c_spmm(a.tocsr(), x)
+    tol = cs.TOL[np.dtype(dtype)]
+    _lib.set_option("bsr_mma", 1)
+    try:
+        for mat in (a, sp.bsr_matrix((np.asfortranarray(a.data.transpose(0, 2, 1)).transpose(0, 2, 1), a.indices, a.indptr),
+                                     shape=a.shape)):
+            got = sdb.dot_product_mkl(mat, x, out=y0.copy(), out_scalar=0.5)
+            assert "spmm_bsr_mma_kernel" in sdb.last_spmm_kernel()
+            assert cs.rel_err(got, want) <= tol
+            assert cs.rel_err(sdb.dot_product_mkl(mat, x), want0) <= tol
+    finally:
+        _lib.set_option("bsr_mma", -1)
+
+
+def test_bsr_tensor_core_falls_back_when_not_covered():
+    a = sp.random(40, 40, density=0.2, format="csr", dtype=np.float32, random_state=1).tobsr(blocksize=(4, 4))
+    x = np.random.default_rng(0).random((40, 12), dtype=np.float32)
+    _lib.set_option("bsr_mma", 1)
+    try:
+        got = sdb.dot_product_mkl(a, x)  # block 4 and n % 8 != 0: the FMA kernel
+        assert "mma" not in sdb.last_spmm_kernel()
+        assert cs.rel_err(got, orc.c_spmm(a.tocsr(), x), orc.value_bound(abs(a.tocsr()), abs(x))) <= 1e-5
+    finally:
+        _lib.set_option("bsr_mma", -1)
+
+
+# ===================================================== SpGEMM: both wide-row formulations, all four bins
+@pytest.mark.parametrize("wide", [1, 2])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_spgemm_wide_formulations_agree_with_the_oracle(dtype, wide):
+    """_sparse_sparse.py:35-40 (mkl_sparse_spmm) + reorder_output: power-law rows reach the warp, small, CTA and
+    wide bins; `spgemm_wide` picks the full-sweep bitmap (1) or the summary formulation (2)."""
+    a = cs.rmat_csr(13, 8, dtype, seed=1)
+    b = cs.rmat_csr(13, 8, dtype, seed=2)
+    _lib.set_option("spgemm_wide", wide)
+    try:
+        got = sdb.dot_product_mkl(a, b, reorder_output=True)
+        want = orc.c_spgemm(a, b, sort=True)
+        assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+        assert cs.rel_err(got.data, want.data) <= cs.TOL[np.dtype(dtype)]
+        unsorted = sdb.dot_product_mkl(a, b)
+        unsorted.sort_indices()
+        assert np.array_equal(unsorted.indices, want.indices)
+        assert cs.rel_err(unsorted.data, want.data) <= cs.TOL[np.dtype(dtype)]
+        g = sdb.gram_matrix_mkl(a, reorder_output=True)
+        wg = orc.c_syrk(a, sort=True)
+        assert np.array_equal(g.indptr, wg.indptr) and np.array_equal(g.indices, wg.indices)
+        assert cs.rel_err(g.data, wg.data) <= cs.TOL[np.dtype(dtype)]
+    finally:
+        _lib.set_option("spgemm_wide", 0)
+
+
+def test_spgemm_duplicate_columns_in_b_rows_use_atomics():
+    """B rows with repeated column indices (not canonical): the warp bin must not take the plain read-modify-write."""
+    rng = np.random.default_rng(3)
+    a = sp.random(300, 200, density=0.05, format="csr", dtype=np.float64, random_state=5)
+    rows = np.repeat(np.arange(200), 6)
+    cols = rng.integers(0, 20, size=rows.shape[0])  # many duplicates inside a row
+    vals = rng.random(rows.shape[0]) + 0.5
+    order = np.lexsort((cols, rows))
+    indptr = np.arange(0, 200 * 6 + 1, 6)
+    b = sp.csr_matrix((vals[order], cols[order], indptr), shape=(200, 20))  # duplicates kept as stored
+    assert not b.has_canonical_format
+    got = sdb.dot_product_mkl(a, b, dense=True)
+    want = a.toarray() @ b.toarray()
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    c = sdb.dot_product_mkl(a, b, reorder_output=True)
+    assert np.abs(c.toarray() - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_options_reject_unknown_names():
+    with pytest.raises(ValueError, match="sdb_set_option returned 3"):
+        _lib.set_option("no_such_switch", 1)
