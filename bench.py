@@ -507,6 +507,14 @@ def run_ours(args):
         plan = None
         configs4 = run_configs4(args, torch, dist, sharded, sdb, world, rank, sync_all)
 
+    # ---- the sparse x sparse and gram products sharded over the same ranks (device-level exchange)
+    sharded_products = None
+    if world > 1 and not args.no_sharded_products:
+        if plan is not None:
+            plan.close()
+            plan = None
+        sharded_products = run_sharded_products(torch, dist, sharded, world, rank, sync_all)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -606,6 +614,7 @@ def run_ours(args):
         "parity_spot_check": check,
         "exchange": tuned,
         "configs4": configs4,
+        "sharded_products": sharded_products,
         "legs": legs,
         "version": sdb.get_version_string(),
     }
@@ -668,6 +677,57 @@ def run_configs4(args, torch, dist, sharded, sdb, world, rank, sync_all):
     })
     plan.close()
     return res
+
+
+def run_sharded_products(torch, dist, sharded, world, rank, sync_all):
+    """SURVEY.md §8e last row at this rank count: C = A @ B (R-MAT scale 20, edge factor 4, sorted output) with the
+    rows of A split across the ranks and the row blocks exchanged device to device, and the dense gram of
+    CSR(400k x 20k, 100 nnz/row) reduce-scattered onto panel owners.  Wall clock per call (max over ranks): uploads
+    of the operands, products, exchange.  Checked with the checksum of checksums / sampled entries."""
+    out = {}
+    try:
+        a = cs.rmat_csr(20, 4, np.float32, seed=1)
+        b = cs.rmat_csr(20, 4, np.float32, seed=2)
+        with sharded.spgemm_sharded_device(a, b, world, rank, reorder_output=True):
+            pass  # warm-up: memory pools, NCCL channels
+        sync_all()
+        t0 = time.perf_counter()
+        c = sharded.spgemm_sharded_device(a, b, world, rank, reorder_output=True)
+        dt = max_over_ranks(torch, dist, world, time.perf_counter() - t0)
+        with c:
+            total = float(c.values.sum(dtype=torch.float64).item())
+            colsum_a = np.bincount(a.indices, weights=a.data.astype(np.float64), minlength=a.shape[1])
+            rowsum_b = np.asarray(b.astype(np.float64).sum(axis=1)).ravel()
+            want = float(np.dot(colsum_a, rowsum_b))
+            srt = bool((torch.diff(c.indices.to(torch.int64)) > 0).sum().item() >= c.nnz - c.shape[0])
+            out["spgemm"] = {"workload": "R-MAT scale 20, edge factor 4, fp32, sorted; rows of A sharded, B replicated",
+                             "ms": dt * 1e3, "nnz_c": int(c.nnz), "total_rel_err": abs(total - want) / want,
+                             "rows_sorted": srt, "exchange": "NCCL broadcasts of the row blocks out of HBM"}
+    except Exception as e:
+        out["spgemm"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    try:
+        m = cs.uniform_rows_csr(400_000, 20_000, 100, np.float32, seed=4)
+        sharded.gram_dense_sharded(m, world, rank, gather=False)
+        sync_all()
+        t0 = time.perf_counter()
+        row0, panel = sharded.gram_dense_sharded(m, world, rank, gather=False)
+        dt = max_over_ranks(torch, dist, world, time.perf_counter() - t0)
+        # this rank's panel against a host recomputation of two of its rows
+        worst = 0.0
+        for r in (row0, row0 + panel.shape[0] - 1):
+            hits = np.flatnonzero(m.indices == r)
+            src = np.searchsorted(m.indptr, hits, side="right") - 1
+            want = np.asarray(m[src].astype(np.float64).T @ m.data[hits].astype(np.float64)).ravel()
+            got = panel[r - row0].astype(np.float64)
+            worst = max(worst, float(np.abs(got[r:] - want[r:]).max() / max(1e-30, np.abs(want[r:]).max())))
+            worst = max(worst, float(np.abs(got[:r]).max()) if r else 0.0)  # strict lower triangle is zero
+        out["gram"] = {"workload": "A^T A of CSR(400k x 20k, 100 nnz/row, fp32), dense upper; rows of A sharded",
+                       "ms": dt * 1e3, "panel_rows_of_this_rank": int(panel.shape[0]),
+                       "max_rel_err_over_ranks": max_over_ranks(torch, dist, world, worst),
+                       "exchange": "NCCL reduce of equal-area row panels onto their owners (reduce-scatter)"}
+    except Exception as e:
+        out["gram"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return out
 
 
 def load_run_configs():
@@ -752,6 +812,7 @@ def main():
     ap.add_argument("--legs", default="bsr16,spgemm_ef1,gram,spgemm_ef4")
     ap.add_argument("--legs-budget", type=float, default=400.0, help="seconds after which remaining legs are skipped")
     ap.add_argument("--c5", action="store_true", help="N > 1: also run BASELINE configs[4] (default at N = 8)")
+    ap.add_argument("--no-sharded-products", action="store_true", help="N > 1: skip the sharded SpGEMM / gram record")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -112,6 +112,13 @@ SDB_API sdb_status sdb_get_info(const sdb_mat* m, int* format, int* dtype,
 SDB_API sdb_status sdb_export(const sdb_mat* m, void* indptr, int indptr_bits,
                               void* indices, int indices_bits, void* values);
 
+/* The interior DEVICE pointers of a handle — what mkl_sparse_?_export_csr returns on the host
+ * (_common.py:442-451: pointers into MKL-owned memory, valid until destroy): int64 row offsets [major + 1],
+ * int32 indices [nnz], values [nnz * block^2].  Borrowed, valid until sdb_destroy / sdb_order.  Lets
+ * device-resident callers (the multi-GPU SpGEMM exchange over NCCL) move a result without a host round trip. */
+SDB_API sdb_status sdb_export_dev(const sdb_mat* m, const int64_t** d_indptr, const int32_t** d_indices,
+                                  const void** d_values);
+
 /* mkl_sparse_order (_common.py:683-692): ascending column order inside every
  * row (CSR) / column (CSC) / block row (BSR), values permuted along. */
 SDB_API sdb_status sdb_order(sdb_mat* m);
@@ -248,6 +255,20 @@ SDB_API sdb_status sdb_syrkd_dev(int op, const sdb_mat* A, const double* alpha,
                                  const double* beta, void* dC, int layout, int64_t ldc,
                                  void* stream);
 
+/* ======================= dense x dense (drop-in completeness) ============== */
+
+/* cblas_{s,d,c,z}gemm (_cfunctions.py:582-598 argtypes, called at _dense_dense.py:55-68) and
+ * cblas_{s,d,c,z}syrk (_cfunctions.py:652-668, called at _gram_matrix.py:233-245) for callers that hand
+ * dot_product_mkl / gram_matrix_mkl two dense arrays.  CBLAS integer codes: layout 101 / 102, transpose 111 /
+ * 112 / 113, uplo 121 (upper; the only one the reference uses).  HOST pointers; alpha / beta as {re, im}
+ * doubles; dtype SDB_F32..SDB_C128.  Not part of the sparse hot path: a plain tiled CUDA kernel, not a tuned
+ * GEMM.  sdb_syrk_dense writes only the upper triangle and leaves the rest of C as it was. */
+SDB_API sdb_status sdb_gemm(int layout, int transa, int transb, int64_t m, int64_t n, int64_t k,
+                            const double* alpha, const void* A, int64_t lda, const void* B, int64_t ldb,
+                            const double* beta, void* C, int64_t ldc, int dtype);
+SDB_API sdb_status sdb_syrk_dense(int layout, int uplo, int trans, int64_t n, int64_t k, const double* alpha,
+                                  const void* A, int64_t lda, const double* beta, void* C, int64_t ldc, int dtype);
+
 /* ======================= host-side helpers ================================= */
 
 /* nnz-balanced contiguous row blocks for the multi-GPU path:
@@ -289,6 +310,7 @@ SDB_API int        sdb_last_error(char* buf, int len);
  *   "spgemm_wide"   SDB_SPGEMM_WIDE    wide SpGEMM rows: 0 automatic, 1 full-sweep bitmap, 2 bitmap with summary
  *   "dense_mode"    SDB_DENSE_MODE     dense-output products: 0 automatic, 1 shared-memory tiles, 2 global reductions
  *   "dense_threads" SDB_DENSE_THREADS  threads per CTA of the global-reduction kernel (0 = default)
+ *   "dense_ctas"    SDB_DENSE_CTAS     resident CTAs per SM of that kernel (0 = as many as fit)
  * Unknown names return SDB_STATUS_INVALID_VALUE.  No reference counterpart (tuning aid for tests and sweeps). */
 SDB_API sdb_status sdb_set_option(const char* name, int value);
 

@@ -12,7 +12,7 @@
 #   benchN=<n>[,<extra args>]        torchrun with n ranks
 #   refarm                           bench.py --impl reference
 #   launches[=<bench args>]          ncu launch list (gpu__time_duration.sum) of a short bench run
-#   ncu=<kernel regex>,<name>[,<skip>[,<python script + args>]]   one `--set full` capture of the top kernel
+#   ncu=<kernel regex>,<name>[,<skip>[,<count>[,<python script + args>]]]   `--set full` capture of <count> launches
 #   configs=<run_configs.py args>    scripts/run_configs.py ...
 #   hashes                           SASS hashes of the profiled kernels (ties ncu bytes to this build)
 #   py=<script and args>             python <script and args>
@@ -53,8 +53,8 @@ for step in "$@"; do
         python ${arg:-$BENCH_SHORT} > $OUT/${TAG}_launches.log 2>&1
       tail -3 $OUT/${TAG}_launches.csv | cut -c1-300 ;;
     ncu)
-      IFS=, read -r regex nm skip cmd <<< "$arg"
-      timeout 1200 ncu --set full $NCU_COMMON --import-source on -k "regex:$regex" -s ${skip:-2} -c 1 -f \
+      IFS=, read -r regex nm skip count cmd <<< "$arg"
+      timeout 1200 ncu --set full $NCU_COMMON --import-source on -k "regex:$regex" -s ${skip:-2} -c ${count:-1} -f \
         -o $OUT/${TAG}_$nm python ${cmd:-$BENCH_SHORT} > $OUT/${TAG}_ncu_$nm.log 2>&1
       tail -2 $OUT/${TAG}_ncu_$nm.log ;;
     configs)

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "sdb_get_info": (_i32, [_vp, _ct.POINTER(_i32), _ct.POINTER(_i32), _ct.POINTER(_i64), _ct.POINTER(_i64),
                             _ct.POINTER(_i64), _ct.POINTER(_i64), _ct.POINTER(_i32)]),
     "sdb_export": (_i32, [_vp, _vp, _i32, _vp, _i32, _vp]),
+    "sdb_export_dev": (_i32, [_vp, _pvp, _pvp, _pvp]),
     "sdb_order": (_i32, [_vp]),
     "sdb_invalidate": (_i32, [_vp]),
     "sdb_convert_csr": (_i32, [_vp, _i32, _pvp]),
@@ -61,6 +62,8 @@ PROTOTYPES = {
     "sdb_syrkd": (_i32, [_i32, _vp, _pd, _pd, _vp, _i32, _i64]),
     "sdb_syrkd_new": (_i32, [_i32, _vp, _pd, _vp, _i32, _i64]),
     "sdb_syrkd_dev": (_i32, [_i32, _vp, _pd, _pd, _vp, _i32, _i64, _vp]),
+    "sdb_gemm": (_i32, [_i32, _i32, _i32, _i64, _i64, _i64, _pd, _vp, _i64, _vp, _i64, _pd, _vp, _i64, _i32]),
+    "sdb_syrk_dense": (_i32, [_i32, _i32, _i32, _i64, _i64, _pd, _vp, _i64, _pd, _vp, _i64, _i32]),
     "sdb_partition_rows": (_i32, [_vp, _i32, _i64, _i32, _ct.POINTER(_i64)]),
     "sdb_host_alloc": (_i32, [_pvp, _ct.c_size_t]),
     "sdb_host_free": (_i32, [_vp]),

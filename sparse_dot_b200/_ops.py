@@ -2,6 +2,8 @@
 Per-operation drivers: validate -> upload handle(s) -> ONE libsdb200 call ->
 download.  Each mirrors the behaviour of a reference driver:
 
+    dense_times_dense         _dense_dense.py:14-71     (_dense_matmul)
+    dot_dense_dense           _dense_dense.py:74-88     (_dense_dot_dense)
     sparse_times_dense        _sparse_dense.py:34-132   (_sparse_dense_matmul)
     dot_sparse_dense          _sparse_dense.py:135-208  (_sparse_dot_dense)
     sparse_times_vector       _sparse_vector.py:28-102  (_sparse_dense_vector_mult)
@@ -112,6 +114,42 @@ def dot_sparse_dense(a, b, cast=False, scalar=1.0, out=None, out_scalar=None):
         sparse_times_dense(b, a.T, scalar=scalar, transpose=True, out=out.T, out_scalar=out_scalar, out_t=True)
         return out
     return sparse_times_dense(b, a.T, scalar=scalar, transpose=True).T
+
+
+# ---------------------------------------------------------------- dense x dense
+_CBLAS_NOTRANS, _CBLAS_TRANS, _CBLAS_UPPER = 111, 112, 121
+
+
+def dense_times_dense(a, b, scalar=1.0, out=None, out_scalar=None):
+    """cblas_?gemm as the reference drives it (_dense_dense.py:14-71): the result takes A's memory order, B is
+    passed as transposed when its order differs, a 1-d B is a column and the result is flattened."""
+    dbl, cplx = _v.precision_flags(a)
+    flatten = b.ndim == 1
+    b = b.reshape(-1, 1) if flatten else b
+    m, n, k = a.shape[0], b.shape[1], a.shape[1]
+    layout_a, lda = _v.dense_layout(a)
+    layout_b, ldb = _v.dense_layout(b)
+    op_b = _CBLAS_TRANS if layout_b != layout_a else _CBLAS_NOTRANS
+    order, ldc = ("C", n) if layout_a == _lib.LAYOUT_C else ("F", m)
+    result = _v.output_array((m, n), _v.OUTPUT_DTYPES[(dbl, cplx)], order, out=out, zero=False)
+    beta = 0.0 if out is None else (1.0 if out_scalar is None else out_scalar)
+    check(
+        SDB.lib.sdb_gemm(layout_a, _CBLAS_NOTRANS, op_b, m, n, k, scalar_pair(1.0 if scalar is None else scalar),
+                         _ptr(a), lda, _ptr(b), ldb, scalar_pair(beta), _ptr(result), ldc,
+                         _h._DTYPE_CODE[np.dtype(a.dtype)]),
+        "sdb_gemm",
+    )
+    return result.ravel() if flatten else result
+
+
+def dot_dense_dense(a, b, cast=False, scalar=1.0, out=None, out_scalar=None):
+    _v.check_shapes(a, b, allow_vector=True)
+    if _v.product_is_empty(a, b):
+        _v.debug_print("Skipping multiplication because A (dot) B must yield an empty matrix")
+        both_f32 = a.dtype == b.dtype and a.dtype == np.float32
+        return _v.output_array((a.shape[0], b.shape[1]), np.float32 if both_f32 else np.float64, out=out)
+    a, b = _v.unify_dtypes(a, b, cast=cast)
+    return dense_times_dense(a, b, scalar=scalar, out=out, out_scalar=out_scalar)
 
 
 # ---------------------------------------------------------------- sparse x vector
@@ -239,6 +277,23 @@ def _gram_sparse_to_dense(a, aat=False, scalar=1.0, out=None, out_scalar=None):
     return result
 
 
+def _gram_dense_to_dense(a, aat=False, scalar=1.0, out=None, out_scalar=None):
+    """cblas_?syrk on a dense array (_gram_matrix.py:196-249): upper triangle of A^T A (or A A^T) in A's memory
+    order; a fresh result has zeros below the diagonal, a given ``out`` keeps what it had there."""
+    n, k = a.shape if aat else a.shape[::-1]
+    layout, lda = _v.dense_layout(a)
+    dbl, cplx = _v.precision_flags(a)
+    result = _v.output_array((n, n), _v.OUTPUT_DTYPES[(dbl, cplx)], "C" if layout == _lib.LAYOUT_C else "F", out=out)
+    beta = 0.0 if out is None else (1.0 if out_scalar is None else out_scalar)
+    check(
+        SDB.lib.sdb_syrk_dense(layout, _CBLAS_UPPER, _CBLAS_NOTRANS if aat else _CBLAS_TRANS, n, k,
+                               scalar_pair(1.0 if scalar is None else scalar), _ptr(a), lda, scalar_pair(beta),
+                               _ptr(result), n, _h._DTYPE_CODE[np.dtype(a.dtype)]),
+        "sdb_syrk_dense",
+    )
+    return result
+
+
 def gram(matrix, transpose=False, cast=False, dense=False, reorder_output=False, out=None, out_scalar=None):
     if _v.product_is_empty(matrix, matrix):
         _v.debug_print("Skipping multiplication because AT (dot) A must yield an empty matrix")
@@ -254,10 +309,7 @@ def gram(matrix, transpose=False, cast=False, dense=False, reorder_output=False,
     if _v.is_csc(matrix) and not cast:
         raise ValueError("gram_matrix cannot use a CSC matrix unless cast=True")
     if not sps.issparse(matrix):
-        raise NotImplementedError(
-            "gram_matrix_mkl on a dense array is a dense BLAS syrk, outside the sparse hot path this "
-            "backend covers (SURVEY.md §2 row 5); use numpy / torch for it"
-        )
+        return _gram_dense_to_dense(matrix, aat=transpose, out=out, out_scalar=out_scalar)
     if dense:
         return _gram_sparse_to_dense(matrix, aat=transpose, out=out, out_scalar=out_scalar)
     if out is not None:

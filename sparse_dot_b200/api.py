@@ -69,10 +69,13 @@ def dot_product_mkl(matrix_a, matrix_b, cast=False, copy=True, reorder_output=Fa
         if a_is_row_vec or b_is_col_vec:
             return _ops.dot_sparse_vector(matrix_a, matrix_b, cast=cast, out=out, out_scalar=out_scalar)
         return _ops.dot_sparse_dense(matrix_a, matrix_b, cast=cast, out=out, out_scalar=out_scalar)
-    raise NotImplementedError(
-        "dot_product_mkl with two dense operands is a dense GEMM, outside the sparse hot path this "
-        "backend covers (SURVEY.md §2 row 7); use numpy / torch for it"
-    )
+    # two dense operands: vector (dot) vector is numpy's, as in the reference (sparse_dot.py:134-143); anything
+    # else is one dense GEMM on the GPU (a plain tiled kernel: outside the sparse hot path, there for drop-in use)
+    if _is_vec(matrix_a) and _is_vec(matrix_b) and (matrix_a.ndim == 1 or matrix_b.ndim == 1):
+        if out_scalar is not None:
+            out *= out_scalar
+        return _np.dot(matrix_a, matrix_b, out=out)
+    return _ops.dot_dense_dense(matrix_a, matrix_b, cast=cast, out=out, out_scalar=out_scalar)
 
 
 def gram_matrix_mkl(matrix, transpose=False, cast=False, dense=False, debug=False, reorder_output=False,

@@ -65,6 +65,7 @@ enum Option {
     kOptSpgemmWide,     // "spgemm_wide"   SDB_SPGEMM_WIDE    wide SpGEMM rows: 0 auto, 1 full-sweep bitmap, 2 summary
     kOptDenseMode,      // "dense_mode"    SDB_DENSE_MODE     dense-output products: 0 auto, 1 shared tiles, 2 global reductions
     kOptDenseThreads,   // "dense_threads" SDB_DENSE_THREADS  threads per CTA of the global-reduction kernel (0 = 1024)
+    kOptDenseCtas,      // "dense_ctas"    SDB_DENSE_CTAS     resident CTAs per SM of that kernel (0 = what fits)
     kOptCount
 };
 int get_option(Option o);

@@ -217,6 +217,16 @@ sdb_status sdb_get_info(const sdb_mat* m, int* format, int* dtype, int64_t* rows
     return SDB_STATUS_SUCCESS;
 }
 
+sdb_status sdb_export_dev(const sdb_mat* m, const int64_t** d_indptr, const int32_t** d_indices,
+                          const void** d_values) {
+    SDB_REQUIRE(m != nullptr, SDB_STATUS_NOT_INITIALIZED, "export_dev: null handle");
+    SDB_REQUIRE(valid(m), SDB_STATUS_INVALID_VALUE, "export_dev: not a live sdb_mat handle");
+    if (d_indptr) *d_indptr = m->indptr;
+    if (d_indices) *d_indices = m->indices;
+    if (d_values) *d_values = m->values;
+    return SDB_STATUS_SUCCESS;
+}
+
 sdb_status sdb_export(const sdb_mat* m, void* indptr, int indptr_bits, void* indices, int indices_bits,
                       void* values) {
     SDB_REQUIRE(m != nullptr, SDB_STATUS_NOT_INITIALIZED, "export: null handle");

@@ -361,47 +361,75 @@ SHIM_API void MKL_Get_Version_String(char* buf, int len) {
 }
 SHIM_API void mkl_free_buffers(void) {}
 
-// ------------------------------------------------------------------ bound by the reference, out of scope here
-SHIM_API void cblas_sgemm(int, int, int, MKL_INT m, MKL_INT n, MKL_INT, float, const float*, MKL_INT, const float*,
-                          MKL_INT, float, float* c, MKL_INT) {
-    unsupported("cblas_sgemm");
-    poison(c, (long long)m * n);
+// ------------------------------------------------------------------ cblas gemm / syrk (dense x dense callers)
+// void functions in CBLAS: a failure cannot be returned, so it is reported on stderr and the output is poisoned
+// with NaNs rather than left looking plausible.
+namespace {
+void gemm_any(const char* who, int dtype, int layout, int ta, int tb, MKL_INT m, MKL_INT n, MKL_INT k, double ar,
+              double ai, const void* a, MKL_INT lda, const void* b, MKL_INT ldb, double br, double bi, void* c,
+              MKL_INT ldc) {
+    const double alpha[2] = {ar, ai}, beta[2] = {br, bi};
+    if (sdb_gemm(layout, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, dtype) != SDB_STATUS_SUCCESS) {
+        unsupported(who);
+        const long long per = dtype == SDB_C64 || dtype == SDB_C128 ? 2 : 1;
+        if (dtype == SDB_F32 || dtype == SDB_C64) poison(static_cast<float*>(c), per * m * n);
+        else poison(static_cast<double*>(c), per * m * n);
+    }
 }
-SHIM_API void cblas_dgemm(int, int, int, MKL_INT m, MKL_INT n, MKL_INT, double, const double*, MKL_INT, const double*,
-                          MKL_INT, double, double* c, MKL_INT) {
-    unsupported("cblas_dgemm");
-    poison(c, (long long)m * n);
+void syrk_any(const char* who, int dtype, int layout, int uplo, int trans, MKL_INT n, MKL_INT k, double ar, double ai,
+              const void* a, MKL_INT lda, double br, double bi, void* c, MKL_INT ldc) {
+    const double alpha[2] = {ar, ai}, beta[2] = {br, bi};
+    if (sdb_syrk_dense(layout, uplo, trans, n, k, alpha, a, lda, beta, c, ldc, dtype) != SDB_STATUS_SUCCESS) {
+        unsupported(who);
+        const long long per = dtype == SDB_C64 || dtype == SDB_C128 ? 2 : 1;
+        if (dtype == SDB_F32 || dtype == SDB_C64) poison(static_cast<float*>(c), per * n * n);
+        else poison(static_cast<double*>(c), per * n * n);
+    }
 }
-SHIM_API void cblas_cgemm(int, int, int, MKL_INT m, MKL_INT n, MKL_INT, const void*, const void*, MKL_INT, const void*,
-                          MKL_INT, const void*, void* c, MKL_INT) {
-    unsupported("cblas_cgemm");
-    poison(static_cast<float*>(c), 2LL * m * n);
+}  // namespace
+
+SHIM_API void cblas_sgemm(int layout, int ta, int tb, MKL_INT m, MKL_INT n, MKL_INT k, float alpha, const float* a,
+                          MKL_INT lda, const float* b, MKL_INT ldb, float beta, float* c, MKL_INT ldc) {
+    gemm_any("cblas_sgemm", SDB_F32, layout, ta, tb, m, n, k, alpha, 0, a, lda, b, ldb, beta, 0, c, ldc);
 }
-SHIM_API void cblas_zgemm(int, int, int, MKL_INT m, MKL_INT n, MKL_INT, const void*, const void*, MKL_INT, const void*,
-                          MKL_INT, const void*, void* c, MKL_INT) {
-    unsupported("cblas_zgemm");
-    poison(static_cast<double*>(c), 2LL * m * n);
+SHIM_API void cblas_dgemm(int layout, int ta, int tb, MKL_INT m, MKL_INT n, MKL_INT k, double alpha, const double* a,
+                          MKL_INT lda, const double* b, MKL_INT ldb, double beta, double* c, MKL_INT ldc) {
+    gemm_any("cblas_dgemm", SDB_F64, layout, ta, tb, m, n, k, alpha, 0, a, lda, b, ldb, beta, 0, c, ldc);
 }
-SHIM_API void cblas_ssyrk(int, int, int, MKL_INT n, MKL_INT, float, const float*, MKL_INT, float, float* c, MKL_INT) {
-    unsupported("cblas_ssyrk");
-    poison(c, (long long)n * n);
+SHIM_API void cblas_cgemm(int layout, int ta, int tb, MKL_INT m, MKL_INT n, MKL_INT k, const void* alpha, const void* a,
+                          MKL_INT lda, const void* b, MKL_INT ldb, const void* beta, void* c, MKL_INT ldc) {
+    const float* al = static_cast<const float*>(alpha);
+    const float* be = static_cast<const float*>(beta);
+    gemm_any("cblas_cgemm", SDB_C64, layout, ta, tb, m, n, k, al[0], al[1], a, lda, b, ldb, be[0], be[1], c, ldc);
 }
-SHIM_API void cblas_dsyrk(int, int, int, MKL_INT n, MKL_INT, double, const double*, MKL_INT, double, double* c,
-                          MKL_INT) {
-    unsupported("cblas_dsyrk");
-    poison(c, (long long)n * n);
+SHIM_API void cblas_zgemm(int layout, int ta, int tb, MKL_INT m, MKL_INT n, MKL_INT k, const void* alpha, const void* a,
+                          MKL_INT lda, const void* b, MKL_INT ldb, const void* beta, void* c, MKL_INT ldc) {
+    const double* al = static_cast<const double*>(alpha);
+    const double* be = static_cast<const double*>(beta);
+    gemm_any("cblas_zgemm", SDB_C128, layout, ta, tb, m, n, k, al[0], al[1], a, lda, b, ldb, be[0], be[1], c, ldc);
 }
-SHIM_API void cblas_csyrk(int, int, int, MKL_INT n, MKL_INT, const void*, const void*, MKL_INT, const void*, void* c,
-                          MKL_INT) {
-    unsupported("cblas_csyrk");
-    poison(static_cast<float*>(c), 2LL * n * n);
+SHIM_API void cblas_ssyrk(int layout, int uplo, int trans, MKL_INT n, MKL_INT k, float alpha, const float* a,
+                          MKL_INT lda, float beta, float* c, MKL_INT ldc) {
+    syrk_any("cblas_ssyrk", SDB_F32, layout, uplo, trans, n, k, alpha, 0, a, lda, beta, 0, c, ldc);
 }
-SHIM_API void cblas_zsyrk(int, int, int, MKL_INT n, MKL_INT, const void*, const void*, MKL_INT, const void*, void* c,
-                          MKL_INT) {
-    unsupported("cblas_zsyrk");
-    poison(static_cast<double*>(c), 2LL * n * n);
+SHIM_API void cblas_dsyrk(int layout, int uplo, int trans, MKL_INT n, MKL_INT k, double alpha, const double* a,
+                          MKL_INT lda, double beta, double* c, MKL_INT ldc) {
+    syrk_any("cblas_dsyrk", SDB_F64, layout, uplo, trans, n, k, alpha, 0, a, lda, beta, 0, c, ldc);
+}
+SHIM_API void cblas_csyrk(int layout, int uplo, int trans, MKL_INT n, MKL_INT k, const void* alpha, const void* a,
+                          MKL_INT lda, const void* beta, void* c, MKL_INT ldc) {
+    const float* al = static_cast<const float*>(alpha);
+    const float* be = static_cast<const float*>(beta);
+    syrk_any("cblas_csyrk", SDB_C64, layout, uplo, trans, n, k, al[0], al[1], a, lda, be[0], be[1], c, ldc);
+}
+SHIM_API void cblas_zsyrk(int layout, int uplo, int trans, MKL_INT n, MKL_INT k, const void* alpha, const void* a,
+                          MKL_INT lda, const void* beta, void* c, MKL_INT ldc) {
+    const double* al = static_cast<const double*>(alpha);
+    const double* be = static_cast<const double*>(beta);
+    syrk_any("cblas_zsyrk", SDB_C128, layout, uplo, trans, n, k, al[0], al[1], a, lda, be[0], be[1], c, ldc);
 }
 
+// ------------------------------------------------------------------ bound by the reference, out of scope here
 SHIM_API int mkl_sparse_qr_reorder(void*, matrix_descr) { return SDB_STATUS_NOT_SUPPORTED; }
 SHIM_API int mkl_sparse_d_qr_factorize(void*, double*) { return SDB_STATUS_NOT_SUPPORTED; }
 SHIM_API int mkl_sparse_s_qr_factorize(void*, float*) { return SDB_STATUS_NOT_SUPPORTED; }

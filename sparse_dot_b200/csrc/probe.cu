@@ -91,11 +91,20 @@ static sdb_status probe_host_copy(int64_t bytes, int iters, double* gbs) {
     }
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     *gbs = double(iters) * double(bytes) / sec / 1e9;
+    // the copies are checked too: an odd-sized, misaligned piece and the last full slot
+    bool ok = true;
+    {
+        const size_t odd = (size_t(5) << 20) + 12345;
+        for (size_t i = 0; i < odd; ++i) src[7 + i] = char(i * 131u + (i >> 9));
+        host_copy(static_cast<char*>(slots[1]) + 3, src + 7, odd);
+        ok = memcmp(static_cast<char*>(slots[1]) + 3, src + 7, odd) == 0;
+    }
     for (auto& p : slots) {
         if (pinned) cudaFreeHost(p);
         else free(p);
     }
     free(src);
+    SDB_REQUIRE(ok, SDB_STATUS_INTERNAL_ERROR, "probe: the copy pool produced a wrong copy");
     return SDB_STATUS_SUCCESS;
 }
 

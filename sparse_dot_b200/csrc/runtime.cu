@@ -1,6 +1,10 @@
 // runtime.cu — host runtime of libsdb200: error plumbing, per-thread context,
 // stream-ordered memory, pinned staging copies, phase timers and the small
 // host-only ABI entry points (version string, device selection, row partitioner).
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
@@ -74,6 +78,7 @@ OptionSlot g_options[kOptCount] = {
     {"spgemm_wide", "SDB_SPGEMM_WIDE", 0, {0}, {false}},
     {"dense_mode", "SDB_DENSE_MODE", 0, {0}, {false}},
     {"dense_threads", "SDB_DENSE_THREADS", 0, {0}, {false}},
+    {"dense_ctas", "SDB_DENSE_CTAS", 0, {0}, {false}},
 };
 }  // namespace
 
@@ -167,6 +172,48 @@ bool is_pinned(const void* p) {
 // sides of sdb_spmm_csr_host do).
 namespace {
 
+// One piece of a staged copy.  The destination is either a page-locked slot the DMA engine reads next or the
+// caller's array after a download: in both cases nothing on this core re-reads it soon, so it is written with
+// non-temporal stores (no read-for-ownership of the destination lines: 2 bytes of memory traffic per byte
+// copied instead of 3).  glibc's memcpy only does that above a threshold far larger than a piece.
+void stream_copy(char* dst, const char* src, size_t bytes) {
+#if defined(__SSE2__)
+    // head up to 16-byte alignment of the destination
+    size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+    if (head > bytes) head = bytes;
+    memcpy(dst, src, head);
+    dst += head;
+    src += head;
+    bytes -= head;
+    size_t blocks = bytes / 64;
+    for (size_t i = 0; i < blocks; ++i) {
+        __builtin_prefetch(src + 512);
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 32));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + 48), d);
+        src += 64;
+        dst += 64;
+    }
+    _mm_sfence();
+    memcpy(dst, src, bytes - blocks * 64);
+#else
+    memcpy(dst, src, bytes);
+#endif
+}
+
+bool use_stream_copy() {
+    static const bool v = [] {
+        const char* e = getenv("SDB_COPY_NT");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
+
 class CopyPool {
   public:
     static CopyPool& get() {
@@ -180,7 +227,8 @@ class CopyPool {
             return size_t(kb >= 64 && kb <= (1 << 20) ? kb : 1024) << 10;
         }();
         if (bytes < 2 * kPiece || workers_ == 0) {
-            memcpy(dst, src, bytes);
+            if (use_stream_copy() && bytes >= (size_t(256) << 10)) stream_copy(static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+            else memcpy(dst, src, bytes);
             return;
         }
         Job job;
@@ -235,7 +283,9 @@ class CopyPool {
     }
     void copy_piece(Job* job, size_t idx) {
         const size_t off = idx * job->piece;
-        memcpy(job->dst + off, job->src + off, std::min(job->piece, job->bytes - off));
+        const size_t len = std::min(job->piece, job->bytes - off);
+        if (use_stream_copy()) stream_copy(job->dst + off, job->src + off, len);
+        else memcpy(job->dst + off, job->src + off, len);
         std::lock_guard<std::mutex> lk(m_);
         if (++job->finished == job->n_pieces) job->done_cv.notify_all();  // `job` must not be touched after this
     }

@@ -736,11 +736,14 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
         SDB_TRY(bm.alloc(size_t(ctas * words) * 4, s));
         SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(ctas * words) * 4, s));
         if (NUMERIC) SDB_TRY(ranks.alloc(size_t(ctas * words) * 4, s));
-        // summary formulation while its shared-memory index fits beside two CTAs per SM (SDB_SPGEMM_WIDE=1: first version)
+        // The summary formulation is opt-in ("spgemm_wide" = 2): measured on R-MAT scale 22 (profiles/r2_logs/
+        // spgemm_trace_ef1*.log) it is SLOWER than the full sweeps (symbolic 15.3 vs 7.1 ms, numeric 35.0 vs 25.5 ms):
+        // the per-row cost is the latency of the sweep iterations, not their DRAM traffic, and a warp walking 32-word
+        // groups makes four times as many dependent iterations as one loading 128-word pieces.
         const int forced = get_option(kOptSpgemmWide);
         const int64_t n_groups = words / 32;
         const size_t smem2 = size_t(n_groups) * 12;
-        if (forced != 1 && smem2 <= size_t(96) * 1024) {
+        if (forced == 2 && smem2 <= size_t(96) * 1024) {
             auto kernel = spgemm_wide2_kernel<T, NUMERIC>;
             SDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem2, 48 * 1024))));
             SDB_LAUNCH(kernel, unsigned(ctas), 1024, smem2, s, lists.list[3], h[3], words, int(n_groups), lp, li, lv, lq,
@@ -899,7 +902,11 @@ __global__ void __launch_bounds__(kDenseMaxThreads)
                             const T* __restrict__ r_val, bool upper, bool zero_lower, T alpha, T beta,
                             T* __restrict__ C, int64_t ldc, bool col_major) {
     const int nthreads = blockDim.x;
-    const int64_t i = blockIdx.x;
+    // Triangular results: row i owns n - i columns.  CTAs are scheduled in blockIdx order, so pairing the longest
+    // rows with the shortest (0, m-1, 1, m-2, ...) keeps the set of accumulator rows resident at any moment at
+    // about (resident CTAs) x (half a row) — they are the working set the global reductions must find in L2.
+    const int64_t b = blockIdx.x, m_rows = gridDim.x;
+    const int64_t i = upper ? ((b & 1) ? m_rows - 1 - (b >> 1) : (b >> 1)) : b;
     const int64_t base = upper ? i : 0;
     const int64_t row_stride = col_major ? 1 : ldc, col_stride = col_major ? ldc : 1;
     T* crow = C + i * row_stride;
@@ -975,7 +982,15 @@ sdb_status spgemm_dense_device(Context* ctx, cudaStream_t s, const CsrView& l, c
         return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
             int threads = get_option(kOptDenseThreads);
             threads = threads >= 64 && threads <= 1024 ? threads / 32 * 32 : 1024;
-            SDB_LAUNCH(spgemm_dense_red_kernel<T>, unsigned(m), threads, 0, s, n, l.indptr, l.indices,
+            // "dense_ctas" caps the resident CTAs per SM by asking for shared memory the kernel does not use
+            const int cap = get_option(kOptDenseCtas);
+            size_t pad = 0;
+            if (cap >= 1 && cap <= 8) {
+                pad = size_t(200) * 1024 / size_t(cap);
+                SDB_CUDA(cudaFuncSetAttribute(spgemm_dense_red_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              int(pad)));
+            }
+            SDB_LAUNCH(spgemm_dense_red_kernel<T>, unsigned(m), threads, pad, s, n, l.indptr, l.indices,
                        static_cast<const T*>(l.values), upper ? l.pos : nullptr, r.indptr, r.indices,
                        static_cast<const T*>(r.values), upper, zero_lower, Num<T>::make(alpha[0], alpha[1]),
                        Num<T>::make(beta[0], beta[1]), static_cast<T*>(dC), ldc, col_major);

@@ -192,7 +192,7 @@ static sdb_status launch_bsr_s(cudaStream_t s, const sdb_mat* a, const T* X, int
 // Ring depth: short block rows (a handful of blocks) finish before a deep ring pays off and a shallow
 // ring lets more CTAs share the SM; long block rows want the deeper prefetch.
 static int ring_depth(const sdb_mat* a);
-constexpr bool kBsrMmaByDefault = false;  // flipped by measurement
+constexpr int64_t kBsrMmaFromBlock = 32;  // smallest block size that takes the tensor-core kernel by default
 
 template <typename T, int B, int CW>
 static sdb_status launch_bsr(cudaStream_t s, const sdb_mat* a, const T* X, int64_t ldx, int64_t n, T alpha, T beta,
@@ -236,8 +236,12 @@ static int ring_depth(const sdb_mat* a) {
 sdb_status spmm_bsr_device(cudaStream_t s, const sdb_mat* a, const double* alpha, const double* beta, const void* dX,
                            int64_t n, int64_t ldx, void* dY, int64_t ldy) {
     // tensor cores (spmm_bsr_mma.cu) when switched on and the shape is covered; see DESIGN.md K2 for the measurements
+    // Automatic rule, from profiles/r2_bsr_mma_table.json: with 16 x 16 blocks the FMA kernel is already at the HBM
+    // roof (fp64 0.93 of peak either way; fp32 0.94 ms against 1.09 ms with 3xTF32, whose operand splits cost more
+    // than the MMAs save) and 8 x 8 blocks half-fill an m16 tile; with 32 x 32 blocks the FMA loop is compute-bound
+    // and the tensor cores win (fp64 5.8 vs 7.7 ms, fp32 3.3 vs 3.6 ms at N = 512).
     const int mma = get_option(kOptBsrMma);
-    if ((mma == 1 || (mma < 0 && kBsrMmaByDefault)) && spmm_bsr_mma_supported(a, n))
+    if ((mma == 1 || (mma < 0 && a->block >= kBsrMmaFromBlock)) && spmm_bsr_mma_supported(a, n))
         return spmm_bsr_mma_device(s, a, alpha, beta, dX, n, ldx, dY, ldy, ring_depth(a));
 #define SDB_BSR_CASE(T, B)                                                                                    \
     return pick_cw<T, B>(s, a, static_cast<const T*>(dX), ldx, n, Num<T>::make(alpha[0], alpha[1]),           \

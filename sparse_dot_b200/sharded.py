@@ -307,12 +307,135 @@ def spmm_sharded(a_csr, x, world_size, rank, allgather="fused", group=None, out=
 
 
 # --------------------------------------------------------------------------- SpGEMM / gram sharding
+def _is_nccl(world_size, group):
+    if world_size == 1:
+        return False
+    import torch.distributed as dist
+
+    return dist.get_backend(group) == "nccl"
+
+
+class ShardedCSR:
+    """A CSR product assembled from the ranks' row blocks and replicated in the HBM of every rank: three torch CUDA
+    tensors (int64 row offsets, int32 columns, values) plus a borrowed-array handle over them, so it can be
+    multiplied again without leaving the GPU.  ``to_scipy()`` brings it to the host."""
+
+    def __init__(self, indptr, indices, values, shape):
+        self.indptr, self.indices, self.values, self.shape = indptr, indices, values, tuple(shape)
+        self.nnz = int(indices.shape[0])
+        self.dtype = np.dtype(str(values.dtype).replace("torch.", ""))
+        ref = _ct.c_void_p()
+        check(
+            SDB.lib.sdb_create_csr_dev(_ct.byref(ref), self.shape[0], self.shape[1], self.nnz,
+                                       _ct.c_void_p(indptr.data_ptr()), _ct.c_void_p(indices.data_ptr()),
+                                       _ct.c_void_p(values.data_ptr()), _h._DTYPE_CODE[self.dtype]),
+            "sdb_create_csr_dev",
+        )
+        self.handle = _h.Handle(ref, self.dtype)
+
+    def to_scipy(self):
+        import scipy.sparse as sps
+
+        indptr = self.indptr.cpu().numpy()
+        it = np.int32 if self.nnz <= np.iinfo(np.int32).max else np.int64
+        return sps.csr_matrix((self.values.cpu().numpy(), self.indices.cpu().numpy().astype(it, copy=False),
+                               indptr.astype(it)), shape=self.shape)
+
+    def close(self):
+        if self.handle:
+            self.handle.destroy()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+def _device_arrays(handle, rows, nnz, dtype):
+    """torch views (no copy) of a handle's interior device arrays (sdb_export_dev)."""
+    import torch
+
+    p_ptr, p_idx, p_val = _ct.c_void_p(), _ct.c_void_p(), _ct.c_void_p()
+    check(SDB.lib.sdb_export_dev(handle.ref, _ct.byref(p_ptr), _ct.byref(p_idx), _ct.byref(p_val)), "sdb_export_dev")
+    indptr = torch.as_tensor(_CudaView(p_ptr.value, (rows + 1,), np.int64), device="cuda")
+    if nnz == 0:
+        return indptr, None, None
+    indices = torch.as_tensor(_CudaView(p_idx.value, (nnz,), np.int32), device="cuda")
+    values = torch.as_tensor(_CudaView(p_val.value, (nnz,), dtype), device="cuda")
+    return indptr, indices, values
+
+
+def spgemm_sharded_device(a_csr, b_csr, world_size, rank, group=None, reorder_output=False):
+    """C = A @ B with the rows of A split nnz-balanced across ranks and B replicated, entirely on the devices:
+    every rank multiplies its row block (sdb_spgemm / sdb_spgemm_ordered; the block stays in HBM), the ranks
+    exchange the block sizes (two integers each) and then the blocks themselves with NCCL broadcasts straight out
+    of the handles' device arrays into the replicated result — no pickling, no host staging.  Returns a
+    ShardedCSR on every rank.  Needs an NCCL process group (or world_size 1)."""
+    import torch
+    import torch.distributed as dist
+
+    bounds = partition_rows(a_csr.indptr, world_size)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    dtype = np.dtype(a_csr.dtype)
+    tdtype = getattr(torch, dtype.name)
+    n_cols = b_csr.shape[1]
+    block = row_block(a_csr, lo, hi)
+    hc = None
+    if hi > lo and block.nnz > 0 and b_csr.nnz > 0:
+        ha, _, _ = _h.create(block)
+        hb, _, _ = _h.create(b_csr)
+        with ha, hb:
+            ref = _ct.c_void_p()
+            fn = "sdb_spgemm_ordered" if reorder_output else "sdb_spgemm"
+            check(getattr(SDB.lib, fn)(_lib.OP_N, ha.ref, hb.ref, _ct.byref(ref)), fn)
+            hc = _h.Handle(ref, dtype)
+    try:
+        my_nnz = _h.info(hc)["nnz"] if hc else 0
+        sizes = _all_gather_obj((hi - lo, my_nnz), world_size, group)
+        rows_total = sum(r for r, _ in sizes)
+        nnz_total = sum(z for _, z in sizes)
+        row_off = np.cumsum([0] + [r for r, _ in sizes])
+        nnz_off = np.cumsum([0] + [z for _, z in sizes])
+        indptr = torch.zeros(rows_total + 1, dtype=torch.int64, device="cuda")
+        indices = torch.empty(nnz_total, dtype=torch.int32, device="cuda")
+        values = torch.empty(nnz_total, dtype=tdtype, device="cuda")
+        if hc:
+            d_ptr, d_idx, d_val = _device_arrays(hc, hi - lo, my_nnz, dtype)
+            indptr[row_off[rank] + 1: row_off[rank + 1] + 1] = d_ptr[1:] + int(nnz_off[rank])
+            if my_nnz:
+                indices[nnz_off[rank]: nnz_off[rank + 1]] = d_idx
+                values[nnz_off[rank]: nnz_off[rank + 1]] = d_val
+        else:
+            indptr[row_off[rank] + 1: row_off[rank + 1] + 1] = int(nnz_off[rank])
+        torch.cuda.synchronize()
+        if world_size > 1:
+            for q in range(world_size):  # exact-size broadcasts: the blocks differ in size
+                r0, r1, z0, z1 = int(row_off[q]), int(row_off[q + 1]), int(nnz_off[q]), int(nnz_off[q + 1])
+                if r1 > r0:
+                    dist.broadcast(indptr[r0 + 1: r1 + 1], src=dist.get_global_rank(group, q) if group else q, group=group)
+                if z1 > z0:
+                    src = dist.get_global_rank(group, q) if group else q
+                    dist.broadcast(indices[z0:z1], src=src, group=group)
+                    dist.broadcast(values[z0:z1], src=src, group=group)
+            torch.cuda.synchronize()
+    finally:
+        if hc:
+            hc.destroy()
+    return ShardedCSR(indptr, indices, values, (rows_total, n_cols))
+
+
 def spgemm_sharded(a_csr, b_csr, world_size, rank, group=None, reorder_output=False):
-    """C = A @ B with the rows of A split nnz-balanced across ranks and B replicated: every rank multiplies
-    its row block on its GPU (dot_product_mkl -> sdb_spgemm), the blocks are independent CSR row ranges, so
-    the only exchange is an all-gather of the finished blocks, which are stacked (row offsets shifted) on
-    the host.  Every rank returns the full product."""
+    """C = A @ B with the rows of A split nnz-balanced across ranks and B replicated; every rank returns the full
+    product as a scipy matrix.  With an NCCL group the blocks travel device to device (spgemm_sharded_device);
+    otherwise (gloo on CPU-only test hosts) every rank multiplies its block through dot_product_mkl and the
+    finished blocks are gathered and stacked on the host."""
     import scipy.sparse as sps
+
+    if _is_nccl(world_size, group):
+        with spgemm_sharded_device(a_csr, b_csr, world_size, rank, group, reorder_output) as c:
+            return c.to_scipy()
 
     from .api import dot_product_mkl
 
@@ -340,51 +463,75 @@ def stack_row_blocks(blocks, n_cols):
     return sps.csr_matrix((data, indices.astype(it, copy=False), indptr.astype(it)), shape=(rows, n_cols))
 
 
-def gram_dense_sharded(a_csr, world_size, rank, group=None):
-    """Dense upper triangle of A^T A with the ROWS of A split across ranks: A^T A = sum over row blocks of
-    A_s^T A_s, so every rank forms the partial gram of its block on its GPU (sdb_syrkd_dev, device
-    resident) and the partial panels are summed with one all-reduce — NCCL on the device panels when the
-    process group is NCCL, otherwise on host copies.  Every rank returns the full n x n array."""
-    from . import _handles as _h2
+def triangle_row_bounds(n, parts):
+    """Row ranges of an n x n upper triangle with about equal AREA: bounds[p] is the first row of owner p
+    (rows near the top are longer, so the top owners get fewer rows)."""
+    total = n * (n + 1) / 2.0
+    bounds = [0]
+    for p in range(1, parts):
+        # rows [0, r) hold r * n - r (r - 1) / 2 entries; solve for the target share
+        target = total * p / parts
+        r = int(round((2 * n + 1 - np.sqrt(max(0.0, (2 * n + 1) ** 2 - 8.0 * target))) / 2.0))
+        bounds.append(min(n, max(bounds[-1], r)))
+    bounds.append(n)
+    return bounds
 
+
+def gram_dense_sharded(a_csr, world_size, rank, group=None, gather=True):
+    """Dense upper triangle of A^T A with the ROWS of A split across ranks: A^T A = sum over row blocks of
+    A_s^T A_s, so every rank forms the partial gram of its block on its GPU (sdb_syrkd_dev into a zeroed device
+    panel) and the partial panels are summed ONTO THEIR OWNERS: the n x n result is cut into row panels of equal
+    triangle area (triangle_row_bounds) and each panel is reduced to one rank (NCCL reduce on the device panels) —
+    a reduce-scatter, n^2 elements moved in total instead of the 2 n^2 of an all-reduce that leaves everything
+    everywhere.  ``gather=True`` then all-gathers the panels so every rank returns the full n x n array (the
+    convenience form); ``gather=False`` returns (first_row, panel) — this rank's rows only."""
     n = a_csr.shape[1]
     dtype = np.dtype(a_csr.dtype)
     bounds = partition_rows(a_csr.indptr, world_size)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    panel = _DevBuf(n * n * dtype.itemsize)
-    try:
-        block = row_block(a_csr, lo, hi)
-        zero, one = scalar_pair(0.0), scalar_pair(1.0)
-        if block.nnz > 0:
-            handle, _, _ = _h2.create(block)
-            with handle:
-                # the kernel never writes the strict lower triangle: start from a zero panel
-                host_zero = np.zeros((n, n), dtype=dtype)
-                check(SDB.lib.sdb_memcpy(panel.ptr, host_zero.ctypes.data_as(_ct.c_void_p), host_zero.nbytes, 1),
-                      "sdb_memcpy")
-                check(SDB.lib.sdb_syrkd_dev(_lib.OP_T, handle.ref, one, zero, panel.ptr, _lib.LAYOUT_C, n, None),
-                      "sdb_syrkd_dev")
-                check(SDB.lib.sdb_device_synchronize(), "sdb_device_synchronize")
-        else:
-            host_zero = np.zeros((n, n), dtype=dtype)
-            check(SDB.lib.sdb_memcpy(panel.ptr, host_zero.ctypes.data_as(_ct.c_void_p), host_zero.nbytes, 1),
-                  "sdb_memcpy")
-        if world_size > 1:
-            import torch
-            import torch.distributed as dist
+    block = row_block(a_csr, lo, hi)
+    zero, one = scalar_pair(0.0), scalar_pair(1.0)
+    owners = triangle_row_bounds(n, world_size)
+    if _is_nccl(world_size, group) or world_size == 1:
+        import torch
+        import torch.distributed as dist
 
-            if dist.get_backend(group) == "nccl":
-                t = torch.as_tensor(_CudaView(panel.ptr.value, (n, n), dtype), device="cuda")
-                dist.all_reduce(t, group=group)
-                torch.cuda.synchronize()
-            else:
-                host = np.empty((n, n), dtype=dtype)
-                check(SDB.lib.sdb_memcpy(host.ctypes.data_as(_ct.c_void_p), panel.ptr, host.nbytes, 2), "sdb_memcpy")
-                t = torch.from_numpy(host)
-                dist.all_reduce(t, group=group)
-                return host
-        out = np.empty((n, n), dtype=dtype)
-        check(SDB.lib.sdb_memcpy(out.ctypes.data_as(_ct.c_void_p), panel.ptr, out.nbytes, 2), "sdb_memcpy")
-        return out
-    finally:
-        panel.free()
+        panel = torch.zeros((n, n), dtype=getattr(torch, dtype.name), device="cuda")  # lower triangle stays zero
+        if block.nnz > 0:
+            handle, _, _ = _h.create(block)
+            with handle:
+                check(SDB.lib.sdb_syrkd_dev(_lib.OP_T, handle.ref, one, zero, _ct.c_void_p(panel.data_ptr()),
+                                            _lib.LAYOUT_C, n, None), "sdb_syrkd_dev")
+                check(SDB.lib.sdb_device_synchronize(), "sdb_device_synchronize")
+        if world_size > 1:
+            for q in range(world_size):
+                r0, r1 = owners[q], owners[q + 1]
+                if r1 > r0:
+                    dst = dist.get_global_rank(group, q) if group else q
+                    dist.reduce(panel[r0:r1], dst=dst, group=group)
+            if gather:
+                for q in range(world_size):
+                    r0, r1 = owners[q], owners[q + 1]
+                    if r1 > r0:
+                        src = dist.get_global_rank(group, q) if group else q
+                        dist.broadcast(panel[r0:r1], src=src, group=group)
+            torch.cuda.synchronize()
+        if gather or world_size == 1:
+            return panel.cpu().numpy()
+        return owners[rank], panel[owners[rank]:owners[rank + 1]].cpu().numpy()
+
+    # no NCCL (gloo on CPU-only test hosts): per-rank partial gram through the host entry point, summed on the host
+    import torch
+    import torch.distributed as dist
+
+    host = np.zeros((n, n), dtype=dtype)
+    if block.nnz > 0:
+        handle, _, _ = _h.create(block)
+        with handle:
+            check(SDB.lib.sdb_syrkd_new(_lib.OP_T, handle.ref, one, host.ctypes.data_as(_ct.c_void_p), _lib.LAYOUT_C, n),
+                  "sdb_syrkd_new")
+    t = torch.from_numpy(host)
+    dist.all_reduce(t, group=group)
+    if gather:
+        return host
+    return owners[rank], host[owners[rank]:owners[rank + 1]]

@@ -107,3 +107,10 @@ def test_bench_helpers():
     assert sha is None or len(sha) == 40
     # gather-model bytes of BASELINE configs[1]: 27.03 GB with beta != 0
     assert abs(bench.algorithmic_bytes(1_000_000, 50_000_000, 128) - 27.032e9) < 1e7
+
+
+def test_host_copy_pool_copies_correctly_and_reports_a_rate():
+    """kind 3 of sdb_probe_bandwidth runs without a GPU: the pageable -> staging copies of the host pipeline
+    (worker threads, non-temporal stores), verified byte for byte inside the probe."""
+    gbs = _lib.probe_bandwidth(3, 64 << 20, 1)
+    assert gbs > 0.1

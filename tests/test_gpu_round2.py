@@ -217,3 +217,71 @@ def test_spgemm_duplicate_columns_in_b_rows_use_atomics():
 def test_options_reject_unknown_names():
     with pytest.raises(ValueError, match="sdb_set_option returned 3"):
         _lib.set_option("no_such_switch", 1)
+
+
+# ===================================================== dense x dense (cblas_?gemm / cblas_?syrk callers)
+ALL4 = [np.float32, np.float64, np.complex64, np.complex128]
+
+
+def _dense(shape, dtype, order, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.random(shape)
+    if np.dtype(dtype).kind == "c":
+        a = a + 1j * rng.random(shape)
+    return np.asarray(a.astype(dtype), order=order)
+
+
+@pytest.mark.parametrize("dtype", ALL4)
+@pytest.mark.parametrize("order_a", ["C", "F"])
+@pytest.mark.parametrize("order_b", ["C", "F"])
+def test_dense_dot_dense(dtype, order_a, order_b):
+    """_dense_dense.py:14-88: the result takes A's memory order, B may have the other one; out / out_scalar."""
+    a = _dense((70, 130), dtype, order_a, 1)
+    b = _dense((130, 45), dtype, order_b, 2)
+    want = a.astype(np.complex128) @ b.astype(np.complex128)
+    tol = cs.TOL[np.dtype(dtype)] * 130
+    got = sdb.dot_product_mkl(a, b)
+    assert got.dtype == np.dtype(dtype) and got.shape == (70, 45)
+    assert got.flags.c_contiguous if order_a == "C" else got.flags.f_contiguous
+    assert np.abs(got - want).max() <= tol * np.abs(want).max()
+    out = np.asarray(np.ones((70, 45), dtype=dtype), order=order_a)
+    res = sdb.dot_product_mkl(a, b, out=out, out_scalar=3.0)
+    assert res is out and np.abs(out - (want + 3.0)).max() <= tol * np.abs(want).max()
+    # a 1-d right operand is a column and the result is flattened (_dense_dense.py:19-21,71)
+    v = sdb.dot_product_mkl(a, b[:, 0].copy())
+    assert v.shape == (70,) and np.abs(v - want[:, 0]).max() <= tol * np.abs(want).max()
+
+
+def test_dense_vector_dot_vector_is_numpys():
+    x, y = np.arange(5.0), np.arange(5.0) + 1
+    assert sdb.dot_product_mkl(x, y) == np.dot(x, y)
+
+
+def test_dense_dot_dense_errors_and_cast():
+    a = np.ones((4, 5), dtype=np.float32)
+    b = np.ones((5, 3), dtype=np.float64)
+    with pytest.raises(ValueError):
+        sdb.dot_product_mkl(a, b)
+    assert sdb.dot_product_mkl(a, b, cast=True).dtype == np.float64
+    with pytest.raises(ValueError):
+        sdb.dot_product_mkl(a, np.ones((4, 3), dtype=np.float32))
+    assert sdb.dot_product_mkl(np.ones((0, 5), dtype=np.float32), np.ones((5, 3), dtype=np.float32)).shape == (0, 3)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_gram_of_a_dense_array(dtype, order, transpose):
+    """_gram_matrix.py:196-249 (cblas_?syrk): upper triangle in A's order; a fresh result is zero below the diagonal,
+    a given out keeps what it had there."""
+    a = _dense((60, 35), dtype, order, 3)
+    full = (a @ a.T if transpose else a.T @ a).astype(np.float64)
+    n = full.shape[0]
+    got = sdb.gram_matrix_mkl(a, transpose=transpose)
+    tol = cs.TOL[np.dtype(dtype)] * 60 * np.abs(full).max()
+    assert got.flags.c_contiguous if order == "C" else got.flags.f_contiguous
+    assert np.abs(np.triu(got) - np.triu(full)).max() <= tol and np.all(np.tril(got, -1) == 0)
+    out = np.asarray(np.full((n, n), 7.0, dtype=dtype), order=order)
+    res = sdb.gram_matrix_mkl(a, transpose=transpose, out=out, out_scalar=2.0)
+    assert res is out and np.all(np.tril(out, -1) == 7.0)
+    assert np.abs(np.triu(out) - np.triu(full + 14.0)).max() <= tol

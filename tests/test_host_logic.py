@@ -114,8 +114,12 @@ def test_rejections_before_any_device_work():
         sdb.gram_matrix_mkl(M1.astype(np.int32))
     with pytest.warns(DeprecationWarning):
         sdb.dot_product_mkl(sp.csr_matrix((200, 300)), M2, debug=True)
-    with pytest.raises(NotImplementedError):
-        sdb.dot_product_mkl(np.ones((3, 3)), np.ones((3, 3)))
+    # two dense operands: validated like the reference (_dense_dense.py:74-88), then a GEMM on the GPU
+    with pytest.raises(ValueError, match="Matrix alignment error"):
+        sdb.dot_product_mkl(np.ones((3, 3)), np.ones((4, 3)))
+    with pytest.raises(ValueError, match="must be the same"):
+        sdb.dot_product_mkl(np.ones((3, 3), dtype=np.float32), np.ones((3, 3)))
+    assert sdb.dot_product_mkl(np.arange(3.0), np.arange(3.0)) == 5.0  # vector (dot) vector is numpy's
 
 
 def test_bsr_block_rules():

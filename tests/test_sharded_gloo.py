@@ -90,3 +90,15 @@ def test_stack_row_blocks_is_exact():
     assert got.shape == c.shape
     assert np.array_equal(got.indptr, c.indptr) and np.array_equal(got.indices, c.indices)
     assert np.array_equal(got.data, c.data)
+
+
+def test_triangle_row_bounds_balance_the_area():
+    """Owners of the reduce-scattered gram panels (sharded.gram_dense_sharded): equal upper-triangle area."""
+    from sparse_dot_b200 import sharded
+
+    n, parts = 100_000, 8
+    b = sharded.triangle_row_bounds(n, parts)
+    assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+    area = [(b[i + 1] - b[i]) * n - (b[i + 1] * (b[i + 1] - 1) - b[i] * (b[i] - 1)) // 2 for i in range(parts)]
+    assert max(area) / min(area) < 1.001
+    assert sharded.triangle_row_bounds(3, 8)[-1] == 3 and sharded.triangle_row_bounds(0, 4) == [0, 0, 0, 0, 0]
