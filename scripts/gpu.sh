@@ -17,6 +17,7 @@
 #   hashes                           SASS hashes of the profiled kernels (ties ncu bytes to this build)
 #   py=<script and args>             python <script and args>
 #   envpy=<label>,<VAR=VAL ..>,<script and args>   the same with environment variables set
+#   sh=<label>,<shell command>       any shell command
 #   smoke                            __graft_entry__.smoke()
 set -u
 cd "$(dirname "$0")/.."
@@ -67,6 +68,9 @@ for step in "$@"; do
     envpy)   # envpy=<label>,<VAR=VAL[ VAR=VAL..]>,<script and args>
       IFS=, read -r label envs cmd <<< "$arg"
       env $envs timeout 1500 python $cmd > $OUT/${TAG}_envpy_$label.log 2>&1; tail -25 $OUT/${TAG}_envpy_$label.log | cut -c1-1500 ;;
+    sh)      # sh=<label>,<shell command>
+      IFS=, read -r label cmd <<< "$arg"
+      timeout 1500 bash -c "$cmd" > $OUT/${TAG}_sh_$label.log 2>&1; tail -30 $OUT/${TAG}_sh_$label.log | cut -c1-400 ;;
     smoke)
       timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; tail -8 $OUT/${TAG}_smoke.log ;;
     *) echo "unknown step $step" ;;

@@ -15,7 +15,7 @@ import numpy as np
 from sparse_dot_b200 import _lib
 import sparse_dot_b200 as sdb
 out = {"threads": os.environ.get("SDB_COPY_THREADS"), "slot_mb": os.environ.get("SDB_STAGE_SLOT_MB"),
-       "piece_kb": os.environ.get("SDB_COPY_PIECE_KB"), "host_copy_gbs": _lib.probe_bandwidth(3, 1 << 30, 3)}
+       "piece_kb": os.environ.get("SDB_COPY_PIECE_KB"), "nt_stores": os.environ.get("SDB_COPY_NT"), "host_copy_gbs": _lib.probe_bandwidth(3, 1 << 30, 3)}
 if "--e2e" in sys.argv:
     from tests import _cases as cs
     a, x, y0 = cs.c2_workload(1_000_000, 1_000_000, 50, 128, seed=0)
@@ -32,8 +32,10 @@ print(json.dumps(out))
 if __name__ == "__main__":
     e2e = ["--e2e"] if "--e2e" in sys.argv else []
     print(json.dumps({"cpu_count": os.cpu_count(), "affinity": len(os.sched_getaffinity(0))}))
-    for threads, slot, piece in [(4, 16, 1024), (8, 16, 1024), (12, 16, 1024), (16, 16, 1024), (24, 16, 1024),
-                                 (16, 32, 2048), (16, 8, 512), (16, 16, 4096)]:
-        env = dict(os.environ, SDB_COPY_THREADS=str(threads), SDB_STAGE_SLOT_MB=str(slot), SDB_COPY_PIECE_KB=str(piece))
+    ncpu = len(os.sched_getaffinity(0))
+    for threads, slot, piece, nt in [(8, 8, 1024, 1), (12, 8, 1024, 1), (ncpu, 8, 1024, 1), (ncpu, 8, 1024, 0),
+                                     (ncpu, 16, 1024, 1), (ncpu, 4, 512, 1), (ncpu, 8, 512, 1), (ncpu, 8, 2048, 1)]:
+        env = dict(os.environ, SDB_COPY_THREADS=str(threads), SDB_STAGE_SLOT_MB=str(slot), SDB_COPY_PIECE_KB=str(piece),
+                   SDB_COPY_NT=str(nt))
         r = subprocess.run([sys.executable, "-c", CHILD] + e2e, env=env, capture_output=True, text=True)
         print(r.stdout.strip() or r.stderr.strip()[-300:], flush=True)

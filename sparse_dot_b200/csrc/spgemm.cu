@@ -33,7 +33,8 @@ constexpr int kSmallSlots = 2048, kSmallSlotsLog2 = 11, kSmallMax = 1024, kSmall
 constexpr int kCtaSlots = 8192, kCtaSlotsLog2 = 13, kCtaMax = 4096;
 constexpr int kHashWarps = 8;  // warps per CTA in the warp-bin kernels
 constexpr int kCtaThreads = 512;
-constexpr int kBins = 4;  // warp, small, CTA, wide
+constexpr int kBins = 5;  // warp, small, CTA, wide, huge
+constexpr int kWideMax = 32768;  // wide rows above this take the batched walk (one CTA per SM, 4 products per lane in flight)
 constexpr int32_t kEmpty = -1;
 
 __device__ __forceinline__ uint32_t hash_slot(int32_t col, int log2size) {
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256) bin_rows_kernel(int64_t rows, const int32
         if (v == 0) {
             if (zero_len) zero_len[i] = 0;
         } else {
-            bin = v <= kWarpMax ? 0 : (v <= kSmallMax ? 1 : (v <= kCtaMax ? 2 : 3));
+            bin = v <= kWarpMax ? 0 : (v <= kSmallMax ? 1 : (v <= kCtaMax ? 2 : (v <= kWideMax ? 3 : 4)));
         }
     }
 #pragma unroll
@@ -295,6 +296,61 @@ __global__ void __launch_bounds__(kHashWarps * 32)
     }
 }
 
+// The same walk in two phases and batches of kWalkBatch products per lane: `pre(col, a, q)` does the loads a
+// product needs and returns what `post` will commit with an atomic.  All the loads of a batch are issued before
+// its first atomic, so a lane keeps kWalkBatch dependent load chains in flight instead of one (an atomic is a
+// barrier for the compiler's scheduling of the loads that follow it) — the wide rows are latency-bound walks.
+constexpr int kWalkBatch = 4;
+template <typename T, bool NEED_VAL, int kStageEntries, typename Item, typename Pre, typename Post>
+__device__ __forceinline__ void for_each_product_cta_batched(int64_t i, const int64_t* __restrict__ l_ptr,
+                                                             const int32_t* __restrict__ l_idx,
+                                                             const T* __restrict__ l_val,
+                                                             const int32_t* __restrict__ l_pos,
+                                                             const int64_t* __restrict__ r_ptr,
+                                                             const int32_t* __restrict__ r_idx,
+                                                             LStage<T, kStageEntries>& st, Pre pre, Post post) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int64_t l_end = l_ptr[i + 1];
+    auto walk = [&](int64_t first, int64_t qe, int64_t stride, T a) {
+        for (int64_t q0 = first; q0 < qe; q0 += stride * kWalkBatch) {
+            int32_t col[kWalkBatch];
+            Item item[kWalkBatch];
+#pragma unroll
+            for (int u = 0; u < kWalkBatch; ++u) {
+                const int64_t q = q0 + stride * u;
+                col[u] = q < qe ? __ldg(r_idx + q) : int32_t(-1);
+            }
+#pragma unroll
+            for (int u = 0; u < kWalkBatch; ++u)
+                if (col[u] >= 0) item[u] = pre(col[u], a, q0 + stride * u);
+#pragma unroll
+            for (int u = 0; u < kWalkBatch; ++u)
+                if (col[u] >= 0) post(item[u]);
+        }
+    };
+    for (int64_t base = l_ptr[i]; base < l_end; base += kStageEntries) {
+        const int cnt = int(min(int64_t(kStageEntries), l_end - base));
+        __syncthreads();  // the previous round has been consumed
+        for (int e = tid; e < cnt; e += blockDim.x) {
+            const int32_t k = l_idx[base + e];
+            st.rb[e] = r_ptr[k] + (l_pos ? l_pos[base + e] : 0);
+            st.re[e] = r_ptr[k + 1];
+            if (NEED_VAL) st.a[e] = l_val[base + e];
+        }
+        __syncthreads();
+        for (int e = warp; e < cnt; e += nwarps) {  // short R rows: one warp each, round-robin
+            const int64_t qb = st.rb[e], qe = st.re[e];
+            if (qe - qb > kLongRRow) continue;
+            walk(qb + lane, qe, 32, NEED_VAL ? st.a[e] : Num<T>::zero());
+        }
+        for (int e = 0; e < cnt; ++e) {  // long R rows (power-law tails): the whole CTA strides each of them
+            const int64_t qb = st.rb[e], qe = st.re[e];
+            if (qe - qb <= kLongRRow) continue;
+            walk(qb + tid, qe, blockDim.x, NEED_VAL ? st.a[e] : Num<T>::zero());
+        }
+    }
+}
+
 // One CTA of THREADS threads per row, one shared-memory table of SLOTS slots (rows of at most SLOTS / 2
 // entries), L entries staged STAGE at a time.  Instantiated for the small bin (128 threads, 2048 slots) and the
 // CTA bin (512 threads, 8192 slots).
@@ -375,11 +431,15 @@ __global__ void __launch_bounds__(THREADS)
 //      is atomically added to c_val[row start + rank] (a compact, L2-resident target);
 //   5. clear the bitmap.
 // The result rows are sorted, so sdb_order has nothing to do for them.
+template <typename T> struct RankedProduct {  // a product and where it lands in its output row
+    int rank;
+    T v;
+};
 constexpr int kPieceWords = 128;
 constexpr int kPiecesPerRound = 1024;  // == blockDim.x of the wide kernel
 
-template <typename T, bool NUMERIC>
-__global__ void __launch_bounds__(1024)
+template <typename T, bool NUMERIC, bool BATCHED>
+__global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
     spgemm_wide_kernel(const int32_t* __restrict__ list, unsigned n_list, int64_t words_padded,
                        const int64_t* __restrict__ l_ptr, const int32_t* __restrict__ l_idx,
                        const T* __restrict__ l_val, const int32_t* __restrict__ l_pos,
@@ -399,11 +459,20 @@ __global__ void __launch_bounds__(1024)
     for (unsigned li = blockIdx.x; li < n_list; li += gridDim.x) {
         const int64_t i = list[li];
         // ---- 1. membership
-        for_each_product_cta<T, false, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
-                                       [&](int32_t col, T, int64_t) {
-                                           if (upper && int64_t(col) < i) return;
-                                           atomicOr(&bm[col >> 5], 1u << (col & 31));
-                                       });
+        if constexpr (BATCHED) {
+            for_each_product_cta_batched<T, false, 256, int32_t>(
+                i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage, [&](int32_t col, T, int64_t) { return col; },
+                [&](int32_t col) {
+                    if (upper && int64_t(col) < i) return;
+                    atomicOr(&bm[col >> 5], 1u << (col & 31));
+                });
+        } else {
+            for_each_product_cta<T, false, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
+                                                [&](int32_t col, T, int64_t) {
+                                                    if (upper && int64_t(col) < i) return;
+                                                    atomicOr(&bm[col >> 5], 1u << (col & 31));
+                                                });
+        }
         if (tid == 0) running = 0;
         __syncthreads();
         const int64_t out0 = NUMERIC ? c_ptr[i] : 0;
@@ -480,14 +549,32 @@ __global__ void __launch_bounds__(1024)
             continue;
         }
         // ---- 4. values: every product is added at its column's rank
-        for_each_product_cta<T, true, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
-                                      [&](int32_t col, T a, int64_t q) {
-                                          if (upper && int64_t(col) < i) return;
-                                          const int w = col >> 5;
-                                          const unsigned below = __ldcg(bm + w) & ((1u << (col & 31)) - 1u);
-                                          const int rank = __ldcg(word_rank + w) + __popc(below);
-                                          atomic_add(c_val + out0 + rank, mul(a, r_val[q]));
-                                      });
+        if constexpr (BATCHED) {
+            for_each_product_cta_batched<T, true, 256, RankedProduct<T>>(
+                i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
+                [&](int32_t col, T a, int64_t q) {
+                    RankedProduct<T> it;
+                    it.rank = -1;
+                    if (upper && int64_t(col) < i) return it;
+                    const int w = col >> 5;
+                    const unsigned below = __ldcg(bm + w) & ((1u << (col & 31)) - 1u);
+                    it.rank = __ldcg(word_rank + w) + __popc(below);
+                    it.v = mul(a, ldg(r_val + q));
+                    return it;
+                },
+                [&](const RankedProduct<T>& it) {
+                    if (it.rank >= 0) atomic_add(c_val + out0 + it.rank, it.v);
+                });
+        } else {
+            for_each_product_cta<T, true, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
+                                               [&](int32_t col, T a, int64_t q) {
+                                                   if (upper && int64_t(col) < i) return;
+                                                   const int w = col >> 5;
+                                                   const unsigned below = __ldcg(bm + w) & ((1u << (col & 31)) - 1u);
+                                                   const int rank = __ldcg(word_rank + w) + __popc(below);
+                                                   atomic_add(c_val + out0 + rank, mul(a, r_val[q]));
+                                               });
+        }
         __syncthreads();
         // ---- 5. clear
         for (int64_t w = int64_t(tid) * 4; w < words_padded; w += int64_t(blockDim.x) * 4) {
@@ -697,8 +784,8 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
     unsigned h[kBins];
     SDB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     SDB_CUDA(cudaStreamSynchronize(s));
-    trace(s, "spgemm %s: bins warp %u, small %u, cta %u, wide %u", NUMERIC ? "numeric" : "symbolic", h[0], h[1], h[2],
-          h[3]);
+    trace(s, "spgemm %s: bins warp %u, small %u, cta %u, wide %u, huge %u", NUMERIC ? "numeric" : "symbolic", h[0],
+          h[1], h[2], h[3], h[4]);
     const int64_t* lp = l.indptr;
     const int32_t* li = l.indices;
     const T* lv = static_cast<const T*>(l.values);
@@ -725,17 +812,17 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
             s, h[2], lists.list[2], lp, li, lv, lq, rp, ri, rv, upper, sort, c_len, c_ptr, c_idx, c_val)));
         trace(s, "spgemm: cta bin done");
     }
-    if (h[3] > 0) {
+    if (h[3] + h[4] > 0) {
         const int64_t n_cols = r.cols;
         const int64_t words = (((n_cols + 31) >> 5) + kPieceWords - 1) / kPieceWords * kPieceWords;  // padded
         // resident CTAs: bounded by the list, two per SM, and ~2 GiB of scratch
         const int64_t per_cta = words * 4 * (NUMERIC ? 2 : 1);
-        int64_t ctas = std::min<int64_t>(h[3], 2 * int64_t(ctx->sm_count));
-        ctas = std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t(2) << 30) / std::max<int64_t>(per_cta, 1)));
+        int64_t max_ctas = 2 * int64_t(ctx->sm_count);
+        max_ctas = std::max<int64_t>(1, std::min<int64_t>(max_ctas, (int64_t(2) << 30) / std::max<int64_t>(per_cta, 1)));
         DevBuf bm, ranks;
-        SDB_TRY(bm.alloc(size_t(ctas * words) * 4, s));
-        SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(ctas * words) * 4, s));
-        if (NUMERIC) SDB_TRY(ranks.alloc(size_t(ctas * words) * 4, s));
+        SDB_TRY(bm.alloc(size_t(max_ctas * words) * 4, s));
+        SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(max_ctas * words) * 4, s));
+        if (NUMERIC) SDB_TRY(ranks.alloc(size_t(max_ctas * words) * 4, s));
         // The summary formulation is opt-in ("spgemm_wide" = 2): measured on R-MAT scale 22 (profiles/r2_logs/
         // spgemm_trace_ef1*.log) it is SLOWER than the full sweeps (symbolic 15.3 vs 7.1 ms, numeric 35.0 vs 25.5 ms):
         // the per-row cost is the latency of the sweep iterations, not their DRAM traffic, and a warp walking 32-word
@@ -743,16 +830,27 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
         const int forced = get_option(kOptSpgemmWide);
         const int64_t n_groups = words / 32;
         const size_t smem2 = size_t(n_groups) * 12;
-        if (forced == 2 && smem2 <= size_t(96) * 1024) {
-            auto kernel = spgemm_wide2_kernel<T, NUMERIC>;
-            SDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(std::max<size_t>(smem2, 48 * 1024))));
-            SDB_LAUNCH(kernel, unsigned(ctas), 1024, smem2, s, lists.list[3], h[3], words, int(n_groups), lp, li, lv, lq,
-                       rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx, c_val);
-            trace(s, "spgemm: wide bin (summary) done (%lld CTAs)", (long long)ctas);
-        } else {
-            SDB_LAUNCH((spgemm_wide_kernel<T, NUMERIC>), unsigned(ctas), 1024, 0, s, lists.list[3], h[3], words, lp, li,
-                       lv, lq, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx, c_val);
-            trace(s, "spgemm: wide bin done (%lld CTAs)", (long long)ctas);
+        for (int b = 3; b <= 4; ++b) {
+            if (h[b] == 0) continue;
+            const bool batched = b == 4 && forced != 1;  // "spgemm_wide" = 1: the unbatched walk for every wide row
+            const int64_t ctas = std::min<int64_t>(std::min<int64_t>(h[b], max_ctas),
+                                                   int64_t(batched ? 1 : 2) * ctx->sm_count);
+            if (forced == 2 && smem2 <= size_t(96) * 1024) {
+                auto kernel = spgemm_wide2_kernel<T, NUMERIC>;
+                SDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              int(std::max<size_t>(smem2, 48 * 1024))));
+                SDB_LAUNCH(kernel, unsigned(ctas), 1024, smem2, s, lists.list[b], h[b], words, int(n_groups), lp, li, lv,
+                           lq, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx, c_val);
+            } else if (batched) {
+                SDB_LAUNCH((spgemm_wide_kernel<T, NUMERIC, true>), unsigned(ctas), 1024, 0, s, lists.list[b], h[b], words,
+                           lp, li, lv, lq, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx,
+                           c_val);
+            } else {
+                SDB_LAUNCH((spgemm_wide_kernel<T, NUMERIC, false>), unsigned(ctas), 1024, 0, s, lists.list[b], h[b], words,
+                           lp, li, lv, lq, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx,
+                           c_val);
+            }
+            trace(s, "spgemm: %s bin done (%lld CTAs)", b == 3 ? "wide" : "huge", (long long)ctas);
         }
     }
     return SDB_STATUS_SUCCESS;

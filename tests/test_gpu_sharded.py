@@ -184,7 +184,8 @@ def _worker_nccl(rank, world, port, q):
             _lib.check(_lib.SDB.lib.sdb_spmm_dev(_lib.OP_N, one, c_dev.handle.ref, _lib.LAYOUT_C, C.c_void_p(x.data_ptr()),
                                                  8, 8, zero, C.c_void_p(y.data_ptr()), 8, None), "sdb_spmm_dev")
             _lib.check(_lib.SDB.lib.sdb_device_synchronize(), "sync")
-            rowsum_err = float(np.abs(y[:, 0].cpu().numpy() - np.asarray(w.sum(axis=1)).ravel()).max())
+            want_rows = np.asarray(w.astype(np.float64).sum(axis=1)).ravel()
+            rowsum_err = float(np.abs(y[:, 0].cpu().numpy() - want_rows).max() / want_rows.max())
         ok_struct = bool(np.array_equal(c.indptr, w.indptr) and np.array_equal(c.indices, w.indices))
         err = cs.rel_err(c.data, w.data)
         m = cs.uniform_rows_csr(3000, 700, 20, np.float64, seed=3)
@@ -193,7 +194,7 @@ def _worker_nccl(rank, world, port, q):
         gerr = float(np.abs(g - wg).max())
         row0, mine = sharded.gram_dense_sharded(m, world, rank, gather=False)
         perr = float(np.abs(mine - wg[row0:row0 + mine.shape[0]]).max())
-        q.put((rank, ok_struct, max(err, rowsum_err * 1e-3), max(gerr, perr)))
+        q.put((rank, ok_struct, max(err, rowsum_err), max(gerr, perr)))
     except Exception as e:
         q.put((rank, repr(e), None, None))
     finally:
