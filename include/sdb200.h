@@ -195,7 +195,11 @@ SDB_API sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, i
  *                   slice into every peer panel itself;
  *   "k1"            "stores" with the row-gather kernel even where the L2-tiled
  *                   streaming kernel would qualify (its CTAs finish continuously,
- *                   which spreads the peer stores over the whole kernel). */
+ *                   which spreads the peer stores over the whole kernel);
+ *   "sm"            row chunks like "ce", but a few copier CTAs push each finished
+ *                   chunk: every 16-byte pack is read from the local panel once and
+ *                   stored into all peer panels, on SMs the streaming kernel's
+ *                   persistent grid leaves free (sdb_set_allgather_sms, default 12). */
 SDB_API sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A,
                                           const void* dX, int64_t n, int64_t ldx,
                                           const double* beta, void* const* dY_peers,
@@ -203,11 +207,13 @@ SDB_API sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A,
                                           void* stream);
 
 /* Choose the exchange strategy of sdb_spmm_dev_allgather at run time (process-wide; overrides
- * SDB_ALLGATHER): strategy 0 = automatic, 1 = "ce", 2 = "stores", 3 = "k1"; chunks = target number of
+ * SDB_ALLGATHER): strategy 0 = automatic, 1 = "ce", 2 = "stores", 3 = "k1", 4 = "sm"; chunks = target number of
  * row chunks of the "ce" pipeline (0 = default, about five).  RowShardedSpMM.autotune() times the
  * candidates on the live NVLink topology during warm-up and keeps the fastest.  No reference
  * counterpart (the reference has no multi-device path). */
 SDB_API sdb_status sdb_set_allgather(int strategy, int chunks);
+/* SMs kept free of SpMM CTAs for the copier CTAs of strategy 4 ("sm"), 1..64. */
+SDB_API sdb_status sdb_set_allgather_sms(int sms);
 
 /* ======================= SpGEMM ==================== */
 

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "sdb_spmm_dev": (_i32, [_i32, _pd, _vp, _i32, _vp, _i64, _i64, _pd, _vp, _i64, _vp]),
     "sdb_spmm_dev_allgather": (_i32, [_pd, _vp, _vp, _i64, _i64, _pd, _pvp, _i32, _i32, _i64, _i64, _vp]),
     "sdb_set_allgather": (_i32, [_i32, _i32]),
+    "sdb_set_allgather_sms": (_i32, [_i32]),
     "sdb_spgemm": (_i32, [_i32, _vp, _vp, _pvp]),
     "sdb_spgemm_ordered": (_i32, [_i32, _vp, _vp, _pvp]),
     "sdb_spgemm_dense": (_i32, [_i32, _vp, _vp, _i32, _vp, _i64]),

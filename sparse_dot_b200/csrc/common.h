@@ -274,6 +274,7 @@ sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype
 bool spmm_slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx);
 // rows one wave of the streaming kernel's persistent grid covers (0 when the call would not use it): row sub-ranges
 // handed to it must start at a multiple of this
+void spmm_slab_reserve_sms(int sms);  // persistent grid leaves this many SMs free (per host thread; 0 = none)
 int64_t spmm_slab_wave_rows(const Context* ctx, const CsrView& a, int dtype, int64_t n, int64_t ldx, bool count_call);
 sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, bool conj_a,
                             const double* alpha, const double* beta, const void* dX, int64_t n, int64_t ldx,

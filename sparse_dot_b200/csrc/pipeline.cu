@@ -60,14 +60,15 @@ int64_t index_at(const void* p, int bits, int64_t i) {
     return bits == 32 ? int64_t(static_cast<const int32_t*>(p)[i]) : static_cast<const int64_t*>(p)[i];
 }
 
-// staging slot size (SDB_STAGE_SLOT_MB, default 8 MiB): large enough to amortise the hand-off to the copy
-// threads, small enough that eight of them pipeline well behind a 48 MiB row chunk (measured: 8 and 16 MiB
-// are within 2 %, 32 MiB is 10 % slower; profiles/r2_logs/host_copy_sweep.log)
+// staging slot size (SDB_STAGE_SLOT_MB, default 16 MiB): large enough to amortise the hand-off to the copy
+// threads, small enough that eight of them pipeline well behind a 48 MiB row chunk (measured on a 16-core host,
+// profiles/r2_logs/host_copy_sweep*.log: 16 MiB slots, 1 MiB pieces, non-temporal stores -> 35.7 ms per configs[1]
+// call from pageable arrays; 8 MiB 40-45 ms, 4 MiB 43 ms, cached stores 71 ms)
 size_t slot_bytes() {
     static const size_t v = [] {
         const char* e = getenv("SDB_STAGE_SLOT_MB");
-        const int mb = e ? atoi(e) : 8;
-        return size_t(mb >= 1 && mb <= 256 ? mb : 8) << 20;
+        const int mb = e ? atoi(e) : 16;
+        return size_t(mb >= 1 && mb <= 256 ? mb : 16) << 20;
     }();
     return v;
 }

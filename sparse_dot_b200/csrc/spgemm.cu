@@ -188,7 +188,6 @@ __device__ __forceinline__ int hash_row_warp(int64_t i, int lane, const int64_t*
 // CTA-wide walk over the products of row i: the L entries' R-row bounds (and values) are staged in
 // shared memory kStageEntries at a time with coalesced loads, then the warps take staged entries
 // round-robin and their lanes stride the R row.  f(col, a, q) is called once per product.
-constexpr int kStageEntries = 256;
 constexpr int kLongRRow = 512;  // R rows longer than this are shared by all warps of the CTA
 template <typename T, int kStageEntries = 256> struct LStage {
     int64_t rb[kStageEntries];
@@ -595,8 +594,8 @@ __global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
 // bitmap word 32 g + b is non-zero — together with two per-group prefix arrays, and
 //   1. the products are walked: atomicOr on the bitmap word (global, fire-and-forget) and, only while the
 //      summary bit is still clear, an atomicOr on the summary (shared);
-//   2. a warp takes a group of 32 words at a time (lane = word; the set words of a group share a 128-byte
-//      line): populations per group -> block-wide exclusive scans -> entry / set-word offsets per group;
+//   2. one lane per group of 32 words walks the words its group has set: populations per group -> block-wide
+//      exclusive scans -> entry / set-word offsets per group;
 //      [symbolic stops here: c_len, then only the set words are cleared]
 //   3. second walk of the non-empty groups: the k-th set word's output rank goes into a COMPACT array
 //      (k = group offset + popc of the lower summary bits), columns are written in ascending order;
@@ -623,7 +622,6 @@ __global__ void __launch_bounds__(1024)
     unsigned* bm = bitmaps + int64_t(blockIdx.x) * words_padded;
     int32_t* wr = NUMERIC ? word_ranks + int64_t(blockIdx.x) * words_padded : nullptr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
     for (int g = tid; g < n_groups; g += blockDim.x) summary[g] = 0u;
     __syncthreads();
     // groups handled by one thread in the block-wide scans (contiguous, so the scan is over ascending columns)
@@ -641,20 +639,27 @@ __global__ void __launch_bounds__(1024)
                                                 if (!(*sp & sb)) atomicOr(summary + (w >> 5), sb);
                                             });
         __syncthreads();
-        // ---- 2. populations per group
-        for (int g = warp; g < n_groups; g += nwarps) {
-            const unsigned sm = summary[g];
-            int c = 0;
-            if (sm) {
-                const unsigned word = (sm >> lane) & 1u ? __ldcg(bm + int64_t(g) * 32 + lane) : 0u;
-                c = __popc(word);
+        // ---- 2. populations per group: one LANE per group (consecutive lanes take consecutive groups, so the dense
+        // low-column groups of a power-law row fill whole warps), each lane walking only the words its group has set,
+        // four loads in flight
+        for (int g = tid; g < n_groups; g += blockDim.x) {
+            unsigned sm = summary[g];
+            const unsigned* gw = bm + int64_t(g) * 32;
+            int ce = 0;
+            grp_wrd[g] = __popc(sm);
+            while (sm) {
+                unsigned w4[4];
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                for (int u = 0; u < 4; ++u) {
+                    w4[u] = 0u;
+                    if (sm) {
+                        w4[u] = __ldcg(gw + (__ffs(sm) - 1));
+                        sm &= sm - 1;
+                    }
+                }
+                ce += __popc(w4[0]) + __popc(w4[1]) + __popc(w4[2]) + __popc(w4[3]);
             }
-            if (lane == 0) {
-                grp_ent[g] = c;
-                grp_wrd[g] = __popc(sm);
-            }
+            grp_ent[g] = ce;
         }
         __syncthreads();
         // block-wide exclusive scans of both arrays: thread-local run, warp scan, scan of the warp totals
@@ -701,22 +706,16 @@ __global__ void __launch_bounds__(1024)
         } else {
             // ---- 3. ranks of the set words (compact) and ordered emission
             const int64_t out0 = c_ptr[i];
-            for (int g = warp; g < n_groups; g += nwarps) {
-                const unsigned sm = summary[g];
+            for (int g = tid; g < n_groups; g += blockDim.x) {
+                unsigned sm = summary[g];
                 if (!sm) continue;
-                const bool mine = (sm >> lane) & 1u;
-                const int64_t w = int64_t(g) * 32 + lane;
-                unsigned word = mine ? __ldcg(bm + w) : 0u;
-                const int c = __popc(word);
-                int incl = c;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += o;
-                }
-                if (mine) {
-                    int rank = grp_ent[g] + incl - c;
-                    wr[grp_wrd[g] + __popc(sm & lt_mask)] = rank;
+                int rank = grp_ent[g], k = grp_wrd[g];
+                while (sm) {
+                    const int b = __ffs(sm) - 1;
+                    sm &= sm - 1;
+                    const int64_t w = int64_t(g) * 32 + b;
+                    unsigned word = __ldcg(bm + w);
+                    wr[k++] = rank;
                     while (word) {
                         const int bit = __ffs(word) - 1;
                         word &= word - 1;
@@ -741,12 +740,14 @@ __global__ void __launch_bounds__(1024)
             __syncthreads();
         }
         // ---- 5. clear the set words and the summary
-        for (int g = warp; g < n_groups; g += nwarps) {
-            const unsigned sm = summary[g];
+        for (int g = tid; g < n_groups; g += blockDim.x) {
+            unsigned sm = summary[g];
             if (!sm) continue;
-            if ((sm >> lane) & 1u) bm[int64_t(g) * 32 + lane] = 0u;
-            __syncwarp();
-            if (lane == 0) summary[g] = 0u;
+            summary[g] = 0u;
+            while (sm) {
+                bm[int64_t(g) * 32 + (__ffs(sm) - 1)] = 0u;
+                sm &= sm - 1;
+            }
         }
         __syncthreads();
     }

@@ -373,6 +373,38 @@ sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype
     return transpose_dense(s, yr.p, n, dY_peers[0], ldy, a.rows, n, es);
 }
 
+// Exchange strategy "sm": finished rows are pushed to the peers by a few COPIER CTAs instead of the copy engines:
+// every 16-byte pack of the chunk is read from the local panel ONCE and stored into each of the n_dst peer
+// panels (the copy engines read it once per peer), with streaming loads / stores so neither side's L2 keeps it.
+// The streaming SpMM kernel leaves `reserve` SMs free for these CTAs (spmm_slab.cu, spmm_slab_reserve_sms).
+struct PushTargets {
+    uint4* dst[kMaxPeers];
+};
+constexpr int kPushThreads = 512, kPushUnroll = 4;
+__global__ void __launch_bounds__(kPushThreads) push_rows_kernel(const uint4* __restrict__ src, PushTargets t, int n_dst,
+                                                                 size_t n_vec) {
+    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; i + (kPushUnroll - 1) * stride < n_vec; i += kPushUnroll * stride) {
+        uint4 v[kPushUnroll];
+#pragma unroll
+        for (int u = 0; u < kPushUnroll; ++u) v[u] = __ldcs(src + i + u * stride);
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q) {
+            if (q < n_dst) {
+#pragma unroll
+                for (int u = 0; u < kPushUnroll; ++u) __stcs(t.dst[q] + i + u * stride, v[u]);
+            }
+        }
+    }
+    for (; i < n_vec; i += stride) {
+        const uint4 v = __ldcs(src + i);
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)
+            if (q < n_dst) __stcs(t.dst[q] + i, v);
+    }
+}
+
 }  // namespace sdb
 
 using namespace sdb;
@@ -417,18 +449,19 @@ sdb_status sdb_spmm_dev(int op, const double* alpha, const sdb_mat* A, int layou
 // How the finished rows reach the peers (SDB_ALLGATHER overrides the automatic choice): "ce" = chunk-pipelined
 // copy-engine exchange, "stores" = the kernel's epilogue stores every finished 16-byte slice into every peer panel
 // itself, "k1" = the same with the row-gather kernel K1 even where the streaming kernel would qualify.
-enum { kXchgAuto = 0, kXchgCopyEngines = 1, kXchgStores = 2, kXchgStoresRowGather = 3 };
+enum { kXchgAuto = 0, kXchgCopyEngines = 1, kXchgStores = 2, kXchgStoresRowGather = 3, kXchgSmCopier = 4 };
 // process-wide; sdb_set_allgather overrides the environment (RowShardedSpMM.autotune measures the strategies on
 // the live topology during warm-up and keeps the fastest)
 static std::atomic<int> g_xchg_strategy{-1};
-static std::atomic<int> g_xchg_chunks{0};  // target number of row chunks of the "ce" pipeline (0 = about five)
+static std::atomic<int> g_xchg_chunks{0};  // target number of row chunks of the "ce" / "sm" pipelines (0 = about five)
+static std::atomic<int> g_xchg_sms{12};    // SMs the "sm" strategy keeps free of SpMM CTAs for its copier CTAs
 static int allgather_strategy() {
     int v = g_xchg_strategy.load(std::memory_order_relaxed);
     if (v >= 0) return v;
     const char* e = getenv("SDB_ALLGATHER");
     v = kXchgAuto;
     if (e && e[0] == 'c') v = kXchgCopyEngines;      // "ce"
-    if (e && e[0] == 's') v = kXchgStores;           // "stores"
+    if (e && e[0] == 's') v = e[1] == 'm' ? kXchgSmCopier : kXchgStores;  // "sm" / "stores"
     if (e && e[0] == 'k') v = kXchgStoresRowGather;  // "k1": epilogue stores, row-gather kernel K1
     g_xchg_strategy.store(v, std::memory_order_relaxed);
     return v;
@@ -475,7 +508,8 @@ sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A, const v
     // continuously, so its peer stores are spread over the whole kernel — ran the same exchange in 5.52 ms/step.
     int strategy = allgather_strategy();
     if (strategy == kXchgAuto) strategy = n_peers <= 4 ? kXchgCopyEngines : kXchgStoresRowGather;
-    if (n_peers == 1 || strategy != kXchgCopyEngines || v.rows == 0 || n == 0) {
+    const bool chunked = strategy == kXchgCopyEngines || strategy == kXchgSmCopier;
+    if (n_peers == 1 || !chunked || v.rows == 0 || n == 0) {
         if (n_peers > 1 && strategy == kXchgStoresRowGather) v.owner = nullptr;  // ad-hoc view: never the streaming kernel
         return spmm_device(ctx, s, v, A->dtype, false, alpha, beta, SDB_LAYOUT_ROW_MAJOR, dX, n, ldx, dY_peers,
                            n_peers, self, row0, ldy);
@@ -484,6 +518,14 @@ sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A, const v
     SDB_TRY(ensure_exchange_streams(ctx, n_peers));
     const size_t row_bytes = size_t(n) * dtype_size(A->dtype);
     const size_t pitch = size_t(ldy) * dtype_size(A->dtype);
+    // the copier kernel moves whole packed rows in 16-byte packs; anything else goes through the copy engines
+    bool sm_push = strategy == kXchgSmCopier && pitch == row_bytes && row_bytes % 16 == 0;
+    for (int q = 0; q < n_peers && sm_push; ++q) sm_push = aligned16(dY_peers[q]);
+    const int reserve = sm_push ? std::max(1, std::min(ctx->sm_count / 2, g_xchg_sms.load(std::memory_order_relaxed))) : 0;
+    spmm_slab_reserve_sms(reserve);
+    struct Unreserve {
+        ~Unreserve() { spmm_slab_reserve_sms(0); }
+    } unreserve;
     // chunking: whole waves of the streaming kernel when it will run, else quarters of the shard
     int64_t chunk = spmm_slab_wave_rows(ctx, v, A->dtype, n, ldx, /*count_call=*/true);
     const int want_chunks = g_xchg_chunks.load(std::memory_order_relaxed);
@@ -510,6 +552,19 @@ sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A, const v
         ctx->xchg_next_event = (ctx->xchg_next_event + 1) % Context::kExchangeEvents;
         SDB_CUDA(cudaEventRecord(done, s));
         const size_t off = size_t(row0 + r0) * pitch;
+        if (sm_push) {
+            cudaStream_t cs = ctx->xchg_stream[self];  // one stream: the copier kernels of successive chunks queue up
+            SDB_CUDA(cudaStreamWaitEvent(cs, done, 0));
+            PushTargets t;
+            int n_dst = 0;
+            for (int q = 0; q < n_peers; ++q)
+                if (q != self) t.dst[n_dst++] = reinterpret_cast<uint4*>(static_cast<char*>(dY_peers[q]) + off);
+            for (int q = n_dst; q < kMaxPeers; ++q) t.dst[q] = nullptr;
+            const size_t n_vec = size_t(r1 - r0) * row_bytes / 16;
+            SDB_LAUNCH(push_rows_kernel, unsigned(reserve) * 2, kPushThreads, 0, cs,
+                       reinterpret_cast<const uint4*>(static_cast<const char*>(dY_peers[self]) + off), t, n_dst, n_vec);
+            continue;
+        }
         for (int q = 0; q < n_peers; ++q) {
             if (q == self) continue;
             cudaStream_t cs = ctx->xchg_stream[q];
@@ -524,7 +579,7 @@ sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A, const v
         }
     }
     for (int q = 0; q < n_peers; ++q) {  // the call is complete on `s` once every push has landed
-        if (q == self) continue;
+        if (sm_push ? q != self : q == self) continue;
         SDB_CUDA(cudaEventRecord(ctx->xchg_done[q], ctx->xchg_stream[q]));
         SDB_CUDA(cudaStreamWaitEvent(s, ctx->xchg_done[q], 0));
     }
@@ -532,10 +587,16 @@ sdb_status sdb_spmm_dev_allgather(const double* alpha, const sdb_mat* A, const v
 }
 
 sdb_status sdb_set_allgather(int strategy, int chunks) {
-    SDB_REQUIRE(strategy >= kXchgAuto && strategy <= kXchgStoresRowGather && chunks >= 0 && chunks <= 64,
-                SDB_STATUS_INVALID_VALUE, "sdb_set_allgather: strategy 0..3, chunks 0..64");
+    SDB_REQUIRE(strategy >= kXchgAuto && strategy <= kXchgSmCopier && chunks >= 0 && chunks <= 64,
+                SDB_STATUS_INVALID_VALUE, "sdb_set_allgather: strategy 0..4, chunks 0..64");
     g_xchg_strategy.store(strategy, std::memory_order_relaxed);
     g_xchg_chunks.store(chunks, std::memory_order_relaxed);
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_set_allgather_sms(int sms) {
+    SDB_REQUIRE(sms >= 1 && sms <= 64, SDB_STATUS_INVALID_VALUE, "sdb_set_allgather_sms: 1..64");
+    g_xchg_sms.store(sms, std::memory_order_relaxed);
     return SDB_STATUS_SUCCESS;
 }
 

@@ -289,7 +289,13 @@ int slab_rpw() {
 }
 int slab_rows_per_sm() { return slab_variant() == 5 ? 416 : 384; }
 
+// SMs the persistent grid leaves free (the "sm" exchange strategy runs its copier CTAs there); per host thread,
+// set around one sdb_spmm_dev_allgather call
+thread_local int t_reserved_sms = 0;
+
 }  // namespace
+
+void spmm_slab_reserve_sms(int sms) { t_reserved_sms = sms < 0 ? 0 : sms; }
 
 template <typename T, int RPW, int WARPS, int U, int CTAS>
 static sdb_status launch_stream(cudaStream_t s, const CsrView& a, const sdb_mat* m, const T* X, int64_t ldx, T alpha,
@@ -303,7 +309,8 @@ static sdb_status launch_stream(cudaStream_t s, const CsrView& a, const sdb_mat*
     const int64_t* sub_indptr = a.indptr + a.sub_begin;
     row0 += a.sub_begin;
     const int64_t n_blocks = (sub_rows + kRows - 1) / kRows;
-    const unsigned grid = unsigned(std::min<int64_t>(n_blocks, int64_t(sm_count) * CTAS));
+    const int live_sms = std::max(1, sm_count - t_reserved_sms);
+    const unsigned grid = unsigned(std::min<int64_t>(n_blocks, int64_t(live_sms) * CTAS));
     SDB_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<T, RPW, WARPS, U, CTAS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmem)));
     note_spmm_kernel("spmm_stream_kernel<%s,%d,%d,%d,%d>", dtype_cname(Num<T>::dtype), RPW, WARPS, U, CTAS);
@@ -354,7 +361,7 @@ bool spmm_slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx) {
 int64_t spmm_slab_wave_rows(const Context* ctx, const CsrView& a, int dtype, int64_t n, int64_t ldx, bool count_call) {
     if (!slab_wanted(a, dtype, n, ldx, count_call)) return 0;
     if (a.owner->strict_sorted == -1) return 0;
-    return int64_t(ctx->sm_count) * slab_rows_per_sm();
+    return int64_t(std::max(1, ctx->sm_count - t_reserved_sms)) * slab_rows_per_sm();
 }
 
 static bool slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx, bool count_call) {

@@ -202,14 +202,16 @@ class RowShardedSpMM:
             dist.all_gather_into_tensor(self._torch_panel, local, group=self.group)
 
     # ------------------------------------------------------------------ exchange strategy
-    STRATEGIES = {"auto": 0, "ce": 1, "stores": 2, "k1": 3}
+    STRATEGIES = {"auto": 0, "ce": 1, "stores": 2, "k1": 3, "sm": 4}
 
     @staticmethod
-    def set_exchange(strategy="auto", chunks=0):
+    def set_exchange(strategy="auto", chunks=0, sms=None):
         """Process-wide exchange strategy of the fused mode (sdb_set_allgather): 'auto', 'ce' (copy engines push
         row chunks while the next chunk's kernel runs; ``chunks`` = how many), 'stores' (the kernel's epilogue
         stores into the peer panels), 'k1' (the same with the row-gather kernel)."""
         check(SDB.lib.sdb_set_allgather(RowShardedSpMM.STRATEGIES[strategy], int(chunks)), "sdb_set_allgather")
+        if sms:
+            check(SDB.lib.sdb_set_allgather_sms(int(sms)), "sdb_set_allgather_sms")
 
     def autotune(self, beta=0.0, stream=None, candidates=None, reps=3):
         """Time the exchange strategies on the live topology (device time, max over ranks) and keep the fastest.
@@ -223,11 +225,12 @@ class RowShardedSpMM:
         if self.mode != "fused" or self.world == 1:
             return {"chosen": None, "steps_run": 0}
         if candidates is None:
-            candidates = [("ce", 5), ("ce", 10), ("ce", 20), ("stores", 0), ("k1", 0)]
+            candidates = [("ce", 5, 0), ("ce", 10, 0), ("ce", 20, 0), ("sm", 10, 8), ("sm", 10, 16), ("sm", 20, 16),
+                          ("stores", 0, 0), ("k1", 0, 0)]
         stream = stream or torch.cuda.current_stream()
         timings, steps_run = [], 0
-        for strategy, chunks in candidates:
-            self.set_exchange(strategy, chunks)
+        for strategy, chunks, sms in candidates:
+            self.set_exchange(strategy, chunks, sms)
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -241,10 +244,10 @@ class RowShardedSpMM:
             steps_run += reps + 1
             t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            timings.append({"strategy": strategy, "chunks": chunks, "ms_per_step": float(t.item()),
+            timings.append({"strategy": strategy, "chunks": chunks, "sms": sms, "ms_per_step": float(t.item()),
                             "kernel": _lib.last_spmm_kernel()})
         best = min(timings, key=lambda r: r["ms_per_step"])  # identical on every rank (all-reduced times)
-        self.set_exchange(best["strategy"], best["chunks"])
+        self.set_exchange(best["strategy"], best["chunks"], best["sms"])
         dist.barrier(group=self.group)
         return {"chosen": best, "candidates": timings, "steps_run": steps_run}
 

@@ -283,5 +283,5 @@ def test_gram_of_a_dense_array(dtype, order, transpose):
     assert np.abs(np.triu(got) - np.triu(full)).max() <= tol and np.all(np.tril(got, -1) == 0)
     out = np.asarray(np.full((n, n), 7.0, dtype=dtype), order=order)
     res = sdb.gram_matrix_mkl(a, transpose=transpose, out=out, out_scalar=2.0)
-    assert res is out and np.all(np.tril(out, -1) == 7.0)
+    assert res is out and np.all(out[np.tril_indices(n, -1)] == 7.0)
     assert np.abs(np.triu(out) - np.triu(full + 14.0)).max() <= tol

@@ -83,6 +83,9 @@ CASES = [
     ("stores", "1", 10_000, "spmm_rowmajor"),
     ("stores", "2", 300_000, "spmm_stream"),
     ("k1", "2", 300_000, "spmm_rowmajor"),
+    ("sm", "1", 10_000, "spmm_rowmajor"),
+    ("sm", "1", 300_000, "spmm_rowmajor"),
+    ("sm", "2", 300_000, "spmm_stream"),
     ("auto", "0", 10_000, "spmm_rowmajor"),
 ]
 
