@@ -313,7 +313,7 @@ SDB_API int        sdb_last_error(char* buf, int len);
 
 /* Run-time switches (process-wide), each also readable from the environment at first use:
  *   "bsr_mma"       SDB_BSR_MMA        BSR x dense on the tensor cores (DMMA fp64, 3xTF32 fp32): -1 automatic, 0 off, 1 on
- *   "spgemm_wide"   SDB_SPGEMM_WIDE    wide SpGEMM rows: 0 automatic, 1 full-sweep bitmap, 2 bitmap with summary
+ *   "spgemm_wide"   SDB_SPGEMM_WIDE    wide SpGEMM rows: 0 automatic (bitmap with a shared-memory summary), 1 full-sweep bitmap
  *   "dense_mode"    SDB_DENSE_MODE     dense-output products: 0 automatic, 1 shared-memory tiles, 2 global reductions
  *   "dense_threads" SDB_DENSE_THREADS  threads per CTA of the global-reduction kernel (0 = default)
  *   "dense_ctas"    SDB_DENSE_CTAS     resident CTAs per SM of that kernel (0 = as many as fit)

@@ -19,6 +19,7 @@ if not _BUILDING:
         dot_product_transpose_mkl,
         get_version_string,
         gram_matrix_mkl,
+        optimize,
         set_debug_mode,
     )
     from ._lib import device_count, kernel_launches, last_spmm_kernel, last_timing_ms  # noqa: F401
@@ -35,4 +36,5 @@ __all__ = [
     "last_timing_ms",
     "last_spmm_kernel",
     "ResidentCSR",
+    "optimize",
 ]

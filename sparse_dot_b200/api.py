@@ -13,6 +13,15 @@ import scipy.sparse as _sps
 from . import _lib
 from . import _ops
 from ._validate import is_dense_vector as _is_vec
+from .resident import ResidentCSR as _ResidentCSR
+
+
+def optimize(matrix):
+    """Upload a scipy CSR / CSC / BSR matrix once and return a device-resident operand that dot_product_mkl accepts
+    as its left argument (close() it, or use it as a context manager).  The analogue of mkl_sparse_optimize, which
+    the reference never calls: repeated products with the same matrix skip its upload and, from the second product
+    on, run the L2-tiled streaming SpMM built by the handle's inspector."""
+    return _ResidentCSR(matrix)
 
 
 def set_debug_mode(debug_bool):
@@ -58,6 +67,13 @@ def dot_product_mkl(matrix_a, matrix_b, cast=False, copy=True, reorder_output=Fa
     """
     _warn_debug_flag(debug)
     _print_debug()
+    # a matrix uploaded once with optimize() / ResidentCSR: only the dense panels cross PCIe, and from the second
+    # product on the handle runs the inspector-built streaming kernel (the reference never calls mkl_sparse_optimize;
+    # this is the opt-in analogue)
+    if isinstance(matrix_a, _ResidentCSR):
+        if _sps.issparse(matrix_b) or isinstance(matrix_b, _ResidentCSR):
+            raise ValueError("a resident left operand multiplies dense arrays; use ResidentCSR.matmat for sparse ones")
+        return matrix_a.dot(matrix_b, out=out, out_scalar=out_scalar)
     n_sparse = int(_sps.issparse(matrix_a)) + int(_sps.issparse(matrix_b))
 
     if n_sparse == 2:

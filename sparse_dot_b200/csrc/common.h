@@ -62,7 +62,7 @@ extern thread_local char t_spmm_kernel[128];
 // through sdb_set_option (tests and sweeps flip them inside one process).  -1 / 0 mean "automatic".
 enum Option {
     kOptBsrMma = 0,     // "bsr_mma"       SDB_BSR_MMA        BSR x dense on tensor cores: -1 auto, 0 off, 1 on
-    kOptSpgemmWide,     // "spgemm_wide"   SDB_SPGEMM_WIDE    wide SpGEMM rows: 0 auto, 1 full-sweep bitmap, 2 summary
+    kOptSpgemmWide,     // "spgemm_wide"   SDB_SPGEMM_WIDE    wide SpGEMM rows: 0 auto (bitmap with summary), 1 full-sweep bitmap
     kOptDenseMode,      // "dense_mode"    SDB_DENSE_MODE     dense-output products: 0 auto, 1 shared tiles, 2 global reductions
     kOptDenseThreads,   // "dense_threads" SDB_DENSE_THREADS  threads per CTA of the global-reduction kernel (0 = 1024)
     kOptDenseCtas,      // "dense_ctas"    SDB_DENSE_CTAS     resident CTAs per SM of that kernel (0 = what fits)

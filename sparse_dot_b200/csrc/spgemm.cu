@@ -300,6 +300,10 @@ __global__ void __launch_bounds__(kHashWarps * 32)
 // its first atomic, so a lane keeps kWalkBatch dependent load chains in flight instead of one (an atomic is a
 // barrier for the compiler's scheduling of the loads that follow it) — the wide rows are latency-bound walks.
 constexpr int kWalkBatch = 4;
+template <typename T> struct RankedProduct {  // a product and where it lands in its output row
+    int rank;
+    T v;
+};
 template <typename T, bool NEED_VAL, int kStageEntries, typename Item, typename Pre, typename Post>
 __device__ __forceinline__ void for_each_product_cta_batched(int64_t i, const int64_t* __restrict__ l_ptr,
                                                              const int32_t* __restrict__ l_idx,
@@ -430,10 +434,6 @@ __global__ void __launch_bounds__(THREADS)
 //      is atomically added to c_val[row start + rank] (a compact, L2-resident target);
 //   5. clear the bitmap.
 // The result rows are sorted, so sdb_order has nothing to do for them.
-template <typename T> struct RankedProduct {  // a product and where it lands in its output row
-    int rank;
-    T v;
-};
 constexpr int kPieceWords = 128;
 constexpr int kPiecesPerRound = 1024;  // == blockDim.x of the wide kernel
 
@@ -586,74 +586,82 @@ __global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
 }
 
 
-// Wide rows, second formulation (the default): the same bitmap, but every pass after the first touches only the
-// bitmap words the row has set.  The first version swept the whole column range (cols / 8 bytes of bitmap plus
-// as much again of per-word ranks) three times per row whatever the row held; at 4M columns and two CTAs per SM
-// those slices no longer fit L2 and the bin ran at the speed of the sweeps' DRAM traffic (38 000 rows x 2.5 MB at
-// R-MAT scale 22).  Here a word-level SUMMARY of the bitmap lives in shared memory — bit b of summary[g] says
-// bitmap word 32 g + b is non-zero — together with two per-group prefix arrays, and
-//   1. the products are walked: atomicOr on the bitmap word (global, fire-and-forget) and, only while the
-//      summary bit is still clear, an atomicOr on the summary (shared);
-//   2. one lane per group of 32 words walks the words its group has set: populations per group -> block-wide
-//      exclusive scans -> entry / set-word offsets per group;
-//      [symbolic stops here: c_len, then only the set words are cleared]
-//   3. second walk of the non-empty groups: the k-th set word's output rank goes into a COMPACT array
-//      (k = group offset + popc of the lower summary bits), columns are written in ascending order;
-//   4. the products are walked again: rank = compact_rank[k] + popc(lower bits of the word) and the product is
-//      atomically added at c_val[row start + rank];
-//   5. the set words and the summary are cleared.
-// Per row the global traffic is proportional to the words it sets, not to the column count.  The result rows
-// come out sorted.  Shared memory: 12 bytes per 1024 columns (up to ~17M columns; beyond, the first version runs).
-template <typename T, bool NUMERIC>
-__global__ void __launch_bounds__(1024)
+// Wide rows, second formulation (the default while its index fits shared memory): the same bitmap, but every
+// pass after the first touches only the bitmap words the row has set, and a product finds its rank with ONE load.
+// The first version sweeps the whole column range (cols / 8 bytes of bitmap plus as much again of per-word ranks)
+// three times per row whatever the row holds; at 4M columns and two CTAs per SM those slices no longer fit L2 and
+// ncu shows the bin moving 100 GB of DRAM traffic at 4.6 TB/s (profiles/r2d_spgemm_ef1_summary.txt).  Here
+//   * the bitmap is an array of (word, rank) PAIRS — 8 bytes per 32 columns — so the value pass reads the word and
+//     the output rank of its first bit with one 8-byte load instead of two scattered 4-byte loads;
+//   * a word-level SUMMARY of the bitmap lives in shared memory (bit b of summary[g] says word 32 g + b is
+//     non-zero) and the sweeps are driven by it: one LANE per group of 32 words walks only the words its group has
+//     set (consecutive lanes take consecutive groups, so the dense low-column groups of a power-law row fill whole
+//     warps), which makes a sweep a handful of latency rounds instead of 32 dependent iterations.
+// Steps: 1. walk the products: atomicOr on the pair's word (global, fire-and-forget) and, while the summary bit is
+// still clear, an atomicOr on the summary (shared); 2. populations per group -> block-wide exclusive scan
+// [symbolic stops here: c_len, then only the set words are cleared]; 3. ranks into the pairs, columns emitted in
+// ascending order; 4. walk the products again: one pair load, rank = pair.rank + popc(lower bits), atomic add at
+// c_val[row start + rank]; 5. clear the set pairs and the summary.  Traffic per row is proportional to the words
+// it sets.  BATCHED (rows above kWideMax, one CTA per SM): the walks keep kWalkBatch products per lane in flight.
+// Shared memory: 8 bytes per 1024 columns.
+template <typename T, bool NUMERIC, bool BATCHED>
+__global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
     spgemm_wide2_kernel(const int32_t* __restrict__ list, unsigned n_list, int64_t words_padded, int n_groups,
                         const int64_t* __restrict__ l_ptr, const int32_t* __restrict__ l_idx,
                         const T* __restrict__ l_val, const int32_t* __restrict__ l_pos,
                         const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
-                        const T* __restrict__ r_val, bool upper, unsigned* __restrict__ bitmaps,
-                        int32_t* __restrict__ word_ranks, int32_t* __restrict__ c_len,
-                        const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
+                        const T* __restrict__ r_val, bool upper, uint2* __restrict__ pairs_all,
+                        int32_t* __restrict__ c_len, const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx,
+                        T* __restrict__ c_val) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned* summary = reinterpret_cast<unsigned*>(smem_raw);           // [n_groups]
-    int* grp_ent = reinterpret_cast<int*>(summary + n_groups);           // [n_groups] entries before group g
-    int* grp_wrd = grp_ent + n_groups;                                   // [n_groups] set words before group g
-    __shared__ int warp_ent[32], warp_wrd[32];
+    unsigned* summary = reinterpret_cast<unsigned*>(smem_raw);  // [n_groups]
+    int* grp_ent = reinterpret_cast<int*>(summary + n_groups);  // [n_groups] entries before group g
+    __shared__ int warp_ent[32];
     __shared__ LStage<T, 256> stage;
-    unsigned* bm = bitmaps + int64_t(blockIdx.x) * words_padded;
-    int32_t* wr = NUMERIC ? word_ranks + int64_t(blockIdx.x) * words_padded : nullptr;
+    uint2* pairs = pairs_all + int64_t(blockIdx.x) * words_padded;  // .x = bitmap word, .y = rank of its first bit
+    unsigned* pair_words = reinterpret_cast<unsigned*>(pairs);       // word of pair w at index 2 w
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     for (int g = tid; g < n_groups; g += blockDim.x) summary[g] = 0u;
     __syncthreads();
-    // groups handled by one thread in the block-wide scans (contiguous, so the scan is over ascending columns)
+    // groups handled by one thread in the block-wide scan (contiguous, so the scan is over ascending columns)
     const int per_thread = (n_groups + int(blockDim.x) - 1) / int(blockDim.x);
+    auto mark = [&](int32_t col) {
+        const int w = col >> 5;
+        atomicOr(pair_words + 2 * int64_t(w), 1u << (col & 31));
+        const unsigned sb = 1u << (w & 31);
+        volatile unsigned* sp = summary + (w >> 5);
+        if (!(*sp & sb)) atomicOr(summary + (w >> 5), sb);
+    };
     for (unsigned li = blockIdx.x; li < n_list; li += gridDim.x) {
         const int64_t i = list[li];
         // ---- 1. membership
-        for_each_product_cta<T, false, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
-                                            [&](int32_t col, T, int64_t) {
-                                                if (upper && int64_t(col) < i) return;
-                                                const int w = col >> 5;
-                                                atomicOr(&bm[w], 1u << (col & 31));
-                                                const unsigned sb = 1u << (w & 31);
-                                                volatile unsigned* sp = summary + (w >> 5);
-                                                if (!(*sp & sb)) atomicOr(summary + (w >> 5), sb);
-                                            });
+        if constexpr (BATCHED) {
+            for_each_product_cta_batched<T, false, 256, int32_t>(
+                i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage, [&](int32_t col, T, int64_t) { return col; },
+                [&](int32_t col) {
+                    if (upper && int64_t(col) < i) return;
+                    mark(col);
+                });
+        } else {
+            for_each_product_cta<T, false, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
+                                                [&](int32_t col, T, int64_t) {
+                                                    if (upper && int64_t(col) < i) return;
+                                                    mark(col);
+                                                });
+        }
         __syncthreads();
-        // ---- 2. populations per group: one LANE per group (consecutive lanes take consecutive groups, so the dense
-        // low-column groups of a power-law row fill whole warps), each lane walking only the words its group has set,
-        // four loads in flight
+        // ---- 2. populations per group, four word loads in flight per lane
         for (int g = tid; g < n_groups; g += blockDim.x) {
             unsigned sm = summary[g];
-            const unsigned* gw = bm + int64_t(g) * 32;
+            const unsigned* gw = pair_words + int64_t(g) * 64;
             int ce = 0;
-            grp_wrd[g] = __popc(sm);
             while (sm) {
                 unsigned w4[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     w4[u] = 0u;
                     if (sm) {
-                        w4[u] = __ldcg(gw + (__ffs(sm) - 1));
+                        w4[u] = __ldcg(gw + 2 * (__ffs(sm) - 1));
                         sm &= sm - 1;
                     }
                 }
@@ -662,60 +670,46 @@ __global__ void __launch_bounds__(1024)
             grp_ent[g] = ce;
         }
         __syncthreads();
-        // block-wide exclusive scans of both arrays: thread-local run, warp scan, scan of the warp totals
-        int e_sum = 0, w_sum = 0;
+        // block-wide exclusive scan: thread-local run, warp scan, scan of the warp totals
+        int e_sum = 0;
         const int g0 = tid * per_thread, g1 = min(n_groups, g0 + per_thread);
-        for (int g = g0; g < g1; ++g) {
-            e_sum += grp_ent[g];
-            w_sum += grp_wrd[g];
-        }
-        int e_inc = e_sum, w_inc = w_sum;
+        for (int g = g0; g < g1; ++g) e_sum += grp_ent[g];
+        int e_inc = e_sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const int eo = __shfl_up_sync(0xffffffffu, e_inc, d), wo = __shfl_up_sync(0xffffffffu, w_inc, d);
-            if (lane >= d) {
-                e_inc += eo;
-                w_inc += wo;
-            }
+            const int eo = __shfl_up_sync(0xffffffffu, e_inc, d);
+            if (lane >= d) e_inc += eo;
         }
-        if (lane == 31) {
-            warp_ent[warp] = e_inc;
-            warp_wrd[warp] = w_inc;
-        }
+        if (lane == 31) warp_ent[warp] = e_inc;
         __syncthreads();
-        int e_before = 0, w_before = 0, e_total = 0;
+        int e_before = 0, e_total = 0;
         for (int x = 0; x < nwarps; ++x) {
-            const int te = warp_ent[x], tw = warp_wrd[x];
-            if (x < warp) {
-                e_before += te;
-                w_before += tw;
-            }
+            const int te = warp_ent[x];
+            if (x < warp) e_before += te;
             e_total += te;
         }
-        int e_run = e_before + e_inc - e_sum, w_run = w_before + w_inc - w_sum;
+        int e_run = e_before + e_inc - e_sum;
         for (int g = g0; g < g1; ++g) {
-            const int ce = grp_ent[g], cw = grp_wrd[g];
+            const int ce = grp_ent[g];
             grp_ent[g] = e_run;
-            grp_wrd[g] = w_run;
             e_run += ce;
-            w_run += cw;
         }
         __syncthreads();
         if (!NUMERIC) {
             if (tid == 0) c_len[i] = e_total;
         } else {
-            // ---- 3. ranks of the set words (compact) and ordered emission
+            // ---- 3. ranks into the pairs and ordered emission
             const int64_t out0 = c_ptr[i];
             for (int g = tid; g < n_groups; g += blockDim.x) {
                 unsigned sm = summary[g];
                 if (!sm) continue;
-                int rank = grp_ent[g], k = grp_wrd[g];
+                int rank = grp_ent[g];
                 while (sm) {
                     const int b = __ffs(sm) - 1;
                     sm &= sm - 1;
                     const int64_t w = int64_t(g) * 32 + b;
-                    unsigned word = __ldcg(bm + w);
-                    wr[k++] = rank;
+                    unsigned word = __ldcg(pair_words + 2 * w);
+                    pair_words[2 * w + 1] = unsigned(rank);
                     while (word) {
                         const int bit = __ffs(word) - 1;
                         word &= word - 1;
@@ -726,26 +720,41 @@ __global__ void __launch_bounds__(1024)
                 }
             }
             __syncthreads();
-            // ---- 4. values: every product is added at its column's rank
-            for_each_product_cta<T, true, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
-                                               [&](int32_t col, T a, int64_t q) {
-                                                   if (upper && int64_t(col) < i) return;
-                                                   const int w = col >> 5, g = w >> 5;
-                                                   const unsigned sm = summary[g];
-                                                   const int k = grp_wrd[g] + __popc(sm & ((1u << (w & 31)) - 1u));
-                                                   const unsigned below = __ldcg(bm + w) & ((1u << (col & 31)) - 1u);
-                                                   const int rank = __ldcg(wr + k) + __popc(below);
-                                                   atomic_add(c_val + out0 + rank, mul(a, r_val[q]));
-                                               });
+            // ---- 4. values: one pair load per product
+            auto rank_of = [&](int32_t col) {
+                const uint2 e = __ldcg(pairs + (col >> 5));
+                return int(e.y) + __popc(e.x & ((1u << (col & 31)) - 1u));
+            };
+            if constexpr (BATCHED) {
+                for_each_product_cta_batched<T, true, 256, RankedProduct<T>>(
+                    i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
+                    [&](int32_t col, T a, int64_t q) {
+                        RankedProduct<T> it;
+                        it.rank = -1;
+                        if (upper && int64_t(col) < i) return it;
+                        it.rank = rank_of(col);
+                        it.v = mul(a, ldg(r_val + q));
+                        return it;
+                    },
+                    [&](const RankedProduct<T>& it) {
+                        if (it.rank >= 0) atomic_add(c_val + out0 + it.rank, it.v);
+                    });
+            } else {
+                for_each_product_cta<T, true, 256>(i, l_ptr, l_idx, l_val, l_pos, r_ptr, r_idx, stage,
+                                                   [&](int32_t col, T a, int64_t q) {
+                                                       if (upper && int64_t(col) < i) return;
+                                                       atomic_add(c_val + out0 + rank_of(col), mul(a, r_val[q]));
+                                                   });
+            }
             __syncthreads();
         }
-        // ---- 5. clear the set words and the summary
+        // ---- 5. clear the set pairs' words and the summary
         for (int g = tid; g < n_groups; g += blockDim.x) {
             unsigned sm = summary[g];
             if (!sm) continue;
             summary[g] = 0u;
             while (sm) {
-                bm[int64_t(g) * 32 + (__ffs(sm) - 1)] = 0u;
+                pair_words[2 * (int64_t(g) * 32 + (__ffs(sm) - 1))] = 0u;
                 sm &= sm - 1;
             }
         }
@@ -817,31 +826,37 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
         const int64_t n_cols = r.cols;
         const int64_t words = (((n_cols + 31) >> 5) + kPieceWords - 1) / kPieceWords * kPieceWords;  // padded
         // resident CTAs: bounded by the list, two per SM, and ~2 GiB of scratch
-        const int64_t per_cta = words * 4 * (NUMERIC ? 2 : 1);
+        const int64_t per_cta = words * 8;
         int64_t max_ctas = 2 * int64_t(ctx->sm_count);
         max_ctas = std::max<int64_t>(1, std::min<int64_t>(max_ctas, (int64_t(2) << 30) / std::max<int64_t>(per_cta, 1)));
-        DevBuf bm, ranks;
-        SDB_TRY(bm.alloc(size_t(max_ctas * words) * 4, s));
-        SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(max_ctas * words) * 4, s));
-        if (NUMERIC) SDB_TRY(ranks.alloc(size_t(max_ctas * words) * 4, s));
-        // The summary formulation is opt-in ("spgemm_wide" = 2): measured on R-MAT scale 22 (profiles/r2_logs/
-        // spgemm_trace_ef1*.log) it is SLOWER than the full sweeps (symbolic 15.3 vs 7.1 ms, numeric 35.0 vs 25.5 ms):
-        // the per-row cost is the latency of the sweep iterations, not their DRAM traffic, and a warp walking 32-word
-        // groups makes four times as many dependent iterations as one loading 128-word pieces.
+        // "spgemm_wide": 0 = the summary formulation (while its index fits shared memory), 1 = the full-sweep
+        // bitmap for every wide row.  Measured on R-MAT scale 22 (profiles/r2_logs/spgemm_trace_*.log): numeric wide
+        // bin 186 -> 136 ms at edge factor 4, 21.7 -> 15.1 ms at edge factor 1.
         const int forced = get_option(kOptSpgemmWide);
         const int64_t n_groups = words / 32;
-        const size_t smem2 = size_t(n_groups) * 12;
+        const size_t smem2 = size_t(n_groups) * 8;
+        const bool summary = forced != 1 && smem2 <= size_t(96) * 1024;
+        DevBuf bm, ranks;
+        SDB_TRY(bm.alloc(size_t(max_ctas * words) * (summary ? 8 : 4), s));
+        SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(max_ctas * words) * (summary ? 8 : 4), s));
+        if (NUMERIC && !summary) SDB_TRY(ranks.alloc(size_t(max_ctas * words) * 4, s));
         for (int b = 3; b <= 4; ++b) {
             if (h[b] == 0) continue;
-            const bool batched = b == 4 && forced != 1;  // "spgemm_wide" = 1: the unbatched walk for every wide row
+            const bool batched = b == 4 && forced != 1;
             const int64_t ctas = std::min<int64_t>(std::min<int64_t>(h[b], max_ctas),
                                                    int64_t(batched ? 1 : 2) * ctx->sm_count);
-            if (forced == 2 && smem2 <= size_t(96) * 1024) {
-                auto kernel = spgemm_wide2_kernel<T, NUMERIC>;
-                SDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              int(std::max<size_t>(smem2, 48 * 1024))));
-                SDB_LAUNCH(kernel, unsigned(ctas), 1024, smem2, s, lists.list[b], h[b], words, int(n_groups), lp, li, lv,
-                           lq, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx, c_val);
+#define SDB_WIDE2(BATCH)                                                                                              \
+    do {                                                                                                              \
+        auto kernel = spgemm_wide2_kernel<T, NUMERIC, BATCH>;                                                         \
+        SDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
+                                      int(std::max<size_t>(smem2, 48 * 1024))));                                      \
+        SDB_LAUNCH(kernel, unsigned(ctas), 1024, smem2, s, lists.list[b], h[b], words, int(n_groups), lp, li, lv, lq, \
+                   rp, ri, rv, upper, static_cast<uint2*>(bm.p), c_len, c_ptr, c_idx, c_val);                         \
+    } while (0)
+            if (summary && batched) {
+                SDB_WIDE2(true);
+            } else if (summary) {
+                SDB_WIDE2(false);
             } else if (batched) {
                 SDB_LAUNCH((spgemm_wide_kernel<T, NUMERIC, true>), unsigned(ctas), 1024, 0, s, lists.list[b], h[b], words,
                            lp, li, lv, lq, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx,
@@ -851,7 +866,9 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
                            lp, li, lv, lq, rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(), c_len, c_ptr, c_idx,
                            c_val);
             }
-            trace(s, "spgemm: %s bin done (%lld CTAs)", b == 3 ? "wide" : "huge", (long long)ctas);
+#undef SDB_WIDE2
+            trace(s, "spgemm: %s bin done (%lld CTAs, %s)", b == 3 ? "wide" : "huge", (long long)ctas,
+                  summary ? "summary" : "full sweep");
         }
     }
     return SDB_STATUS_SUCCESS;

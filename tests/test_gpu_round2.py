@@ -171,11 +171,11 @@ def test_bsr_tensor_core_falls_back_when_not_covered():
 
 
 # ===================================================== SpGEMM: both wide-row formulations, all four bins
-@pytest.mark.parametrize("wide", [1, 2])
+@pytest.mark.parametrize("wide", [0, 1])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_spgemm_wide_formulations_agree_with_the_oracle(dtype, wide):
     """_sparse_sparse.py:35-40 (mkl_sparse_spmm) + reorder_output: power-law rows reach the warp, small, CTA and
-    wide bins; `spgemm_wide` picks the full-sweep bitmap (1) or the summary formulation (2)."""
+    wide bins; `spgemm_wide` picks the summary formulation (0, default) or the full-sweep bitmap (1)."""
     a = cs.rmat_csr(13, 8, dtype, seed=1)
     b = cs.rmat_csr(13, 8, dtype, seed=2)
     _lib.set_option("spgemm_wide", wide)
@@ -285,3 +285,21 @@ def test_gram_of_a_dense_array(dtype, order, transpose):
     res = sdb.gram_matrix_mkl(a, transpose=transpose, out=out, out_scalar=2.0)
     assert res is out and np.all(out[np.tril_indices(n, -1)] == 7.0)
     assert np.abs(np.triu(out) - np.triu(full + 14.0)).max() <= tol
+
+
+# ===================================================== optimize(): the public call reaches the streaming kernel
+def test_optimize_makes_dot_product_mkl_reuse_the_handle_and_reach_the_streaming_kernel():
+    a, x, y0 = cs.c2_workload(120_000, 500_000, 40, 128, seed=6)
+    want = orc.c_spmm(a, x, beta=0.5, y=y0.copy())
+    _lib_env = None
+    with sdb.optimize(a) as ra:
+        kernels = []
+        for _ in range(3):
+            got = sdb.dot_product_mkl(ra, x, out=y0.copy(), out_scalar=0.5)
+            kernels.append(sdb.last_spmm_kernel())
+            assert cs.rel_err(got, want) <= 1e-5
+        assert kernels[0].startswith("spmm_rowmajor")  # first product: the row-gather kernel
+        # X is 256 MB (> 192 MB) and one wave of rows reuses X rows >= 1.5 times: the inspector runs on the 2nd call
+        assert kernels[2].startswith("spmm_stream"), kernels
+        with pytest.raises(ValueError):
+            sdb.dot_product_mkl(ra, a)
