@@ -261,6 +261,11 @@ class CopyPool {
     };
     CopyPool() {
         unsigned hw = std::thread::hardware_concurrency();
+        // one process per GPU (torchrun exports LOCAL_WORLD_SIZE): the ranks of a node share its cores
+        if (const char* lw = getenv("LOCAL_WORLD_SIZE")) {
+            const int ranks = atoi(lw);
+            if (ranks > 1) hw = std::max(1u, hw / unsigned(ranks));
+        }
         int n = hw > 1 ? int(hw) - 1 : 0;
         if (n > 15) n = 15;
         if (const char* e = getenv("SDB_COPY_THREADS")) n = std::max(0, std::min(63, atoi(e) - 1));

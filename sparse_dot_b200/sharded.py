@@ -225,8 +225,8 @@ class RowShardedSpMM:
         if self.mode != "fused" or self.world == 1:
             return {"chosen": None, "steps_run": 0}
         if candidates is None:
-            candidates = [("ce", 5, 0), ("ce", 10, 0), ("ce", 20, 0), ("sm", 10, 8), ("sm", 10, 16), ("sm", 20, 16),
-                          ("stores", 0, 0), ("k1", 0, 0)]
+            candidates = [("ce", 5, 0), ("ce", 10, 0), ("ce", 20, 0), ("sm", 10, 8), ("sm", 20, 16), ("sm", 20, 32),
+                          ("sm", 20, 48), ("stores", 0, 0), ("k1", 0, 0)]
         stream = stream or torch.cuda.current_stream()
         timings, steps_run = [], 0
         for strategy, chunks, sms in candidates:
