@@ -11,8 +11,9 @@ output panel so that every GPU ends up with all of Y.  Three exchange modes:
          the shard is cut into a few row chunks and the copy engines push chunk c
          to the peers while chunk c + 1's kernel runs; SDB_ALLGATHER=stores makes
          the kernel's epilogue store into the peer panels itself.
-  nccl   kernel into the local block, then ncclAllGather (all_gather_into_tensor)
-         — the baseline the fused kernel is compared with.
+  nccl   kernel into the local block, then ncclAllGather (all_gather_into_tensor; per-owner
+         broadcasts when the blocks differ in row count) — the baseline the fused kernel is
+         compared with.
   none   no exchange (independent shards).
 
 torch is used here for the process group only (rendezvous, token exchange, the
@@ -147,8 +148,6 @@ class RowShardedSpMM:
                 self.peer_ptrs.append(p.value)
         self._torch_panel = None
         if self.mode == "nccl":
-            if not self.layout.uniform:
-                raise ValueError("allgather='nccl' needs equal row counts per rank (ncclAllGather)")
             import torch
 
             self._torch_panel = torch.as_tensor(
@@ -198,8 +197,17 @@ class RowShardedSpMM:
 
             if stream is None:  # NCCL orders after torch's current stream, not the library's
                 check(SDB.lib.sdb_device_synchronize(), "sdb_device_synchronize")
-            local = self._torch_panel[self.row0:self.row0 + self.rows_local]
-            dist.all_gather_into_tensor(self._torch_panel, local, group=self.group)
+            if self.layout.uniform:
+                local = self._torch_panel[self.row0:self.row0 + self.rows_local]
+                dist.all_gather_into_tensor(self._torch_panel, local, group=self.group)
+            else:
+                # nnz-balanced blocks differ in row count: ncclAllGather wants equal pieces, so every block is
+                # broadcast by its owner instead (same bytes on the wire, one collective per rank)
+                for q in range(self.world):
+                    first, count = self.layout.block(q)
+                    if count:
+                        src = dist.get_global_rank(self.group, q) if self.group is not None else q
+                        dist.broadcast(self._torch_panel[first:first + count], src=src, group=self.group)
 
     # ------------------------------------------------------------------ exchange strategy
     STRATEGIES = {"auto": 0, "ce": 1, "stores": 2, "k1": 3, "sm": 4}

@@ -191,13 +191,20 @@ def _worker_nccl(rank, world, port, q):
             rowsum_err = float(np.abs(y[:, 0].cpu().numpy() - want_rows).max() / want_rows.max())
         ok_struct = bool(np.array_equal(c.indptr, w.indptr) and np.array_equal(c.indices, w.indices))
         err = cs.rel_err(c.data, w.data)
+        # the NCCL baseline mode with nnz-balanced (unequal) row blocks: per-owner broadcasts
+        top = cs.uniform_rows_csr(600, 900, 40, np.float32, seed=1)
+        bottom = cs.uniform_rows_csr(2400, 900, 5, np.float32, seed=2)
+        ab = sp.vstack([top, bottom]).tocsr()
+        xb = np.random.default_rng(3).random((900, 64), dtype=np.float32)
+        got = sharded.spmm_sharded(ab, xb, world, rank, allgather="nccl")
+        nccl_err = cs.rel_err(got, orc.c_spmm(ab, xb))
         m = cs.uniform_rows_csr(3000, 700, 20, np.float64, seed=3)
         wg = orc.c_syrkd(m)
         g = sharded.gram_dense_sharded(m, world, rank)
         gerr = float(np.abs(g - wg).max())
         row0, mine = sharded.gram_dense_sharded(m, world, rank, gather=False)
         perr = float(np.abs(mine - wg[row0:row0 + mine.shape[0]]).max())
-        q.put((rank, ok_struct, max(err, rowsum_err), max(gerr, perr)))
+        q.put((rank, ok_struct, max(err, rowsum_err, nccl_err), max(gerr, perr)))
     except Exception as e:
         q.put((rank, repr(e), None, None))
     finally:
