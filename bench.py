@@ -79,9 +79,11 @@ def unique_bytes(rows, cols, nnz, n_dense, beta_nonzero=True, si=4, sv=4):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the query runs every 20 ms from before
+    the warm-up steps (nvidia-smi needs ~0.1 s to deliver its first line) and carries nvidia-smi's own timestamp;
+    stop(t0, t1) keeps the samples taken between the two wall-clock marks of the timed region."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -93,7 +95,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
@@ -104,27 +106,35 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0 / t1: time.time() just before / after the timed region."""
+        import datetime
+
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for ln in self.lines:
             f = [t.strip() for t in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                stamp = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((stamp, float(f[1]), float(f[2]), [n for n, flag in zip(names, f[4:8])
+                                                               if flag.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, flag in zip(names, f[3:7]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if t0 is not None and t0 - 0.005 <= r[0] <= t1 + 0.005]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: the loaded stretch around it (warm-up + timed steps)
+            inside = [r for r in rows if t0 is not None and t0 - 0.25 <= r[0] <= t1 + 0.05] or rows
+            window = "warm-up + timed region (no sample fell inside the timed region itself)"
+        sm = [r[1] for r in inside]
+        reasons = sorted({n for r in inside for n in r[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+                "samples": len(sm), "window": window, "period_ms": 20, "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------- ncu traffic, tied to the SASS
@@ -457,19 +467,22 @@ def run_ours(args):
     if world > 1 and mode == "fused" and not args.no_autotune:
         tuned = plan.autotune(beta=BETA, stream=stream)
         steps_done += tuned["steps_run"]
-    for _ in range(args.warmup):
-        step()
-    steps_done += args.warmup
-    sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)  # nvidia-smi's first sample
+    for _ in range(max(args.warmup, 3)):
+        step()
+    steps_done += max(args.warmup, 3)
+    sync_all()
     launches0 = sdb.kernel_launches()
+    wall0 = time.time()
     total_ms, kernel_ms = timed_steps(torch, stream, step, args.steps, sync_all)
+    wall1 = time.time()
     steps_done += args.steps
     launches = sdb.kernel_launches() - launches0
     kernel_name = sdb.last_spmm_kernel()  # what the timed steps launched (same thread)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms_per_step = max_over_ranks(torch, dist, world, total_ms) / args.steps
 
     # parity of what was just timed: local rows and (N > 1) rows of every peer's block in this rank's panel
