@@ -160,8 +160,8 @@ def sass_sha(kernel_substr):
             if m:
                 keep = kernel_substr in m.group(1)
                 found = found or keep
-                if keep:
-                    h.update(m.group(1).encode())
+                if keep:  # the anonymous-namespace tag in a mangled name is derived from the file, not from the kernel
+                    h.update(re.sub(r"_GLOBAL__N__[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]+", "_ANON_", m.group(1)).encode())
                 continue
             if keep:
                 m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", line)

@@ -57,7 +57,11 @@ for step in "$@"; do
       IFS=, read -r regex nm skip count cmd <<< "$arg"
       timeout 1200 ncu --set full $NCU_COMMON --import-source on -k "regex:$regex" -s ${skip:-2} -c ${count:-1} -f \
         -o $OUT/${TAG}_$nm python ${cmd:-$BENCH_SHORT} > $OUT/${TAG}_ncu_$nm.log 2>&1
-      tail -2 $OUT/${TAG}_ncu_$nm.log ;;
+      tail -2 $OUT/${TAG}_ncu_$nm.log
+      # gpurun brings back at most 64 MiB: summarise on the box and keep the report itself only when it is small
+      python scripts/ncu_summary.py $OUT/${TAG}_$nm.ncu-rep > $OUT/${TAG}_${nm}_summary.txt 2>&1
+      python scripts/ncu_traffic.py --dump $OUT/${TAG}_$nm.ncu-rep > $OUT/${TAG}_${nm}_launches.json 2>/dev/null
+      if [ "$(stat -c %s $OUT/${TAG}_$nm.ncu-rep 2>/dev/null || echo 0)" -gt 8000000 ]; then rm -f $OUT/${TAG}_$nm.ncu-rep; fi ;;
     configs)
       timeout 1500 python scripts/run_configs.py $arg > $OUT/${TAG}_configs.log 2>&1; cat $OUT/${TAG}_configs.log | cut -c1-1200 ;;
     hashes)

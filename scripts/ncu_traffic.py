@@ -3,7 +3,8 @@
 ncu_traffic.py — keeps profiles/kernel_traffic.json, the table bench.py reads `roofline.traffic` from.
 
     python scripts/ncu_traffic.py --hashes                       (on the GPU box: SASS sha1 per profiled kernel family)
-    python scripts/ncu_traffic.py --update <tag> <rep> [<rep>..] (here: fold .ncu-rep captures + that run's hashes in)
+    python scripts/ncu_traffic.py --dump <rep>                   (on the GPU box: per-launch numbers as JSON)
+    python scripts/ncu_traffic.py --update <tag> <rep|json> ..   (here: fold captures / dumps + that run's hashes in)
 
 An entry is only quoted by bench.py while the SASS of the kernel is the one that was profiled: the hash written
 by `--hashes` in the same gpurun call travels back in gpurun_out/<tag>_sass_hashes.json and is stored with the bytes.
@@ -57,6 +58,8 @@ def hashes():
 
 
 def read_rep(path):
+    if path.endswith(".json"):  # a dump made on the GPU box (--dump): the reports themselves are too big to bring back
+        return json.load(open(path))
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -130,10 +133,13 @@ def update(tag, reps, family_key=None):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--hashes", action="store_true")
+    ap.add_argument("--dump", metavar="REP", help="per-launch numbers of an .ncu-rep as JSON on stdout")
     ap.add_argument("--update", nargs="+", metavar=("TAG", "REP"))
     ap.add_argument("--family", default=None, help="store the capture as ONE entry under this key (sum of its launches)")
     a = ap.parse_args()
-    if a.hashes:
+    if a.dump:
+        print(json.dumps(read_rep(a.dump)))
+    elif a.hashes:
         hashes()
     elif a.update:
         update(a.update[0], a.update[1:], a.family)

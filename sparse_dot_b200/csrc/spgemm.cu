@@ -611,9 +611,10 @@ __global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
                         const T* __restrict__ l_val, const int32_t* __restrict__ l_pos,
                         const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
                         const T* __restrict__ r_val, bool upper, uint2* __restrict__ pairs_all,
-                        int32_t* __restrict__ c_len, const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx,
-                        T* __restrict__ c_val) {
+                        unsigned* __restrict__ next_row, int32_t* __restrict__ c_len,
+                        const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned claimed;
     unsigned* summary = reinterpret_cast<unsigned*>(smem_raw);  // [n_groups]
     int* grp_ent = reinterpret_cast<int*>(summary + n_groups);  // [n_groups] entries before group g
     __shared__ int warp_ent[32];
@@ -632,7 +633,13 @@ __global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
         volatile unsigned* sp = summary + (w >> 5);
         if (!(*sp & sb)) atomicOr(summary + (w >> 5), sb);
     };
-    for (unsigned li = blockIdx.x; li < n_list; li += gridDim.x) {
+    // rows are claimed one at a time from a global counter: their sizes span two orders of magnitude, a static
+    // round-robin would leave most CTAs idle behind the one that drew the million-product rows
+    while (true) {
+        if (tid == 0) claimed = atomicAdd(next_row, 1u);
+        __syncthreads();
+        const unsigned li = claimed;
+        if (li >= n_list) break;
         const int64_t i = list[li];
         // ---- 1. membership
         if constexpr (BATCHED) {
@@ -836,7 +843,9 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
         const int64_t n_groups = words / 32;
         const size_t smem2 = size_t(n_groups) * 8;
         const bool summary = forced != 1 && smem2 <= size_t(96) * 1024;
-        DevBuf bm, ranks;
+        DevBuf bm, ranks, work;
+        SDB_TRY(work.alloc(2 * sizeof(unsigned), s));
+        SDB_CUDA(cudaMemsetAsync(work.p, 0, 2 * sizeof(unsigned), s));
         SDB_TRY(bm.alloc(size_t(max_ctas * words) * (summary ? 8 : 4), s));
         SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(max_ctas * words) * (summary ? 8 : 4), s));
         if (NUMERIC && !summary) SDB_TRY(ranks.alloc(size_t(max_ctas * words) * 4, s));
@@ -851,7 +860,8 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
         SDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
                                       int(std::max<size_t>(smem2, 48 * 1024))));                                      \
         SDB_LAUNCH(kernel, unsigned(ctas), 1024, smem2, s, lists.list[b], h[b], words, int(n_groups), lp, li, lv, lq, \
-                   rp, ri, rv, upper, static_cast<uint2*>(bm.p), c_len, c_ptr, c_idx, c_val);                         \
+                   rp, ri, rv, upper, static_cast<uint2*>(bm.p), work.as<unsigned>() + (b - 3), c_len, c_ptr, c_idx,  \
+                   c_val);                                                                                            \
     } while (0)
             if (summary && batched) {
                 SDB_WIDE2(true);

@@ -239,9 +239,12 @@ sdb_status spmm_bsr_device(cudaStream_t s, const sdb_mat* a, const double* alpha
     // Automatic rule, from profiles/r2_bsr_mma_table.json: with 16 x 16 blocks the FMA kernel is already at the HBM
     // roof (fp64 0.93 of peak either way; fp32 0.94 ms against 1.09 ms with 3xTF32, whose operand splits cost more
     // than the MMAs save) and 8 x 8 blocks half-fill an m16 tile; with 32 x 32 blocks the FMA loop is compute-bound
-    // and the tensor cores win (fp64 5.8 vs 7.7 ms, fp32 3.3 vs 3.6 ms at N = 512).
+    // and the tensor cores win (fp64 5.8 vs 7.7 ms, fp32 3.3 vs 3.6 ms at N = 512).  Only fp64 takes them by
+    // default: DMMA is exact, while the fp32 accumulation inside an HMMA truncates, so the 3xTF32 error grows with
+    // the number of terms of a row (6e-6 at 512 terms, 1.1e-5 at 928: over the 1e-5 bar on long block rows) —
+    // fp32 stays opt-in ("bsr_mma" = 1) for callers who know their rows are short.
     const int mma = get_option(kOptBsrMma);
-    if ((mma == 1 || (mma < 0 && a->block >= kBsrMmaFromBlock)) && spmm_bsr_mma_supported(a, n))
+    if ((mma == 1 || (mma < 0 && a->block >= kBsrMmaFromBlock && a->dtype == SDB_F64)) && spmm_bsr_mma_supported(a, n))
         return spmm_bsr_mma_device(s, a, alpha, beta, dX, n, ldx, dY, ldy, ring_depth(a));
 #define SDB_BSR_CASE(T, B)                                                                                    \
     return pick_cw<T, B>(s, a, static_cast<const T*>(dX), ldx, n, Num<T>::make(alpha[0], alpha[1]),           \
