@@ -58,6 +58,26 @@ def run_c1():
             "kernel_ms": sdb.last_timing_ms()[1]}
 
 
+def chunked_rowsums(vals, indptr, w=None, idx=None, chunk=200_000_000):
+    """float64 row sums of a CSR value array (optionally weighted by w[column]) without a full float64 copy."""
+    rows = indptr.shape[0] - 1
+    out = np.zeros(rows)
+    r0 = 0
+    while r0 < rows:
+        r1 = int(np.searchsorted(indptr, indptr[r0] + chunk, side="right")) - 1
+        r1 = min(rows, max(r1, r0 + 1))
+        p0, p1 = int(indptr[r0]), int(indptr[r1])
+        if p1 > p0:
+            v = vals[p0:p1].astype(np.float64)
+            if w is not None:
+                v *= w[idx[p0:p1]]
+            local = indptr[r0:r1] - p0
+            nonempty = np.flatnonzero(np.diff(indptr[r0:r1 + 1]) > 0)
+            out[r0 + nonempty] = np.add.reduceat(v, local[nonempty])
+        r0 = r1
+    return out
+
+
 def run_c3_resident(scale, ef):
     """configs[2] at an edge factor whose result does not fit a host export comfortably: the product stays
     in HBM; only the values come back (one array) for the checksum-of-checksums."""
@@ -109,6 +129,23 @@ def run_c3_resident(scale, ef):
             want_total = float(np.dot(colsum_a, rowsum_b))
             got_total = float(vals.sum(dtype=np.float64))
             res["total_rel_err"] = abs(got_total - want_total) / want_total
+            # the checksum above does not see WHERE a product landed: per-row sums (C 1 = A (B 1)) catch a product in the
+            # wrong row, and — when the result is small enough to bring its indices back — a random weighting of the
+            # columns (C w = A (B w)) catches one in the wrong column of the right row
+            indptr = np.empty(a.shape[0] + 1, dtype=np.int64)
+            _lib.check(lib.sdb_export(hc.ref, indptr.ctypes.data_as(C.c_void_p), 64, None, 32, None), "sdb_export")
+            rows_got = chunked_rowsums(vals, indptr)
+            want_rows = a.astype(np.float64) @ rowsum_b
+            res["rowsum_max_rel_err"] = float(np.max(np.abs(rows_got - want_rows) / np.maximum(want_rows, 1e-300)))
+            if nnz < 1_500_000_000:
+                idx = np.empty(nnz, dtype=np.int32)
+                _lib.check(lib.sdb_export(hc.ref, None, 64, idx.ctypes.data_as(C.c_void_p), 32, None), "sdb_export")
+                w = np.random.default_rng(7).random(b.shape[1]) + 0.5
+                wrow = chunked_rowsums(vals, indptr, w, idx)
+                want_w = a.astype(np.float64) @ (b.astype(np.float64) @ w)
+                res["weighted_rowsum_max_rel_err"] = float(np.max(np.abs(wrow - want_w) / np.maximum(want_w, 1e-300)))
+                dec = np.flatnonzero(np.diff(idx.astype(np.int64)) <= 0) + 1
+                res["rows_strictly_sorted_after_order"] = bool(np.all(np.isin(dec, indptr)))
     return res
 
 

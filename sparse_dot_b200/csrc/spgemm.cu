@@ -587,56 +587,66 @@ __global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
 
 
 // Wide rows, second formulation (the default while its index fits shared memory): the same bitmap, but every
-// pass after the first touches only the bitmap words the row has set, and a product finds its rank with ONE load.
-// The first version sweeps the whole column range (cols / 8 bytes of bitmap plus as much again of per-word ranks)
-// three times per row whatever the row holds; at 4M columns and two CTAs per SM those slices no longer fit L2 and
-// ncu shows the bin moving 100 GB of DRAM traffic at 4.6 TB/s (profiles/r2d_spgemm_ef1_summary.txt).  Here
-//   * the bitmap is an array of (word, rank) PAIRS — 8 bytes per 32 columns — so the value pass reads the word and
-//     the output rank of its first bit with one 8-byte load instead of two scattered 4-byte loads;
-//   * a word-level SUMMARY of the bitmap lives in shared memory (bit b of summary[g] says word 32 g + b is
-//     non-zero) and the sweeps are driven by it: one LANE per group of 32 words walks only the words its group has
-//     set (consecutive lanes take consecutive groups, so the dense low-column groups of a power-law row fill whole
-//     warps), which makes a sweep a handful of latency rounds instead of 32 dependent iterations.
-// Steps: 1. walk the products: atomicOr on the pair's word (global, fire-and-forget) and, while the summary bit is
-// still clear, an atomicOr on the summary (shared); 2. populations per group -> block-wide exclusive scan
-// [symbolic stops here: c_len, then only the set words are cleared]; 3. ranks into the pairs, columns emitted in
-// ascending order; 4. walk the products again: one pair load, rank = pair.rank + popc(lower bits), atomic add at
-// c_val[row start + rank]; 5. clear the set pairs and the summary.  Traffic per row is proportional to the words
-// it sets.  BATCHED (rows above kWideMax, one CTA per SM): the walks keep kWalkBatch products per lane in flight.
-// Shared memory: 8 bytes per 1024 columns.
+// pass after the first touches only the bitmap words the row has set.  The first version sweeps the whole column
+// range (cols / 8 bytes of bitmap plus as much again of per-word ranks) three times per row whatever the row
+// holds; at 4M columns and two CTAs per SM those slices no longer fit L2 and ncu shows the bin moving 100 GB of
+// DRAM traffic at 4.6 TB/s (profiles/r2d_spgemm_ef1_summary.txt).  Here a word-level SUMMARY of the bitmap lives
+// in shared memory (bit b of summary[g] says bitmap word 32 g + b is non-zero) together with two per-group prefix
+// arrays, and the sweeps are driven by it: one LANE per group of 32 words walks only the words its group has set
+// (consecutive lanes take consecutive groups, so the dense low-column groups of a power-law row fill whole warps),
+// which makes a sweep a handful of latency rounds instead of 32 dependent iterations.
+//   1. walk the products: atomicOr on the bitmap word (global, fire-and-forget) and, only while the summary bit
+//      is still clear, an atomicOr on the summary (shared);
+//   2. populations per group -> block-wide exclusive scans -> entry / set-word offsets per group;
+//      [symbolic stops here: c_len, then only the set words are cleared]
+//   3. the k-th set word's output rank goes into a COMPACT array (k = group offset + popc of the lower summary
+//      bits), columns are written in ascending order;
+//   4. walk the products again: rank = compact_rank[k] + popc(lower bits of the word), atomic add at
+//      c_val[row start + rank];
+//   5. the set words and the summary are cleared.
+// Traffic per row is proportional to the words it sets; rows come out sorted.  Rows are claimed one at a time from a
+// global counter.  BATCHED (rows above kWideMax, one CTA per SM): the walks keep kWalkBatch products per lane in
+// flight.  Shared memory: 12 bytes per 1024 columns (up to ~8M columns beside two CTAs per SM; beyond, the first
+// version runs).  (A variant with (word, rank) pairs in one 8-byte array — one load per product instead of two —
+// measured 6x SLOWER in the value pass, 92.9 vs 15.1 ms at scale 22 ef 1, and was dropped:
+// profiles/r2_logs/spgemm_trace_ef1_pairs.log.)
 template <typename T, bool NUMERIC, bool BATCHED>
 __global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
     spgemm_wide2_kernel(const int32_t* __restrict__ list, unsigned n_list, int64_t words_padded, int n_groups,
                         const int64_t* __restrict__ l_ptr, const int32_t* __restrict__ l_idx,
                         const T* __restrict__ l_val, const int32_t* __restrict__ l_pos,
                         const int64_t* __restrict__ r_ptr, const int32_t* __restrict__ r_idx,
-                        const T* __restrict__ r_val, bool upper, uint2* __restrict__ pairs_all,
-                        unsigned* __restrict__ next_row, int32_t* __restrict__ c_len,
-                        const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx, T* __restrict__ c_val) {
+                        const T* __restrict__ r_val, bool upper, unsigned* __restrict__ bitmaps,
+                        int32_t* __restrict__ word_ranks, unsigned* __restrict__ next_row,
+                        int32_t* __restrict__ c_len, const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx,
+                        T* __restrict__ c_val) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned claimed;
     unsigned* summary = reinterpret_cast<unsigned*>(smem_raw);  // [n_groups]
     int* grp_ent = reinterpret_cast<int*>(summary + n_groups);  // [n_groups] entries before group g
-    __shared__ int warp_ent[32];
+    int* grp_wrd = grp_ent + n_groups;                          // [n_groups] set words before group g
+    __shared__ int warp_ent[32], warp_wrd[32];
     __shared__ LStage<T, 256> stage;
-    uint2* pairs = pairs_all + int64_t(blockIdx.x) * words_padded;  // .x = bitmap word, .y = rank of its first bit
-    unsigned* pair_words = reinterpret_cast<unsigned*>(pairs);       // word of pair w at index 2 w
+    unsigned* bm = bitmaps + int64_t(blockIdx.x) * words_padded;
+    int32_t* wr = NUMERIC ? word_ranks + int64_t(blockIdx.x) * words_padded : nullptr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     for (int g = tid; g < n_groups; g += blockDim.x) summary[g] = 0u;
     __syncthreads();
-    // groups handled by one thread in the block-wide scan (contiguous, so the scan is over ascending columns)
+    // groups handled by one thread in the block-wide scans (contiguous, so the scan is over ascending columns)
     const int per_thread = (n_groups + int(blockDim.x) - 1) / int(blockDim.x);
     auto mark = [&](int32_t col) {
         const int w = col >> 5;
-        atomicOr(pair_words + 2 * int64_t(w), 1u << (col & 31));
+        atomicOr(&bm[w], 1u << (col & 31));
         const unsigned sb = 1u << (w & 31);
         volatile unsigned* sp = summary + (w >> 5);
         if (!(*sp & sb)) atomicOr(summary + (w >> 5), sb);
     };
-    // rows are claimed one at a time from a global counter: their sizes span two orders of magnitude, a static
-    // round-robin would leave most CTAs idle behind the one that drew the million-product rows
+    // rows are claimed one at a time from a global counter (their sizes span two orders of magnitude); without a
+    // counter (next_row == nullptr) the static round-robin of the first version is used
+    unsigned static_li = blockIdx.x;
     while (true) {
-        if (tid == 0) claimed = atomicAdd(next_row, 1u);
+        if (tid == 0) claimed = next_row ? atomicAdd(next_row, 1u) : static_li;
+        static_li += gridDim.x;
         __syncthreads();
         const unsigned li = claimed;
         if (li >= n_list) break;
@@ -660,15 +670,16 @@ __global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
         // ---- 2. populations per group, four word loads in flight per lane
         for (int g = tid; g < n_groups; g += blockDim.x) {
             unsigned sm = summary[g];
-            const unsigned* gw = pair_words + int64_t(g) * 64;
+            const unsigned* gw = bm + int64_t(g) * 32;
             int ce = 0;
+            grp_wrd[g] = __popc(sm);
             while (sm) {
                 unsigned w4[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     w4[u] = 0u;
                     if (sm) {
-                        w4[u] = __ldcg(gw + 2 * (__ffs(sm) - 1));
+                        w4[u] = __ldcg(gw + (__ffs(sm) - 1));
                         sm &= sm - 1;
                     }
                 }
@@ -677,46 +688,60 @@ __global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
             grp_ent[g] = ce;
         }
         __syncthreads();
-        // block-wide exclusive scan: thread-local run, warp scan, scan of the warp totals
-        int e_sum = 0;
+        // block-wide exclusive scans of both arrays: thread-local run, warp scan, scan of the warp totals
+        int e_sum = 0, w_sum = 0;
         const int g0 = tid * per_thread, g1 = min(n_groups, g0 + per_thread);
-        for (int g = g0; g < g1; ++g) e_sum += grp_ent[g];
-        int e_inc = e_sum;
+        for (int g = g0; g < g1; ++g) {
+            e_sum += grp_ent[g];
+            w_sum += grp_wrd[g];
+        }
+        int e_inc = e_sum, w_inc = w_sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const int eo = __shfl_up_sync(0xffffffffu, e_inc, d);
-            if (lane >= d) e_inc += eo;
+            const int eo = __shfl_up_sync(0xffffffffu, e_inc, d), wo = __shfl_up_sync(0xffffffffu, w_inc, d);
+            if (lane >= d) {
+                e_inc += eo;
+                w_inc += wo;
+            }
         }
-        if (lane == 31) warp_ent[warp] = e_inc;
+        if (lane == 31) {
+            warp_ent[warp] = e_inc;
+            warp_wrd[warp] = w_inc;
+        }
         __syncthreads();
-        int e_before = 0, e_total = 0;
+        int e_before = 0, w_before = 0, e_total = 0;
         for (int x = 0; x < nwarps; ++x) {
-            const int te = warp_ent[x];
-            if (x < warp) e_before += te;
+            const int te = warp_ent[x], tw = warp_wrd[x];
+            if (x < warp) {
+                e_before += te;
+                w_before += tw;
+            }
             e_total += te;
         }
-        int e_run = e_before + e_inc - e_sum;
+        int e_run = e_before + e_inc - e_sum, w_run = w_before + w_inc - w_sum;
         for (int g = g0; g < g1; ++g) {
-            const int ce = grp_ent[g];
+            const int ce = grp_ent[g], cw = grp_wrd[g];
             grp_ent[g] = e_run;
+            grp_wrd[g] = w_run;
             e_run += ce;
+            w_run += cw;
         }
         __syncthreads();
         if (!NUMERIC) {
             if (tid == 0) c_len[i] = e_total;
         } else {
-            // ---- 3. ranks into the pairs and ordered emission
+            // ---- 3. ranks of the set words (compact) and ordered emission
             const int64_t out0 = c_ptr[i];
             for (int g = tid; g < n_groups; g += blockDim.x) {
                 unsigned sm = summary[g];
                 if (!sm) continue;
-                int rank = grp_ent[g];
+                int rank = grp_ent[g], k = grp_wrd[g];
                 while (sm) {
                     const int b = __ffs(sm) - 1;
                     sm &= sm - 1;
                     const int64_t w = int64_t(g) * 32 + b;
-                    unsigned word = __ldcg(pair_words + 2 * w);
-                    pair_words[2 * w + 1] = unsigned(rank);
+                    unsigned word = __ldcg(bm + w);
+                    wr[k++] = rank;
                     while (word) {
                         const int bit = __ffs(word) - 1;
                         word &= word - 1;
@@ -727,10 +752,12 @@ __global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
                 }
             }
             __syncthreads();
-            // ---- 4. values: one pair load per product
+            // ---- 4. values: every product is added at its column's rank
             auto rank_of = [&](int32_t col) {
-                const uint2 e = __ldcg(pairs + (col >> 5));
-                return int(e.y) + __popc(e.x & ((1u << (col & 31)) - 1u));
+                const int w = col >> 5, g = w >> 5;
+                const int k = grp_wrd[g] + __popc(summary[g] & ((1u << (w & 31)) - 1u));
+                const unsigned below = __ldcg(bm + w) & ((1u << (col & 31)) - 1u);
+                return __ldcg(wr + k) + __popc(below);
             };
             if constexpr (BATCHED) {
                 for_each_product_cta_batched<T, true, 256, RankedProduct<T>>(
@@ -755,13 +782,13 @@ __global__ void __launch_bounds__(1024, BATCHED ? 1 : 2)
             }
             __syncthreads();
         }
-        // ---- 5. clear the set pairs' words and the summary
+        // ---- 5. clear the set words and the summary
         for (int g = tid; g < n_groups; g += blockDim.x) {
             unsigned sm = summary[g];
             if (!sm) continue;
             summary[g] = 0u;
             while (sm) {
-                pair_words[2 * (int64_t(g) * 32 + (__ffs(sm) - 1))] = 0u;
+                bm[int64_t(g) * 32 + (__ffs(sm) - 1)] = 0u;
                 sm &= sm - 1;
             }
         }
@@ -841,14 +868,18 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
         // bin 186 -> 136 ms at edge factor 4, 21.7 -> 15.1 ms at edge factor 1.
         const int forced = get_option(kOptSpgemmWide);
         const int64_t n_groups = words / 32;
-        const size_t smem2 = size_t(n_groups) * 8;
+        const size_t smem2 = size_t(n_groups) * 12;
         const bool summary = forced != 1 && smem2 <= size_t(96) * 1024;
+        static const bool dynamic = [] {
+            const char* e = getenv("SDB_SPGEMM_DYNAMIC");
+            return !(e && e[0] == '0');
+        }();
         DevBuf bm, ranks, work;
         SDB_TRY(work.alloc(2 * sizeof(unsigned), s));
         SDB_CUDA(cudaMemsetAsync(work.p, 0, 2 * sizeof(unsigned), s));
-        SDB_TRY(bm.alloc(size_t(max_ctas * words) * (summary ? 8 : 4), s));
-        SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(max_ctas * words) * (summary ? 8 : 4), s));
-        if (NUMERIC && !summary) SDB_TRY(ranks.alloc(size_t(max_ctas * words) * 4, s));
+        SDB_TRY(bm.alloc(size_t(max_ctas * words) * 4, s));
+        SDB_CUDA(cudaMemsetAsync(bm.p, 0, size_t(max_ctas * words) * 4, s));
+        if (NUMERIC) SDB_TRY(ranks.alloc(size_t(max_ctas * words) * 4, s));
         for (int b = 3; b <= 4; ++b) {
             if (h[b] == 0) continue;
             const bool batched = b == 4 && forced != 1;
@@ -860,7 +891,8 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
         SDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,                            \
                                       int(std::max<size_t>(smem2, 48 * 1024))));                                      \
         SDB_LAUNCH(kernel, unsigned(ctas), 1024, smem2, s, lists.list[b], h[b], words, int(n_groups), lp, li, lv, lq, \
-                   rp, ri, rv, upper, static_cast<uint2*>(bm.p), work.as<unsigned>() + (b - 3), c_len, c_ptr, c_idx,  \
+                   rp, ri, rv, upper, bm.as<unsigned>(), ranks.as<int32_t>(),                                         \
+                   dynamic ? work.as<unsigned>() + (b - 3) : nullptr, c_len, c_ptr, c_idx,                            \
                    c_val);                                                                                            \
     } while (0)
             if (summary && batched) {
