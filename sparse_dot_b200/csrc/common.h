@@ -66,6 +66,7 @@ enum Option {
     kOptDenseMode,      // "dense_mode"    SDB_DENSE_MODE     dense-output products: 0 auto, 1 shared tiles, 2 global reductions
     kOptDenseThreads,   // "dense_threads" SDB_DENSE_THREADS  threads per CTA of the global-reduction kernel (0 = 1024)
     kOptDenseCtas,      // "dense_ctas"    SDB_DENSE_CTAS     resident CTAs per SM of that kernel (0 = what fits)
+    kOptSpgemmSortedCta,  // "spgemm_sorted_cta" SDB_SPGEMM_SORTED_CTA  sorted SpGEMM: 1 keeps 1025..4096-entry rows in the CTA hash bin
     kOptCount
 };
 int get_option(Option o);

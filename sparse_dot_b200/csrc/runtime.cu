@@ -79,6 +79,7 @@ OptionSlot g_options[kOptCount] = {
     {"dense_mode", "SDB_DENSE_MODE", 0, {0}, {false}},
     {"dense_threads", "SDB_DENSE_THREADS", 0, {0}, {false}},
     {"dense_ctas", "SDB_DENSE_CTAS", 0, {0}, {false}},
+    {"spgemm_sorted_cta", "SDB_SPGEMM_SORTED_CTA", 0, {0}, {false}},
 };
 }  // namespace
 

@@ -86,7 +86,7 @@ struct BinLists {
 };
 __global__ void __launch_bounds__(256) bin_rows_kernel(int64_t rows, const int32_t* __restrict__ size,
                                                        int32_t* __restrict__ zero_len, BinLists lists,
-                                                       unsigned* __restrict__ counters) {
+                                                       unsigned* __restrict__ counters, int cta_max) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int bin = -1;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) bin_rows_kernel(int64_t rows, const int32
         if (v == 0) {
             if (zero_len) zero_len[i] = 0;
         } else {
-            bin = v <= kWarpMax ? 0 : (v <= kSmallMax ? 1 : (v <= kCtaMax ? 2 : (v <= kWideMax ? 3 : 4)));
+            bin = v <= kWarpMax ? 0 : (v <= kSmallMax ? 1 : (v <= cta_max ? 2 : (v <= kWideMax ? 3 : 4)));
         }
     }
 #pragma unroll
@@ -823,8 +823,13 @@ static sdb_status run_pass(Context* ctx, const CsrView& l, const CsrView& r, boo
     }
     SDB_TRY(counters.alloc(kBins * sizeof(unsigned), s));
     SDB_CUDA(cudaMemsetAsync(counters.p, 0, kBins * sizeof(unsigned), s));
+    // Sorted results: a CTA-bin row pays an in-shared-memory bitonic sort of its hash table (17.7 ms for the bin at
+    // R-MAT scale 22 ef 1 against 4.6 ms unsorted), while the bitmap bins emit in column order for free — so when
+    // the result must be sorted the rows above the small bin go to the bitmap formulation ("spgemm_sorted_cta" = 1
+    // keeps them in the CTA bin).
+    const int cta_max = NUMERIC && sort && get_option(kOptSpgemmSortedCta) != 1 ? kSmallMax : kCtaMax;
     SDB_LAUNCH(bin_rows_kernel, unsigned((rows + 255) / 256), 256, 0, s, rows, sizes, NUMERIC ? nullptr : c_len, lists,
-               counters.as<unsigned>());
+               counters.as<unsigned>(), cta_max);
     unsigned h[kBins];
     SDB_CUDA(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     SDB_CUDA(cudaStreamSynchronize(s));
