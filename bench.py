@@ -139,9 +139,10 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- ncu traffic, tied to the SASS
 def sass_sha(kernel_substr):
-    """sha1 of the SASS of every function of libsdb200's objects whose name contains `kernel_substr`
-    (addresses and comments stripped), or None when cuobjdump / the objects are not there.  The ncu DRAM
-    bytes in profiles/kernel_traffic.json are only quoted for the SASS they were captured from."""
+    """sha1 of the instruction text of every function of libsdb200's objects whose mangled name contains
+    `kernel_substr` (addresses, comments and the names themselves left out), or None when cuobjdump / the
+    objects are not there.  The ncu DRAM bytes in profiles/kernel_traffic.json are only quoted for the SASS they
+    were captured from."""
     obj_dir = os.path.join(ROOT, "sparse_dot_b200", "csrc", "_obj")
     try:
         objs = sorted(f for f in os.listdir(obj_dir) if f.endswith(".o"))
@@ -160,9 +161,7 @@ def sass_sha(kernel_substr):
             if m:
                 keep = kernel_substr in m.group(1)
                 found = found or keep
-                if keep:  # the anonymous-namespace tag in a mangled name is derived from the file, not from the kernel
-                    h.update(re.sub(r"_GLOBAL__N__[0-9a-f]+_\d+_\w+?_cu_[0-9a-f]+", "_ANON_", m.group(1)).encode())
-                continue
+                continue  # names are not hashed: only the instruction text of the matching functions, in file order
             if keep:
                 m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
                 if m:

@@ -317,6 +317,7 @@ SDB_API int        sdb_last_error(char* buf, int len);
  *   "dense_mode"    SDB_DENSE_MODE     dense-output products: 0 automatic, 1 shared-memory tiles, 2 global reductions
  *   "dense_threads" SDB_DENSE_THREADS  threads per CTA of the global-reduction kernel (0 = default)
  *   "dense_ctas"    SDB_DENSE_CTAS     resident CTAs per SM of that kernel (0 = as many as fit)
+ *   "slab_keep"     SDB_SLAB_KEEP      streaming SpMM: gathers of X rows carry an L2 evict_last policy (0 / 1)
  *   "spgemm_sorted_cta" SDB_SPGEMM_SORTED_CTA  sorted SpGEMM: 1 keeps rows of 1025..4096 entries in the CTA hash bin (0: bitmap bin)
  * Unknown names return SDB_STATUS_INVALID_VALUE.  No reference counterpart (tuning aid for tests and sweeps). */
 SDB_API sdb_status sdb_set_option(const char* name, int value);

@@ -33,6 +33,12 @@ FAMILIES = {
     "spgemm_dense_red_kernel": "spgemm_dense_red_kernel",
     "spgemm_": "spgemm_",
 }
+# per-instantiation matches for the kernels bench.py quotes (mangled-name fragments)
+MATCH = {
+    "spmm_stream_kernel<float,6,32,2,2>": "spmm_stream_kernelIfLi6ELi32ELi2ELi2ELb0",
+    "spmm_bsr_kernel<float,16,256,0,2>": "spmm_bsr_kernelIfLi16ELi256ELb0ELi2E",
+    "spgemm_dense_red_kernel<float>": "spgemm_dense_red_kernelIf",
+}
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 TSCALE = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "second": 1.0, "msecond": 1e-3, "usecond": 1e-6,
           "nsecond": 1e-9}
@@ -94,8 +100,17 @@ def update(tag, reps, family_key=None):
     table["note"] = ("DRAM bytes per launch from ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum), "
                      "each stored with the sha1 of the SASS it was captured from (scripts/ncu_traffic.py); bench.py quotes "
                      "an entry only while the SASS of the build matches")
+    import bench
+
+    # The hash is taken from the objects HERE: run --update right after the gpurun call, before touching a kernel
+    # (the box builds nothing: it runs the objects this tree shipped).  The family hashes written on the box by
+    # --hashes (gpurun_out/<tag>_sass_hashes.json) are kept beside them as a cross-check.
     hpath = os.path.join(ROOT, "gpurun_out", f"{tag}_sass_hashes.json")
-    sass = json.load(open(hpath)) if os.path.exists(hpath) else {}
+    box = json.load(open(hpath)) if os.path.exists(hpath) else {}
+    here = {fam: bench.sass_sha(sub) for fam, sub in FAMILIES.items()}
+    for fam, sha in box.items():
+        if sha and here.get(fam) and sha != here[fam]:
+            raise SystemExit(f"{fam}: the objects here differ from the ones the box profiled ({here[fam]} vs {sha})")
     for rep in reps:
         launches = read_rep(rep)
         if family_key:
@@ -112,7 +127,7 @@ def update(tag, reps, family_key=None):
                 "dram_bytes_write_per_launch": tot["dram_bytes_write_per_launch"],
                 "dram_bytes_per_launch": tot["dram_bytes_read_per_launch"] + tot["dram_bytes_write_per_launch"],
                 "duration_ms_under_ncu": tot["seconds"] * 1e3,
-                "sass_match": FAMILIES.get(fam, fam), "sass_sha1": sass.get(fam),
+                "sass_match": FAMILIES.get(fam, fam), "sass_sha1": bench.sass_sha(FAMILIES.get(fam, fam)),
             }
             continue
         for k in launches:
@@ -124,7 +139,8 @@ def update(tag, reps, family_key=None):
                 "l2_to_sm_bytes_per_launch": k["l2_to_sm"],
                 "duration_ms_under_ncu": (k["seconds"] or 0.0) * 1e3, "l2_hit_rate_pct": k["l2_hit_pct"],
                 "warps_active_pct": k["warps_active_pct"],
-                "sass_match": FAMILIES.get(fam, k["name"].split("<")[0]), "sass_sha1": sass.get(fam),
+                "sass_match": MATCH.get(k["name"], FAMILIES.get(fam, k["name"].split("<")[0])),
+                "sass_sha1": bench.sass_sha(MATCH.get(k["name"], FAMILIES.get(fam, k["name"].split("<")[0]))),
             }
     json.dump(table, open(TABLE, "w"), indent=1)
     print(json.dumps({k: (v["dram_bytes_per_launch"], v.get("sass_sha1")) for k, v in table["kernels"].items()}, indent=1))

@@ -67,6 +67,7 @@ enum Option {
     kOptDenseThreads,   // "dense_threads" SDB_DENSE_THREADS  threads per CTA of the global-reduction kernel (0 = 1024)
     kOptDenseCtas,      // "dense_ctas"    SDB_DENSE_CTAS     resident CTAs per SM of that kernel (0 = what fits)
     kOptSpgemmSortedCta,  // "spgemm_sorted_cta" SDB_SPGEMM_SORTED_CTA  sorted SpGEMM: 1 keeps 1025..4096-entry rows in the CTA hash bin
+    kOptSlabKeep,       // "slab_keep"     SDB_SLAB_KEEP      streaming SpMM gathers with an L2 evict_last policy (0 / 1)
     kOptCount
 };
 int get_option(Option o);

@@ -80,6 +80,7 @@ OptionSlot g_options[kOptCount] = {
     {"dense_threads", "SDB_DENSE_THREADS", 0, {0}, {false}},
     {"dense_ctas", "SDB_DENSE_CTAS", 0, {0}, {false}},
     {"spgemm_sorted_cta", "SDB_SPGEMM_SORTED_CTA", 0, {0}, {false}},
+    {"slab_keep", "SDB_SLAB_KEEP", 0, {0}, {false}},
 };
 }  // namespace
 

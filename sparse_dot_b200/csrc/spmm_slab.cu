@@ -108,6 +108,18 @@ template <typename T> __device__ __forceinline__ Pack16<T> gather16(const char* 
     *reinterpret_cast<float4*>(&r) = q;
     return r;
 }
+// The same gather with an L2 evict_last policy: X rows of the active slabs are kept in L2 in preference to lines
+// without a policy — the output panel rows peers write into this GPU during a fused all-gather (SDB_SLAB_KEEP=1).
+template <typename T>
+__device__ __forceinline__ Pack16<T> gather16_keep(const char* xlane, uint32_t col, uint32_t row_bytes, uint64_t policy) {
+    float4 q;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                 : "l"(xlane + uint64_t(col) * row_bytes), "l"(policy));
+    Pack16<T> r;
+    *reinterpret_cast<float4*>(&r) = q;
+    return r;
+}
 
 // One staged entry: packed (local row << 27 | column) and the value; 8 bytes (fp32) or 16 bytes (fp64), so a
 // warp-uniform read of it is ONE shared-memory wavefront (broadcast) where two shuffles would be two.
@@ -123,7 +135,7 @@ template <typename T> struct alignas(sizeof(T) == 4 ? 8 : 16) StagedEntry {
 // l1tex__data_pipe_lsu_wavefronts), so the hot loop is written to spend as few wavefronts per stored entry as
 // possible: 4 for the 512-byte gather (irreducible), 1 for the staged-entry broadcast, and 8 per row change
 // (store the running sums, load the next row's) amortised over the run of entries a row has inside one slab.
-template <typename T, int RPW, int WARPS, int U, int CTAS>
+template <typename T, int RPW, int WARPS, int U, int CTAS, bool KEEP = false>
 __global__ void __launch_bounds__(WARPS * 32, CTAS)
     spmm_stream_kernel(int64_t rows, const int64_t* __restrict__ indptr, const uint32_t* __restrict__ ent_rc,
                        const T* __restrict__ ent_val, const T* __restrict__ X, uint32_t row_bytes, T alpha, T beta,
@@ -142,6 +154,12 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
     Pack16<T> zero;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) zero.v[i] = Num<T>::zero();
+    uint64_t keep_policy = 0;
+    if constexpr (KEEP) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_policy));
+    auto gather = [&](uint32_t col) {
+        if constexpr (KEEP) return gather16_keep<T>(xlane, col, row_bytes, keep_policy);
+        else return gather16<T>(xlane, col, row_bytes);
+    };
 
     for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) {
         const int64_t row_base = rb * kRows + int64_t(warp) * RPW;
@@ -203,21 +221,21 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     e[u] = stage[u];
-                    x[u] = gather16<T>(xlane, e[u].rc & kColMask, row_bytes);
+                    x[u] = gather(e[u].rc & kColMask);
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     consume(e[j % U], x[j % U]);
                     if (j + U < 32) {
                         e[j % U] = stage[j + U];
-                        x[j % U] = gather16<T>(xlane, e[j % U].rc & kColMask, row_bytes);
+                        x[j % U] = gather(e[j % U].rc & kColMask);
                     }
                 }
             } else {
                 // ragged last chunk of the group: one entry at a time
                 for (int j = 0; j < cnt; ++j) {
                     const Ent ej = stage[j];
-                    const Pack16<T> xj = gather16<T>(xlane, ej.rc & kColMask, row_bytes);
+                    const Pack16<T> xj = gather(ej.rc & kColMask);
                     consume(ej, xj);
                 }
             }
@@ -297,7 +315,7 @@ thread_local int t_reserved_sms = 0;
 
 void spmm_slab_reserve_sms(int sms) { t_reserved_sms = sms < 0 ? 0 : sms; }
 
-template <typename T, int RPW, int WARPS, int U, int CTAS>
+template <typename T, int RPW, int WARPS, int U, int CTAS, bool KEEP = false>
 static sdb_status launch_stream(cudaStream_t s, const CsrView& a, const sdb_mat* m, const T* X, int64_t ldx, T alpha,
                                 T beta, void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy,
                                 int sm_count, int col_chunks) {
@@ -311,16 +329,17 @@ static sdb_status launch_stream(cudaStream_t s, const CsrView& a, const sdb_mat*
     const int64_t n_blocks = (sub_rows + kRows - 1) / kRows;
     const int live_sms = std::max(1, sm_count - t_reserved_sms);
     const unsigned grid = unsigned(std::min<int64_t>(n_blocks, int64_t(live_sms) * CTAS));
-    SDB_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<T, RPW, WARPS, U, CTAS>,
+    SDB_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<T, RPW, WARPS, U, CTAS, KEEP>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmem)));
-    note_spmm_kernel("spmm_stream_kernel<%s,%d,%d,%d,%d>", dtype_cname(Num<T>::dtype), RPW, WARPS, U, CTAS);
+    note_spmm_kernel(KEEP ? "spmm_stream_kernel<%s,%d,%d,%d,%d,keep>" : "spmm_stream_kernel<%s,%d,%d,%d,%d>",
+                     dtype_cname(Num<T>::dtype), RPW, WARPS, U, CTAS);
     // panels wider than 512 bytes per row: one sweep per 512-byte column chunk (the accumulator tile is 512 B wide)
     constexpr int kChunkElems = 512 / int(sizeof(T));
     for (int c = 0; c < col_chunks; ++c) {
         SlabPeers<T> peers;
         for (int q = 0; q < kSlabMaxPeers; ++q)
             peers.y[q] = q < n_peers ? static_cast<T*>(dY_peers[q]) + int64_t(c) * kChunkElems : nullptr;
-        SDB_LAUNCH((spmm_stream_kernel<T, RPW, WARPS, U, CTAS>), grid, WARPS * 32, kSmem, s, sub_rows, sub_indptr,
+        SDB_LAUNCH((spmm_stream_kernel<T, RPW, WARPS, U, CTAS, KEEP>), grid, WARPS * 32, kSmem, s, sub_rows, sub_indptr,
                    static_cast<const uint32_t*>(m->slab_rc), static_cast<const T*>(m->slab_val),
                    X + int64_t(c) * kChunkElems, uint32_t(ldx * int64_t(sizeof(T))), alpha, beta, peers.y[self], peers,
                    n_peers, self, row0, ldy);
@@ -339,7 +358,12 @@ static sdb_status launch_variant(cudaStream_t s, const CsrView& a, const sdb_mat
         case 3: return launch_stream<T, 8, 24, 4, 2>(SDB_SLAB_ARGS);
         case 4: return launch_stream<T, 8, 16, 3, 3>(SDB_SLAB_ARGS);
         case 5: return launch_stream<T, 13, 32, 4, 1>(SDB_SLAB_ARGS);
-        default: return launch_stream<T, 6, 32, 2, 2>(SDB_SLAB_ARGS);
+        default: {
+            // option "slab_keep" (SDB_SLAB_KEEP=1): the gathers carry an L2 evict_last policy, so the X rows of the
+            // active slabs outlive the lines peers write into this GPU's panel during a fused all-gather
+            if (get_option(kOptSlabKeep) == 1) return launch_stream<T, 6, 32, 2, 2, true>(SDB_SLAB_ARGS);
+            return launch_stream<T, 6, 32, 2, 2>(SDB_SLAB_ARGS);
+        }
     }
 }
 #undef SDB_SLAB_ARGS

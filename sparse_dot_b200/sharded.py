@@ -213,13 +213,14 @@ class RowShardedSpMM:
     STRATEGIES = {"auto": 0, "ce": 1, "stores": 2, "k1": 3, "sm": 4}
 
     @staticmethod
-    def set_exchange(strategy="auto", chunks=0, sms=None):
+    def set_exchange(strategy="auto", chunks=0, sms=None, keep=0):
         """Process-wide exchange strategy of the fused mode (sdb_set_allgather): 'auto', 'ce' (copy engines push
         row chunks while the next chunk's kernel runs; ``chunks`` = how many), 'stores' (the kernel's epilogue
         stores into the peer panels), 'k1' (the same with the row-gather kernel)."""
         check(SDB.lib.sdb_set_allgather(RowShardedSpMM.STRATEGIES[strategy], int(chunks)), "sdb_set_allgather")
         if sms:
             check(SDB.lib.sdb_set_allgather_sms(int(sms)), "sdb_set_allgather_sms")
+        _lib.set_option("slab_keep", 1 if keep else 0)
 
     def autotune(self, beta=0.0, stream=None, candidates=None, reps=3):
         """Time the exchange strategies on the live topology (device time, max over ranks) and keep the fastest.
@@ -233,12 +234,14 @@ class RowShardedSpMM:
         if self.mode != "fused" or self.world == 1:
             return {"chosen": None, "steps_run": 0}
         if candidates is None:
-            candidates = [("ce", 5, 0), ("ce", 10, 0), ("ce", 20, 0), ("sm", 10, 8), ("sm", 20, 16), ("sm", 20, 32),
-                          ("sm", 20, 48), ("stores", 0, 0), ("k1", 0, 0)]
+            # (strategy, chunks, copier SMs, keep): keep = the streaming kernel's gathers carry an L2 evict_last policy
+            candidates = [("ce", 5, 0, 0), ("ce", 10, 0, 0), ("ce", 20, 0, 0), ("ce", 10, 0, 1), ("ce", 20, 0, 1),
+                          ("sm", 10, 8, 0), ("sm", 20, 16, 0), ("sm", 20, 16, 1), ("stores", 0, 0, 0),
+                          ("stores", 0, 0, 1), ("k1", 0, 0, 0)]
         stream = stream or torch.cuda.current_stream()
         timings, steps_run = [], 0
-        for strategy, chunks, sms in candidates:
-            self.set_exchange(strategy, chunks, sms)
+        for strategy, chunks, sms, keep in candidates:
+            self.set_exchange(strategy, chunks, sms, keep)
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -252,10 +255,10 @@ class RowShardedSpMM:
             steps_run += reps + 1
             t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            timings.append({"strategy": strategy, "chunks": chunks, "sms": sms, "ms_per_step": float(t.item()),
-                            "kernel": _lib.last_spmm_kernel()})
+            timings.append({"strategy": strategy, "chunks": chunks, "sms": sms, "keep": keep,
+                            "ms_per_step": float(t.item()), "kernel": _lib.last_spmm_kernel()})
         best = min(timings, key=lambda r: r["ms_per_step"])  # identical on every rank (all-reduced times)
-        self.set_exchange(best["strategy"], best["chunks"], best["sms"])
+        self.set_exchange(best["strategy"], best["chunks"], best["sms"], best["keep"])
         dist.barrier(group=self.group)
         return {"chosen": best, "candidates": timings, "steps_run": steps_run}
 

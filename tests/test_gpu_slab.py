@@ -77,6 +77,29 @@ def test_slab_kernel_matches_oracle(variant):
     assert "OK" in out
 
 
+def test_slab_kernel_with_evict_last_gathers():
+    """Option slab_keep: the same executor with an L2 evict_last policy on its gathers (the variant the fused
+    all-gather may pick); results must be the same as the plain one."""
+    out = _run("""
+        import numpy as np
+        import sparse_dot_b200 as sdb
+        from sparse_dot_b200 import sharded
+        from oracle import oracle as orc
+        from tests import _cases as cs
+        a = cs.uniform_rows_csr(6000, 20000, 30, np.float32, seed=1)
+        x = np.random.default_rng(2).random((20000, 128), dtype=np.float32)
+        y0 = np.random.default_rng(3).random((6000, 128), dtype=np.float32)
+        with sharded.RowShardedSpMM(a, 128) as plan:
+            plan.set_x(x); plan.set_local_y(y0)
+            plan.run(alpha=1.0, beta=0.5); plan.synchronize()
+            got = plan.read_panel()
+            assert sdb.last_spmm_kernel().endswith("keep>"), sdb.last_spmm_kernel()
+        assert cs.rel_err(got, orc.c_spmm(a, x, beta=0.5, y=y0.copy())) <= 1e-5
+        print("OK")
+    """, extra_env={"SDB_SLAB_KEEP": "1"})
+    assert "OK" in out
+
+
 def test_slab_kernel_two_rank_fused_allgather():
     out = _run("""
         import subprocess, sys

@@ -32,8 +32,10 @@ def _kernel_sass(pattern):
 @pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.exists(OBJ),
                     reason="needs cuobjdump and the in-tree object file")
 @pytest.mark.parametrize("dtype_code", ["f", "d"])
-def test_default_streaming_kernel_keeps_its_gather_ring_rolling(dtype_code):
-    sass = _kernel_sass(f"spmm_stream_kernelI{dtype_code}Li6ELi32ELi2ELi2E")  # <T, RPW=6, WARPS=32, U=2, CTAS=2>
+@pytest.mark.parametrize("keep", [0, 1])
+def test_default_streaming_kernel_keeps_its_gather_ring_rolling(dtype_code, keep):
+    # <T, RPW=6, WARPS=32, U=2, CTAS=2, KEEP>: the plain gathers and the ones with an L2 evict_last policy
+    sass = _kernel_sass(f"spmm_stream_kernelI{dtype_code}Li6ELi32ELi2ELi2ELb{keep}E")
     assert sass, "default streaming kernel not found in spmm_slab.o"
     at = [i for i, ins in enumerate(sass) if "LDG.E.128" in ins]
     gaps = collections.Counter(b - a for a, b in zip(at, at[1:]))
