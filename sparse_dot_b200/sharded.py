@@ -235,9 +235,9 @@ class RowShardedSpMM:
             return {"chosen": None, "steps_run": 0}
         if candidates is None:
             # (strategy, chunks, copier SMs, keep): keep = the streaming kernel's gathers carry an L2 evict_last policy
-            candidates = [("ce", 5, 0, 0), ("ce", 10, 0, 0), ("ce", 20, 0, 0), ("ce", 10, 0, 1), ("ce", 20, 0, 1),
-                          ("sm", 10, 8, 0), ("sm", 20, 16, 0), ("sm", 20, 16, 1), ("stores", 0, 0, 0),
-                          ("stores", 0, 0, 1), ("k1", 0, 0, 0)]
+            # (measured at N = 4, profiles/r2_logs/bench_n4_keep.json: keep never wins, so it is not in the default list)
+            candidates = [("ce", 5, 0, 0), ("ce", 10, 0, 0), ("ce", 20, 0, 0), ("sm", 10, 8, 0), ("sm", 20, 16, 0),
+                          ("stores", 0, 0, 0), ("k1", 0, 0, 0)]
         stream = stream or torch.cuda.current_stream()
         timings, steps_run = [], 0
         for strategy, chunks, sms, keep in candidates:
