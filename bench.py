@@ -781,7 +781,8 @@ def run_legs(args, peak):
                 # numeric (4+4) + symbolic 4 bytes per product, A once per pass, C written once
                 gb = (r["products"] * 12 + 2 * r["nnz_a"] * 8 + r["nnz_c"] * 8) / 1e9
                 r["g_products_per_s_ordered"] = r["products"] / (ms * 1e-3) / 1e9
-                r["roofline"] = roof(name, gb, ms, "spgemm_ordered")
+                # the ncu capture (sum over the kernels of one ordered call) exists for edge factor 1 only
+                r["roofline"] = roof(name, gb, ms, "spgemm_ordered" if ef == 1 else "spgemm_ordered_ef4")
                 r["config"] = f"BASELINE configs[2]: R-MAT scale 22, edge factor {ef}, fp32, sorted sparse output " \
                               "(sdb_spgemm_ordered = reorder_output=True), result kept in HBM"
             elif name == "gram":
