@@ -90,12 +90,32 @@ CASES = [
 ]
 
 
+# the same with 4 and 8 ranks (the SCALE run's rank counts; they share the visible GPUs round-robin): every peer list
+# length the library supports, the seven-target copier kernel, epilogue stores into seven peer panels
+MANY_RANK_CASES = [
+    (8, "ce", "1", 40_000, "spmm_rowmajor"),
+    (8, "sm", "2", 400_000, "spmm_stream"),
+    (8, "stores", "2", 400_000, "spmm_stream"),
+    (8, "k1", "1", 40_000, "spmm_rowmajor"),
+    (4, "sm", "1", 200_000, "spmm_rowmajor"),
+]
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,strategy,slab,rows,kernel", MANY_RANK_CASES)
+def test_many_rank_fused_allgather_matches_oracle(world, strategy, slab, rows, kernel):
+    _run_fused_case(world, strategy, slab, rows, kernel)
+
+
 @pytest.mark.timeout(300)
 @pytest.mark.parametrize("strategy,slab,rows,kernel", CASES)
 def test_two_rank_fused_allgather_matches_oracle(strategy, slab, rows, kernel):
+    _run_fused_case(2, strategy, slab, rows, kernel)
+
+
+def _run_fused_case(world, strategy, slab, rows, kernel):
     import torch.multiprocessing as mp
 
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
