@@ -269,6 +269,138 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS)
     }
 }
 
+// ---------------------------------------------------------------- executor for 256-byte rows
+// Panels of n * sv = 256 bytes per row (N = 64 fp32, N = 32 fp64): a row is 16 lanes x 16 bytes, so a warp runs
+// TWO independent streams, one per half-warp.  Half h of warp w owns group 2 w + h of the CTA (RPW rows, its own
+// accumulators, its own 16-entry staging buffer, its own running sums); the halves never touch each other's state,
+// they only share the instruction stream.  Everything that synchronises (__syncwarp) sits at warp-uniform points:
+// the chunk loop runs to the longer of the two streams and each half masks what it has run out of.  The common
+// case — both halves hold a full chunk of 16 entries — takes an unguarded unrolled path with the same rolling ring
+// of two gathers as the 512-byte kernel.  Same inspector (slab-ordered copy per group of RPW rows), same epilogue.
+template <typename T, int RPW, int WARPS, int CTAS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS)
+    spmm_stream_half_kernel(int64_t rows, const int64_t* __restrict__ indptr, const uint32_t* __restrict__ ent_rc,
+                            const T* __restrict__ ent_val, const T* __restrict__ X, uint32_t row_bytes, T alpha, T beta,
+                            T* __restrict__ y_self, SlabPeers<T> peers, int n_peers, int self, int64_t row0,
+                            int64_t ldy) {
+    constexpr int VEC = Pack16<T>::N;
+    constexpr int kGroups = WARPS * 2;     // groups (half-warps) per CTA
+    constexpr int kRows = RPW * kGroups;   // rows per CTA
+    constexpr unsigned kFull = 0xffffffffu;
+    using Ent = StagedEntry<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, sub = lane & 15;
+    const int group = warp * 2 + half;
+    Pack16<T>* acc = reinterpret_cast<Pack16<T>*>(smem_raw) + group * RPW * 16 + sub;  // [RPW rows][16 lanes]
+    Ent* stage = reinterpret_cast<Ent*>(smem_raw + size_t(kRows) * 256) + group * 16;
+    const char* xlane = reinterpret_cast<const char*>(X + sub * VEC);
+    const int64_t n_blocks = (rows + kRows - 1) / kRows;
+    Pack16<T> zero;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) zero.v[i] = Num<T>::zero();
+
+    for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) {
+        const int64_t row_base = rb * kRows + int64_t(group) * RPW;
+        const bool live = row_base < rows;  // per half; the warp stays together
+        const int live_rows = live ? int(min(int64_t(RPW), rows - row_base)) : 0;
+        int64_t beg = 0;
+        int n_ent = 0;
+        if (live) {
+            beg = indptr[row_base];
+            n_ent = int(min(indptr[row_base + live_rows] - beg, int64_t(INT32_MAX)));
+        }
+        const uint32_t* __restrict__ erc = ent_rc + beg;
+        const T* __restrict__ eva = ent_val + beg;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) acc[r * 16] = zero;
+        Pack16<T> cur = zero;
+        uint32_t cur_row = 0;
+        auto consume = [&](const Ent& e, const Pack16<T>& x) {
+            const uint32_t r = e.rc >> kColBits;
+            if (r != cur_row) {  // uniform inside a half-warp
+                acc[cur_row * 16] = cur;
+                cur_row = r;
+                cur = acc[r * 16];
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) cur.v[i] = madd(e.v, x.v[i], cur.v[i]);
+        };
+        // the longer stream of the two halves bounds the chunk loop (warp-uniform)
+        const int n_other = __shfl_xor_sync(kFull, n_ent, 16);
+        const int n_max = max(n_ent, n_other);
+        uint32_t rc_nx = 0;
+        T v_nx = Num<T>::zero();
+        if (sub < n_ent) {
+            rc_nx = __ldcs(erc + sub);
+            v_nx = ldcs(eva + sub);
+        }
+        for (int f = 0; f < n_max; f += 16) {
+            __syncwarp();  // the previous chunk has been consumed by every lane
+            Ent mine;
+            mine.rc = rc_nx;
+            mine.v = v_nx;
+            stage[sub] = mine;
+            __syncwarp();
+            if (f + 16 + sub < n_ent) {
+                rc_nx = __ldcs(erc + f + 16 + sub);
+                v_nx = ldcs(eva + f + 16 + sub);
+            }
+            const int cnt = max(0, min(16, n_ent - f));  // this half's entries in the chunk
+            if (__all_sync(kFull, cnt == 16)) {
+                Ent e[2];
+                Pack16<T> x[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    e[u] = stage[u];
+                    x[u] = gather16<T>(xlane, e[u].rc & kColMask, row_bytes);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    consume(e[j % 2], x[j % 2]);
+                    if (j + 2 < 16) {
+                        e[j % 2] = stage[j + 2];
+                        x[j % 2] = gather16<T>(xlane, e[j % 2].rc & kColMask, row_bytes);
+                    }
+                }
+            } else {
+                // ragged end of either stream: one entry at a time, each half masking what it does not have
+                for (int j = 0; j < 16; ++j) {
+                    if (j < cnt) {
+                        const Ent ej = stage[j];
+                        const Pack16<T> xj = gather16<T>(xlane, ej.rc & kColMask, row_bytes);
+                        consume(ej, xj);
+                    }
+                }
+            }
+        }
+        acc[cur_row * 16] = cur;
+
+        const bool beta_zero = Num<T>::is_zero(beta);
+        for (int r = 0; r < live_rows; ++r) {
+            const int64_t o = (row0 + row_base + r) * ldy + sub * VEC;
+            const Pack16<T> t = acc[r * 16];
+            Pack16<T> out;
+            if (beta_zero) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) out.v[i] = mul(alpha, t.v[i]);
+            } else {
+                Pack16<T> old;
+                *reinterpret_cast<float4*>(&old) = __ldcs(reinterpret_cast<const float4*>(y_self + o));
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) out.v[i] = madd(alpha, t.v[i], mul(beta, old.v[i]));
+            }
+            __stcs(reinterpret_cast<float4*>(y_self + o), *reinterpret_cast<const float4*>(&out));
+            if (n_peers > 1) {
+#pragma unroll
+                for (int q = 0; q < kSlabMaxPeers; ++q)
+                    if (q < n_peers && q != self)
+                        __stcs(reinterpret_cast<float4*>(peers.y[q] + o), *reinterpret_cast<const float4*>(&out));
+            }
+        }
+    }
+}
+
 size_t slab_target_bytes() {
     static const size_t v = [] {
         const char* e = getenv("SDB_SLAB_MB");
@@ -347,6 +479,32 @@ static sdb_status launch_stream(cudaStream_t s, const CsrView& a, const sdb_mat*
     return SDB_STATUS_SUCCESS;
 }
 
+// 256-byte rows: two groups per warp (spmm_stream_half_kernel); rows per SM as for the 512-byte kernel
+template <typename T>
+static sdb_status launch_half(cudaStream_t s, const CsrView& a, const sdb_mat* m, const T* X, int64_t ldx, T alpha, T beta,
+                              void* const* dY_peers, int n_peers, int self, int64_t row0, int64_t ldy, int sm_count) {
+    constexpr int RPW = 6, WARPS = 16, CTAS = 4;  // 4 CTAs x 16 warps x 2 groups x 6 rows = 768 rows of 256 B per SM
+    constexpr int kRows = RPW * WARPS * 2;
+    constexpr size_t kSmem = size_t(kRows) * 256 + size_t(WARPS) * 32 * sizeof(StagedEntry<T>);
+    static_assert((kSmem + 1024) * CTAS <= 233472, "shared memory per SM");
+    const int64_t sub_rows = a.sub_rows < 0 ? a.rows : a.sub_rows;
+    SDB_REQUIRE(a.sub_begin % kRows == 0, SDB_STATUS_INVALID_VALUE, "spmm_slab: sub-range not aligned to the row groups");
+    const int64_t* sub_indptr = a.indptr + a.sub_begin;
+    row0 += a.sub_begin;
+    const int64_t n_blocks = (sub_rows + kRows - 1) / kRows;
+    const int live_sms = std::max(1, sm_count - t_reserved_sms);
+    const unsigned grid = unsigned(std::min<int64_t>(n_blocks, int64_t(live_sms) * CTAS));
+    auto kernel = spmm_stream_half_kernel<T, RPW, WARPS, CTAS>;
+    SDB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmem)));
+    note_spmm_kernel("spmm_stream_half_kernel<%s,%d,%d,%d>", dtype_cname(Num<T>::dtype), RPW, WARPS, CTAS);
+    SlabPeers<T> peers;
+    for (int q = 0; q < kSlabMaxPeers; ++q) peers.y[q] = q < n_peers ? static_cast<T*>(dY_peers[q]) : nullptr;
+    SDB_LAUNCH(kernel, grid, WARPS * 32, kSmem, s, sub_rows, sub_indptr, static_cast<const uint32_t*>(m->slab_rc),
+               static_cast<const T*>(m->slab_val), X, uint32_t(ldx * int64_t(sizeof(T))), alpha, beta, peers.y[self], peers,
+               n_peers, self, row0, ldy);
+    return SDB_STATUS_SUCCESS;
+}
+
 #define SDB_SLAB_ARGS s, a, m, X, ldx, alpha, beta, dY_peers, n_peers, self, row0, ldy, sm_count, col_chunks
 template <typename T>
 static sdb_status launch_variant(cudaStream_t s, const CsrView& a, const sdb_mat* m, const T* X, int64_t ldx, T alpha,
@@ -395,7 +553,9 @@ static bool slab_wanted(const CsrView& a, int dtype, int64_t n, int64_t ldx, boo
     if (!a.owner->owns) return false;
     if (dtype != SDB_F32 && dtype != SDB_F64) return false;
     const size_t sv = dtype_size(dtype);
-    if (n <= 0 || (size_t(n) * sv) % 512 != 0 || size_t(n) * sv > 4096) return false;  // 1..8 column chunks of 512 B
+    // 1..8 column chunks of 512 bytes, or one row of 256 bytes (two groups per warp)
+    const size_t row_b = size_t(n > 0 ? n : 0) * sv;
+    if (n <= 0 || !(row_b == 256 || (row_b % 512 == 0 && row_b <= 4096))) return false;
     if ((size_t(ldx) * sv) % 16 != 0 || size_t(ldx) * sv >= (size_t(1) << 31)) return false;
     if (a.cols >= (int64_t(1) << kColBits) || a.rows <= 0 || a.nnz <= 0) return false;
     if (a.owner->strict_sorted == -1) return false;
@@ -421,8 +581,9 @@ sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int 
     }
     if (m->strict_sorted != 1) return SDB_STATUS_NOT_SUPPORTED;
     const size_t sv = dtype_size(dtype);
-    const int64_t width = std::max<int64_t>(64, int64_t(slab_target_bytes() / 512));
-    const int rpw = slab_rpw();
+    const bool half_rows = size_t(n) * sv == 256;
+    const int64_t width = std::max<int64_t>(64, int64_t(slab_target_bytes() / (half_rows ? 256 : 512)));
+    const int rpw = half_rows ? 6 : slab_rpw();
     if (m->slab_rc == nullptr || m->slab_width != width || m->slab_rpw != rpw) {
         // inspector: the slab-ordered copy of A, cached on the handle until sdb_order / destroy
         cudaStream_t ls = ctx->stream;
@@ -447,6 +608,13 @@ sdb_status spmm_slab_device(Context* ctx, cudaStream_t s, const CsrView& a, int 
         if (s != ls) SDB_CUDA(cudaStreamSynchronize(ls));
     }
     cache_lock.unlock();
+    if (half_rows) {
+        if (dtype == SDB_F32)
+            return launch_half<float>(s, a, m, static_cast<const float*>(dX), ldx, float(alpha[0]), float(beta[0]),
+                                      dY_peers, n_peers, self, row0, ldy, ctx->sm_count);
+        return launch_half<double>(s, a, m, static_cast<const double*>(dX), ldx, alpha[0], beta[0], dY_peers, n_peers,
+                                   self, row0, ldy, ctx->sm_count);
+    }
     const int col_chunks = int(size_t(n) * sv / 512);
     if (dtype == SDB_F32)
         return launch_variant<float>(s, a, m, static_cast<const float*>(dX), ldx, float(alpha[0]), float(beta[0]),

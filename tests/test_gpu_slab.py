@@ -35,7 +35,8 @@ def test_slab_kernel_matches_oracle(variant):
         from oracle import oracle as orc
         from tests import _cases as cs
         before = sdb.kernel_launches()
-        for dtype, n in ((np.float32, 128), (np.float64, 64), (np.float32, 256), (np.float64, 192)):
+        for dtype, n in ((np.float32, 128), (np.float64, 64), (np.float32, 256), (np.float64, 192),
+                         (np.float32, 64), (np.float64, 32)):  # the last two: 256-byte rows, two groups per warp
             a = cs.uniform_rows_csr(5000, 20000, 30, dtype, seed=1).tolil()
             a[7, :] = 0
             a[4999, :] = 0
@@ -59,7 +60,8 @@ def test_slab_kernel_matches_oracle(variant):
                 got = plan.read_panel()
                 want = orc.c_spmm(a, x, alpha=2.0, beta=0.5, y=y0.copy())
                 assert cs.rel_err(got, want, 2 * bound + 0.5 * y0) <= tol, "beta=0.5"
-                assert sdb.last_spmm_kernel().startswith("spmm_stream_kernel"), sdb.last_spmm_kernel()
+                want_kernel = "spmm_stream_half_kernel" if n * np.dtype(dtype).itemsize == 256 else "spmm_stream_kernel"
+                assert sdb.last_spmm_kernel().startswith(want_kernel), sdb.last_spmm_kernel()
             # through the public API (fresh handle per call)
             got = sdb.dot_product_mkl(a, x, out=y0.copy(), out_scalar=0.5)
             want = orc.c_spmm(a, x, beta=0.5, y=y0.copy())
