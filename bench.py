@@ -367,10 +367,12 @@ def bind_to_gpu_numa(gpu_index):
         h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
         cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
-        cpus &= set(os.sched_getaffinity(0))
-        if cpus:
+        allowed = set(os.sched_getaffinity(0))
+        cpus &= allowed
+        if cpus and cpus != allowed:  # a real restriction: this GPU has its own NUMA-local cores
             os.sched_setaffinity(0, cpus)
-        return len(cpus)
+            return len(cpus)
+        return 0  # NVML names every allowed core for this GPU (one NUMA node, e.g. a VM): nothing to bind to
     except Exception:
         return 0
 
@@ -497,7 +499,8 @@ def run_ours(args):
             "value": g1 * world / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3, "steps": e2e_steps,
             "h2d_bytes_per_step": int(a.data.nbytes + a.indices.nbytes + a.indptr.nbytes + x.nbytes + y0.nbytes),
             "d2h_bytes_per_step": int(y0.nbytes),
-            "host_memory": "pinned (sdb_host_alloc)" + (f", rank bound to {local_cpus} GPU-local cores" if local_cpus else ""),
+            "host_memory": "pinned (sdb_host_alloc)" + (f", rank bound to {local_cpus} GPU-local cores" if local_cpus else
+                                                        (", all ranks share one NUMA node" if world > 1 else "")),
             "device_spans_ms": {"start_to_last_upload": phases[0], "kernel_sum": phases[1], "whole_call": phases[2]},
             "max_rel_err": err,
             "api": "sparse_dot_b200.dot_product_mkl(csr, ndarray, out=, out_scalar=) -> sdb_spmm_csr_host "
