@@ -12,14 +12,16 @@
 //   CTA bin    one 512-thread CTA, 8192-slot shared-memory hash table
 //   wide bin   one CTA, bitmap of the column range in global memory (L2 resident) with a
 //              word-level summary in shared memory, emitted in ascending column order
+//   huge bin   rows above 32768 entries: the same, one CTA per SM, four products per lane in flight
+// (sorted results send rows of 1025..4096 entries to the wide bin instead of the CTA bin: sorted for free)
 // (teams and tables are sized to the rows they serve: a row's fixed costs — clearing and scanning its
 // table — are proportional to the table, so a 300-product row must not pay for an 8192-slot one)
 // MKL's structural convention is kept: an entry exists for every structural
 // product even if the values cancel to 0.0 (SURVEY §8c parity hazard 2), and
 // columns inside a row are unordered until sdb_order.
 // sdb_syrk is the same two passes on (A^T, A) or (A, A^T) with a col >= row
-// filter.  Dense results accumulate one output row (column tile) per CTA in
-// shared memory and write it once.  HBM/L2-bound integer + FMA work.
+// filter.  Dense results accumulate one output row per CTA, in a shared-memory column tile or with global
+// reductions into the L2-resident row.  Atomic-path- and latency-bound integer + FMA work.
 #include <cstdlib>
 
 #include "common.h"
