@@ -53,6 +53,14 @@ for step in "$@"; do
       timeout 900 ncu --metrics gpu__time_duration.sum $NCU_COMMON -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
         python ${arg:-$BENCH_SHORT} > $OUT/${TAG}_launches.log 2>&1
       tail -3 $OUT/${TAG}_launches.csv | cut -c1-300 ;;
+    ncuenv)  # ncuenv=<VAR=VAL>,<kernel regex>,<name>,<skip>,<count>,<cmd>: the same with one environment variable set
+      IFS=, read -r envs regex nm skip count cmd <<< "$arg"
+      env $envs timeout 1200 ncu --set full $NCU_COMMON --import-source on -k "regex:$regex" -s ${skip:-2} -c ${count:-1} -f \
+        -o $OUT/${TAG}_$nm python ${cmd:-$BENCH_SHORT} > $OUT/${TAG}_ncu_$nm.log 2>&1
+      tail -2 $OUT/${TAG}_ncu_$nm.log
+      python scripts/ncu_summary.py $OUT/${TAG}_$nm.ncu-rep > $OUT/${TAG}_${nm}_summary.txt 2>&1
+      python scripts/ncu_traffic.py --dump $OUT/${TAG}_$nm.ncu-rep > $OUT/${TAG}_${nm}_launches.json 2>/dev/null
+      if [ "$(stat -c %s $OUT/${TAG}_$nm.ncu-rep 2>/dev/null || echo 0)" -gt 8000000 ]; then rm -f $OUT/${TAG}_$nm.ncu-rep; fi ;;
     ncu)
       IFS=, read -r regex nm skip count cmd <<< "$arg"
       timeout 1200 ncu --set full $NCU_COMMON --import-source on -k "regex:$regex" -s ${skip:-2} -c ${count:-1} -f \

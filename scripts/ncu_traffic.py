@@ -27,6 +27,7 @@ TABLE = os.path.join(ROOT, "profiles", "kernel_traffic.json")
 # kernel families whose SASS is hashed on the box: substring of the mangled name
 FAMILIES = {
     "spmm_stream_kernel": "spmm_stream_kernel",
+    "spmm_stream_half_kernel": "spmm_stream_half_kernel",
     "spmm_rowmajor_kernel": "spmm_rowmajor_kernel",
     "spmm_bsr_kernel": "spmm_bsr_kernel",
     "spmm_bsr_mma_kernel": "spmm_bsr_mma_kernel",
@@ -38,6 +39,9 @@ MATCH = {
     "spmm_stream_kernel<float,6,32,2,2>": "spmm_stream_kernelIfLi6ELi32ELi2ELi2ELb0",
     "spmm_bsr_kernel<float,16,256,0,2>": "spmm_bsr_kernelIfLi16ELi256ELb0ELi2E",
     "spgemm_dense_red_kernel<float>": "spgemm_dense_red_kernelIf",
+    "spmm_rowmajor_kernel<float,4,32,2,8>": "spmm_rowmajor_kernelIfLi4ELi32ELi2ELi8E",
+    "spmm_bsr_mma_kernel<float,16,256,0,2>": "spmm_bsr_mma_kernelIfLi16ELi256ELb0ELi2E",
+    "spmm_stream_half_kernel<float,6,16,4>": "spmm_stream_half_kernelIfLi6ELi16ELi4E",
 }
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 TSCALE = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "second": 1.0, "msecond": 1e-3, "usecond": 1e-6,
