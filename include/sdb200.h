@@ -292,6 +292,11 @@ SDB_API sdb_status sdb_host_free(void* p);
 SDB_API sdb_status sdb_dev_alloc(void** p, size_t bytes);
 SDB_API sdb_status sdb_dev_free(void* p);
 SDB_API sdb_status sdb_memcpy(void* dst, const void* src, size_t bytes, int kind);
+/* The same for a panel of `rows` rows of `row_bytes` each with different pitches (bytes between row starts) on
+ * the two sides, kind 1 or 2: a column range of a row-major array, or an array with a leading dimension.  Pageable
+ * host memory is staged through the page-locked ring by the library's copy threads, as in sdb_memcpy. */
+SDB_API sdb_status sdb_memcpy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes,
+                                 size_t rows, int kind);
 SDB_API sdb_status sdb_device_synchronize(void);
 
 /* Peer mapping of an sdb_dev_alloc buffer into another process on the same

@@ -71,6 +71,7 @@ PROTOTYPES = {
     "sdb_dev_alloc": (_i32, [_pvp, _ct.c_size_t]),
     "sdb_dev_free": (_i32, [_vp]),
     "sdb_memcpy": (_i32, [_vp, _vp, _ct.c_size_t, _i32]),
+    "sdb_memcpy_2d": (_i32, [_vp, _ct.c_size_t, _vp, _ct.c_size_t, _ct.c_size_t, _ct.c_size_t, _i32]),
     "sdb_ipc_export": (_i32, [_vp, _ct.c_char_p]),
     "sdb_ipc_open": (_i32, [_ct.c_char_p, _pvp]),
     "sdb_ipc_close": (_i32, [_vp]),

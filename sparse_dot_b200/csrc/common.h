@@ -164,6 +164,7 @@ struct DevBuf {
 // with independent pitches (dense panels with ld != n).
 bool is_pinned(const void* p);  // page-locked (or managed) host memory: DMA without staging
 void host_copy(void* dst, const void* src, size_t bytes);  // memcpy split over the library's copy threads
+void host_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows);
 sdb_status ensure_ring(PinnedRing* ring, size_t slot_bytes);
 sdb_status h2d(Context* ctx, void* d_dst, const void* h_src, size_t bytes);
 sdb_status d2h(Context* ctx, void* h_dst, const void* d_src, size_t bytes);

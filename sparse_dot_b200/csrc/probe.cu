@@ -99,6 +99,19 @@ static sdb_status probe_host_copy(int64_t bytes, int iters, double* gbs) {
         host_copy(static_cast<char*>(slots[1]) + 3, src + 7, odd);
         ok = memcmp(static_cast<char*>(slots[1]) + 3, src + 7, odd) == 0;
     }
+    if (ok && size_t(bytes) >= (size_t(8) << 20)) {
+        // strided panels (host_copy_2d): 997 rows of 5003 bytes, pitch 8191 -> packed, and back out to pitch 6007
+        const size_t rows = 997, rb = 5003, sp = 8191, dp = 6007;
+        char* packed = static_cast<char*>(slots[2]);
+        char* spread = static_cast<char*>(slots[3]);
+        memset(spread, 0x33, rows * dp);
+        host_copy_2d(packed, rb, src + 11, sp, rb, rows);
+        host_copy_2d(spread + 5, dp, packed, rb, rb, rows);
+        for (size_t r = 0; r < rows && ok; ++r) {
+            ok = memcmp(packed + r * rb, src + 11 + r * sp, rb) == 0 && memcmp(spread + 5 + r * dp, src + 11 + r * sp, rb) == 0;
+            for (size_t g = rb; g < dp && ok && r + 1 < rows; ++g) ok = spread[5 + r * dp + g] == 0x33;  // gaps untouched
+        }
+    }
     for (auto& p : slots) {
         if (pinned) cudaFreeHost(p);
         else free(p);

@@ -251,12 +251,44 @@ class CopyPool {
         std::unique_lock<std::mutex> lk(m_);
         job.done_cv.wait(lk, [&] { return job.finished == job.n_pieces; });
     }
+    // `rows` rows of `row_bytes` each, row r from src + r * spitch to dst + r * dpitch: pieces are row ranges
+    void copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows) {
+        if (rows == 0 || row_bytes == 0) return;
+        if (dpitch == row_bytes && spitch == row_bytes) return copy(dst, src, row_bytes * rows);
+        Job job;
+        job.dst = static_cast<char*>(dst);
+        job.src = static_cast<const char*>(src);
+        job.bytes = rows;  // counted in rows for a 2-D job
+        job.row_bytes = row_bytes;
+        job.dpitch = dpitch;
+        job.spitch = spitch;
+        // about one piece per thread, at least ~256 KiB of payload each
+        const size_t min_rows = std::max<size_t>(1, (size_t(256) << 10) / row_bytes);
+        job.piece = std::max(min_rows, (rows + size_t(workers_)) / size_t(workers_ + 1));
+        job.n_pieces = (rows + job.piece - 1) / job.piece;
+        if (job.n_pieces > 1 && workers_ > 0) {
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                jobs_.push_back(&job);
+            }
+            cv_.notify_all();
+        } else {
+            job.n_pieces = 1;
+            job.piece = rows;
+            job.local = true;
+        }
+        run_pieces(&job);
+        std::unique_lock<std::mutex> lk(m_);
+        job.done_cv.wait(lk, [&] { return job.finished == job.n_pieces; });
+    }
 
   private:
     struct Job {
         char* dst;
         const char* src;
         size_t bytes, piece, n_pieces;
+        size_t row_bytes = 0, dpitch = 0, spitch = 0;  // row_bytes != 0: a 2-D job, `bytes` and `piece` count rows
+        bool local = false;                            // never queued: the submitter runs its only piece
         size_t next = 0;      // guarded by m_
         size_t finished = 0;  // guarded by m_
         std::condition_variable done_cv;
@@ -279,7 +311,7 @@ class CopyPool {
     // `finished` increment has been published.
     size_t claim(Job* job) {
         const size_t idx = job->next++;
-        if (job->next == job->n_pieces) {
+        if (job->next == job->n_pieces && !job->local) {
             for (size_t i = 0; i < jobs_.size(); ++i)
                 if (jobs_[i] == job) {
                     jobs_.erase(jobs_.begin() + long(i));
@@ -291,8 +323,17 @@ class CopyPool {
     void copy_piece(Job* job, size_t idx) {
         const size_t off = idx * job->piece;
         const size_t len = std::min(job->piece, job->bytes - off);
-        if (use_stream_copy()) stream_copy(job->dst + off, job->src + off, len);
-        else memcpy(job->dst + off, job->src + off, len);
+        if (job->row_bytes) {
+            const bool nt = use_stream_copy() && job->row_bytes >= 4096;
+            for (size_t r = off; r < off + len; ++r) {
+                if (nt) stream_copy(job->dst + r * job->dpitch, job->src + r * job->spitch, job->row_bytes);
+                else memcpy(job->dst + r * job->dpitch, job->src + r * job->spitch, job->row_bytes);
+            }
+        } else if (use_stream_copy()) {
+            stream_copy(job->dst + off, job->src + off, len);
+        } else {
+            memcpy(job->dst + off, job->src + off, len);
+        }
         std::lock_guard<std::mutex> lk(m_);
         if (++job->finished == job->n_pieces) job->done_cv.notify_all();  // `job` must not be touched after this
     }
@@ -330,6 +371,9 @@ class CopyPool {
 }  // namespace
 
 void host_copy(void* dst, const void* src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
+void host_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows) {
+    CopyPool::get().copy_2d(dst, dpitch, src, spitch, row_bytes, rows);
+}
 
 static void fast_memcpy(void* dst, const void* src, size_t bytes) { host_copy(dst, src, bytes); }
 
@@ -395,10 +439,26 @@ sdb_status h2d_2d(Context* ctx, void* d_dst, size_t d_pitch, const void* h_src, 
                   size_t row_bytes, size_t rows) {
     if (rows == 0 || row_bytes == 0) return SDB_STATUS_SUCCESS;
     if (d_pitch == row_bytes && h_pitch == row_bytes) return h2d(ctx, d_dst, h_src, row_bytes * rows);
-    // strided panels are rare (ld != n): let the driver do the 2-D copy
-    SDB_CUDA(cudaMemcpy2DAsync(d_dst, d_pitch, h_src, h_pitch, row_bytes, rows,
-                               cudaMemcpyHostToDevice, ctx->stream));
-    if (!is_pinned(h_src)) SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (is_pinned(h_src) || row_bytes > Context::kChunkBytes) {
+        SDB_CUDA(cudaMemcpy2DAsync(d_dst, d_pitch, h_src, h_pitch, row_bytes, rows,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+        if (!is_pinned(h_src)) SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SDB_STATUS_SUCCESS;
+    }
+    // strided pageable panel: whole rows are packed into the page-locked chunks by the copy pool, the DMA engine
+    // spreads them to the device pitch
+    SDB_TRY(ensure_staging(ctx));
+    const size_t per = Context::kChunkBytes / row_bytes;
+    for (size_t r = 0; r < rows; r += per) {
+        const size_t nr = std::min(per, rows - r);
+        int k = ctx->next_chunk;
+        ctx->next_chunk = (k + 1) % Context::kChunks;
+        SDB_CUDA(cudaEventSynchronize(ctx->chunk_free[k]));
+        host_copy_2d(ctx->chunk[k], row_bytes, (const char*)h_src + r * h_pitch, h_pitch, row_bytes, nr);
+        SDB_CUDA(cudaMemcpy2DAsync((char*)d_dst + r * d_pitch, d_pitch, ctx->chunk[k], row_bytes, row_bytes, nr,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+        SDB_CUDA(cudaEventRecord(ctx->chunk_free[k], ctx->stream));
+    }
     return SDB_STATUS_SUCCESS;
 }
 
@@ -406,9 +466,40 @@ sdb_status d2h_2d(Context* ctx, void* h_dst, size_t h_pitch, const void* d_src, 
                   size_t row_bytes, size_t rows) {
     if (rows == 0 || row_bytes == 0) return SDB_STATUS_SUCCESS;
     if (d_pitch == row_bytes && h_pitch == row_bytes) return d2h(ctx, h_dst, d_src, row_bytes * rows);
-    SDB_CUDA(cudaMemcpy2DAsync(h_dst, h_pitch, d_src, d_pitch, row_bytes, rows,
-                               cudaMemcpyDeviceToHost, ctx->stream));
-    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (is_pinned(h_dst) || row_bytes > Context::kChunkBytes) {
+        SDB_CUDA(cudaMemcpy2DAsync(h_dst, h_pitch, d_src, d_pitch, row_bytes, rows,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+        SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SDB_STATUS_SUCCESS;
+    }
+    // strided pageable destination: the DMA engine packs whole rows into the page-locked chunks, the copy pool
+    // spreads each chunk to the caller's pitch while the next one is in flight
+    SDB_TRY(ensure_staging(ctx));
+    const size_t per = Context::kChunkBytes / row_bytes;
+    struct Pending { int k; size_t r, nr; };
+    Pending pend[Context::kChunks];
+    int head = 0, tail = 0, inflight = 0;
+    size_t r = 0;
+    while (r < rows || inflight > 0) {
+        while (r < rows && inflight < Context::kChunks - 1) {
+            const size_t nr = std::min(per, rows - r);
+            int k = ctx->next_chunk;
+            ctx->next_chunk = (k + 1) % Context::kChunks;
+            SDB_CUDA(cudaEventSynchronize(ctx->chunk_free[k]));
+            SDB_CUDA(cudaMemcpy2DAsync(ctx->chunk[k], row_bytes, (const char*)d_src + r * d_pitch, d_pitch, row_bytes, nr,
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+            SDB_CUDA(cudaEventRecord(ctx->chunk_free[k], ctx->stream));
+            pend[tail] = {k, r, nr};
+            tail = (tail + 1) % Context::kChunks;
+            ++inflight;
+            r += nr;
+        }
+        Pending p = pend[head];
+        head = (head + 1) % Context::kChunks;
+        --inflight;
+        SDB_CUDA(cudaEventSynchronize(ctx->chunk_free[p.k]));
+        host_copy_2d((char*)h_dst + p.r * h_pitch, h_pitch, ctx->chunk[p.k], row_bytes, row_bytes, p.nr);
+    }
     return SDB_STATUS_SUCCESS;
 }
 
@@ -560,6 +651,21 @@ sdb_status sdb_memcpy(void* dst, const void* src, size_t bytes, int kind) {
     } else {
         SDB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    SDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SDB_STATUS_SUCCESS;
+}
+
+sdb_status sdb_memcpy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows,
+                         int kind) {
+    SDB_REQUIRE(kind == 1 || kind == 2, SDB_STATUS_INVALID_VALUE, "sdb_memcpy_2d: kind must be 1 (to device) or 2 (to host)");
+    if (rows == 0 || row_bytes == 0) return SDB_STATUS_SUCCESS;
+    SDB_REQUIRE(dst && src, SDB_STATUS_INVALID_VALUE, "sdb_memcpy_2d: null pointer");
+    SDB_REQUIRE(dpitch >= row_bytes && spitch >= row_bytes, SDB_STATUS_INVALID_VALUE,
+                "sdb_memcpy_2d: a pitch is smaller than the row");
+    Context* ctx;
+    SDB_TRY(get_context(&ctx));
+    if (kind == 1) SDB_TRY(h2d_2d(ctx, dst, dpitch, src, spitch, row_bytes, rows));
+    else SDB_TRY(d2h_2d(ctx, dst, dpitch, src, spitch, row_bytes, rows));
     SDB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SDB_STATUS_SUCCESS;
 }

@@ -303,3 +303,30 @@ def test_optimize_makes_dot_product_mkl_reuse_the_handle_and_reach_the_streaming
         assert kernels[2].startswith("spmm_stream"), kernels
         with pytest.raises(ValueError):
             sdb.dot_product_mkl(ra, a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,row_elems,hpitch_elems,dpitch_elems", [(37, 1000, 1500, 1200), (3000, 9000, 20000, 9000),
+                                                                    (5, 3, 7, 3), (2000, 20000, 20000, 20000)])
+def test_memcpy_2d_round_trip(rows, row_elems, hpitch_elems, dpitch_elems):
+    """sdb_memcpy_2d: a column range of a pageable row-major array to the device and back (strided on either side,
+    staged through the page-locked ring by the copy threads), untouched bytes left alone."""
+    import ctypes as ct
+
+    rng = np.random.default_rng(rows)
+    src = rng.standard_normal((rows, hpitch_elems)).astype(np.float32)
+    dev = ct.c_void_p()
+    _lib.check(_lib.SDB.lib.sdb_dev_alloc(ct.byref(dev), rows * dpitch_elems * 4), "sdb_dev_alloc")
+    try:
+        off = (hpitch_elems - row_elems) // 2
+        _lib.check(_lib.SDB.lib.sdb_memcpy_2d(dev, dpitch_elems * 4, ct.c_void_p(src.ctypes.data + off * 4), hpitch_elems * 4,
+                                    row_elems * 4, rows, 1), "sdb_memcpy_2d")
+        back = np.full((rows, hpitch_elems + 3), 7.0, dtype=np.float32)
+        _lib.check(_lib.SDB.lib.sdb_memcpy_2d(ct.c_void_p(back.ctypes.data + 2 * 4), (hpitch_elems + 3) * 4, dev, dpitch_elems * 4,
+                                    row_elems * 4, rows, 2), "sdb_memcpy_2d")
+    finally:
+        _lib.check(_lib.SDB.lib.sdb_dev_free(dev), "sdb_dev_free")
+    assert np.array_equal(back[:, 2:2 + row_elems], src[:, off:off + row_elems])
+    assert np.all(back[:, :2] == 7.0) and np.all(back[:, 2 + row_elems:] == 7.0)
+    with pytest.raises(Exception):
+        _lib.check(_lib.SDB.lib.sdb_memcpy_2d(ct.c_void_p(back.ctypes.data), 4, dev, 8, 16, 2, 2), "sdb_memcpy_2d")
