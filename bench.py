@@ -802,6 +802,11 @@ def run_legs(args, peak):
                 r["roofline"] = roof(name, gb, ms, r.get("kernel", "spmm_bsr_kernel"))
                 r["config"] = "BASELINE configs[4] BSR variant: 1M x 1M, 62 500 block rows x 4 blocks of 16x16 fp32, " \
                               "x dense(1M x 256)"
+            elif name == "spmv":
+                r = rc.run_spmv(1_000_000, 1_000_000, 50)
+                r["roofline"] = roof(name, r["algorithmic_bytes"] / 1e9, r["spmv_ms"], "spmv_wide_kernel<float,16>")
+                r["config"] = "SURVEY 8f rank 2 (mkl_sparse_?_mv): the configs[1] matrix x one dense column, fp32, " \
+                              "beta = 0.5, operands in HBM"
             else:
                 r = {"skipped": "unknown leg"}
         except Exception as e:  # a leg must never take the headline down with it
@@ -825,7 +830,7 @@ def main():
     ap.add_argument("--no-probes", action="store_true")
     ap.add_argument("--no-autotune", action="store_true", help="N > 1: keep the library's default exchange strategy")
     ap.add_argument("--no-legs", action="store_true", help="N = 1: skip the configs[2] / [3] / BSR legs")
-    ap.add_argument("--legs", default="bsr16,spgemm_ef1,gram,spgemm_ef4")
+    ap.add_argument("--legs", default="bsr16,spmv,spgemm_ef1,gram,spgemm_ef4")
     ap.add_argument("--legs-budget", type=float, default=400.0, help="seconds after which remaining legs are skipped")
     ap.add_argument("--c5", action="store_true", help="N > 1: also run BASELINE configs[4] (default at N = 8)")
     ap.add_argument("--no-sharded-products", action="store_true", help="N > 1: skip the sharded SpGEMM / gram record")

@@ -324,6 +324,7 @@ SDB_API int        sdb_last_error(char* buf, int len);
  *   "dense_ctas"    SDB_DENSE_CTAS     resident CTAs per SM of that kernel (0 = as many as fit)
  *   "slab_keep"     SDB_SLAB_KEEP      streaming SpMM: gathers of X rows carry an L2 evict_last policy (0 / 1)
  *   "spgemm_sorted_cta" SDB_SPGEMM_SORTED_CTA  sorted SpGEMM: 1 keeps rows of 1025..4096 entries in the CTA hash bin (0: bitmap bin)
+ *   "spmv_wide"     SDB_SPMV_WIDE      SpMV: 0 automatic (16-byte loads of A, four entries per lane and step), 1 scalar loads
  * Unknown names return SDB_STATUS_INVALID_VALUE.  No reference counterpart (tuning aid for tests and sweeps). */
 SDB_API sdb_status sdb_set_option(const char* name, int value);
 

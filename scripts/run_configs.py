@@ -353,6 +353,47 @@ def run_c5bsr(block_rows, blocks_per_row, b, n):
     return res
 
 
+def run_spmv(rows, cols, per_row, dtype=np.float32):
+    """y = beta*y + A x on the configs[1] matrix (one dense column), operands in HBM; the
+    16-byte-load kernel and the scalar one ("spmv_wide" 0 / 1), every row checked against float64 numpy."""
+    a = cs.uniform_rows_csr(rows, cols, per_row, dtype, seed=2)
+    rng = np.random.default_rng(7)
+    x = rng.random(cols).astype(dtype)
+    y0 = rng.random(rows).astype(dtype)
+    es = np.dtype(dtype).itemsize
+    res = {"config": "spmv", "rows": rows, "cols": cols, "nnz": int(a.nnz), "dtype": np.dtype(dtype).name,
+           # A once (index + value per entry, 8 B of row offset per row), x once, y read and written
+           "algorithmic_bytes": int(a.nnz * (4 + es) + rows * 8 + cols * es + 2 * rows * es)}
+    want = 0.5 * y0.astype(np.float64) + a.astype(np.float64) @ x.astype(np.float64)
+    ha, _, _ = H.create(a)
+    with ha:
+        d_x, d_y = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.sdb_dev_alloc(C.byref(d_x), x.nbytes), "alloc")
+        _lib.check(lib.sdb_dev_alloc(C.byref(d_y), y0.nbytes), "alloc")
+        try:
+            _lib.check(lib.sdb_memcpy(d_x, x.ctypes.data_as(C.c_void_p), x.nbytes, 1), "memcpy")
+            one, half = _lib.scalar_pair(1.0), _lib.scalar_pair(0.5)
+            call = lambda: _lib.check(lib.sdb_spmm_dev(_lib.OP_N, one, ha.ref, _lib.LAYOUT_C, d_x, 1, 1, half, d_y,
+                                                       1, None), "sdb_spmm_dev")
+            for label, opt in (("scalar", 1), ("wide", 0)):
+                _lib.set_option("spmv_wide", opt)
+                _lib.check(lib.sdb_memcpy(d_y, y0.ctypes.data_as(C.c_void_p), y0.nbytes, 1), "memcpy")
+                call()
+                got = np.empty_like(y0)
+                _lib.check(lib.sdb_memcpy(got.ctypes.data_as(C.c_void_p), d_y, y0.nbytes, 2), "memcpy")
+                res[f"{label}_max_rel_err"] = float(np.max(np.abs(got - want) / np.abs(want)))
+                call()
+                ms, _ = timed(call, reps=50)
+                res[f"{label}_ms"] = ms
+                res[f"{label}_gbs"] = res["algorithmic_bytes"] / (ms * 1e-3) / 1e9
+            res["spmv_ms"] = res["wide_ms"]
+        finally:
+            _lib.set_option("spmv_wide", 0)
+            lib.sdb_dev_free(d_x)
+            lib.sdb_dev_free(d_y)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=["c1", "c3", "c4", "c5bsr"])
@@ -378,6 +419,10 @@ def main():
             r = run_c5(1_000_000, 1_000_000, 64, 256)
         elif w == "c5bsr":
             r = run_c5bsr(args.bsr_block_rows, 4, 16, 256)
+        elif w == "spmv":
+            r = run_spmv(1_000_000, 1_000_000, 50)
+        elif w == "spmv64":
+            r = run_spmv(1_000_000, 1_000_000, 50, np.float64)
         else:
             raise SystemExit(f"unknown config {w}")
         r["wall_s"] = time.perf_counter() - t0

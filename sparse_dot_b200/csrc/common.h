@@ -68,6 +68,7 @@ enum Option {
     kOptDenseCtas,      // "dense_ctas"    SDB_DENSE_CTAS     resident CTAs per SM of that kernel (0 = what fits)
     kOptSpgemmSortedCta,  // "spgemm_sorted_cta" SDB_SPGEMM_SORTED_CTA  sorted SpGEMM: 1 keeps 1025..4096-entry rows in the CTA hash bin
     kOptSlabKeep,       // "slab_keep"     SDB_SLAB_KEEP      streaming SpMM gathers with an L2 evict_last policy (0 / 1)
+    kOptSpmvWide,       // "spmv_wide"     SDB_SPMV_WIDE      SpMV: 0 auto (16-byte loads of A when rows are long enough), 1 scalar loads
     kOptCount
 };
 int get_option(Option o);

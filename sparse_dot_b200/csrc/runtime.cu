@@ -81,6 +81,7 @@ OptionSlot g_options[kOptCount] = {
     {"dense_ctas", "SDB_DENSE_CTAS", 0, {0}, {false}},
     {"spgemm_sorted_cta", "SDB_SPGEMM_SORTED_CTA", 0, {0}, {false}},
     {"slab_keep", "SDB_SLAB_KEEP", 0, {0}, {false}},
+    {"spmv_wide", "SDB_SPMV_WIDE", 0, {0}, {false}},
 };
 }  // namespace
 

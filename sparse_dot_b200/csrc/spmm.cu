@@ -277,11 +277,102 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t rows, const int64_t* 
     }
 }
 
+// Four consecutive stored values / column indices with 16-byte streaming loads (read exactly once).  `p` must be
+// 16-byte aligned: entry index a multiple of 4 from a 16-byte aligned base.
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+    const float4 q = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+}
+__device__ __forceinline__ void load4(const double* p, double (&v)[4]) {
+    const double2 q0 = __ldcs(reinterpret_cast<const double2*>(p)), q1 = __ldcs(reinterpret_cast<const double2*>(p) + 1);
+    v[0] = q0.x, v[1] = q0.y, v[2] = q1.x, v[3] = q1.y;
+}
+__device__ __forceinline__ void load4(const cf32* p, cf32 (&v)[4]) {
+    const float4 q0 = __ldcs(reinterpret_cast<const float4*>(p)), q1 = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = cf32{q0.x, q0.y}, v[1] = cf32{q0.z, q0.w}, v[2] = cf32{q1.x, q1.y}, v[3] = cf32{q1.z, q1.w};
+}
+__device__ __forceinline__ void load4(const cf64* p, cf64 (&v)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double2 q = __ldcs(reinterpret_cast<const double2*>(p) + i);
+        v[i] = cf64{q.x, q.y};
+    }
+}
+
+// The same product with 16-byte loads of A: every lane takes four consecutive entries per step (one int4 of column
+// indices, 16-64 bytes of values), so a warp has 4x the bytes in flight of spmv_kernel for the same occupancy — what
+// an HBM-bound stream of A wants.  Rows start anywhere: the entries before the first multiple-of-4 position and
+// after the last whole pack (at most 3 + 3) are taken one per lane.
+template <typename T, int LANES>
+__global__ void __launch_bounds__(256) spmv_wide_kernel(int64_t rows, const int64_t* __restrict__ indptr,
+                                                        const int32_t* __restrict__ indices,
+                                                        const T* __restrict__ values, bool conj_a,
+                                                        const T* __restrict__ x, int64_t incx, T alpha, T beta,
+                                                        T* __restrict__ y, int64_t incy) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LANES;
+    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / LANES;
+    T acc = Num<T>::zero();
+    if (row < rows) {
+        const int64_t b = indptr[row], e = indptr[row + 1];
+        const int64_t body = min(e, (b + 3) & ~int64_t(3));
+        const int64_t tail = body + ((e - body) & ~int64_t(3));
+        for (int64_t p = body + 4 * sub; p < tail; p += 4 * LANES) {
+            const int4 c = __ldcs(reinterpret_cast<const int4*>(indices + p));
+            T v[4];
+            load4(values + p, v);
+            if (conj_a) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = conj_(v[i]);
+            }
+            acc = madd(v[0], ldg(x + int64_t(c.x) * incx), acc);
+            acc = madd(v[1], ldg(x + int64_t(c.y) * incx), acc);
+            acc = madd(v[2], ldg(x + int64_t(c.z) * incx), acc);
+            acc = madd(v[3], ldg(x + int64_t(c.w) * incx), acc);
+        }
+        for (int64_t p = b + sub; p < body; p += LANES) {
+            T v = ldg(values + p);
+            if (conj_a) v = conj_(v);
+            acc = madd(v, ldg(x + int64_t(__ldg(indices + p)) * incx), acc);
+        }
+        for (int64_t p = tail + sub; p < e; p += LANES) {
+            T v = ldg(values + p);
+            if (conj_a) v = conj_(v);
+            acc = madd(v, ldg(x + int64_t(__ldg(indices + p)) * incx), acc);
+        }
+    }
+#pragma unroll
+    for (int d = LANES / 2; d > 0; d >>= 1) acc = add(acc, shfl(0xffffffffu, acc, (lane ^ d), 32));
+    if (row < rows && sub == 0) {
+        T* out = y + row * incy;
+        *out = Num<T>::is_zero(beta) ? mul(alpha, acc) : madd(alpha, acc, mul(beta, *out));
+    }
+}
+
 template <typename T>
 static sdb_status spmv(cudaStream_t s, const CsrView& a, bool conj_a, const double* alpha_d, const double* beta_d,
                        const void* dX, int64_t incx, void* dY, int64_t incy) {
     const T alpha = Num<T>::make(alpha_d[0], alpha_d[1]), beta = Num<T>::make(beta_d[0], beta_d[1]);
     const double mean = a.rows > 0 ? double(a.nnz) / double(a.rows) : 0.0;
+    // rows long enough to fill packs of four, arrays aligned for 16-byte loads: the wide kernel ("spmv_wide" 1 = never)
+    const bool packs_ok = ((reinterpret_cast<uintptr_t>(a.indices) | reinterpret_cast<uintptr_t>(a.values)) & 15u) == 0;
+    if (mean > 6 && packs_ok && get_option(kOptSpmvWide) != 1) {
+#define SDB_SPMV_WIDE(L)                                                                                       \
+    do {                                                                                                       \
+        const int64_t blocks = (a.rows * L + 255) / 256;                                                       \
+        SDB_REQUIRE(blocks < (int64_t(1) << 31), SDB_STATUS_NOT_SUPPORTED, "spmv: grid too large");             \
+        SDB_LAUNCH((spmv_wide_kernel<T, L>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices,         \
+                   static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,      \
+                   static_cast<T*>(dY), incy);                                                                 \
+        return SDB_STATUS_SUCCESS;                                                                             \
+    } while (0)
+        if (mean > 96) SDB_SPMV_WIDE(32);
+        if (mean > 48) SDB_SPMV_WIDE(16);
+        if (mean > 24) SDB_SPMV_WIDE(8);
+        if (mean > 12) SDB_SPMV_WIDE(4);
+        SDB_SPMV_WIDE(2);
+#undef SDB_SPMV_WIDE
+    }
 #define SDB_SPMV(L)                                                                                            \
     do {                                                                                                       \
         const int64_t blocks = (a.rows * L + 255) / 256;                                                       \

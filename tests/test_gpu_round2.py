@@ -330,3 +330,44 @@ def test_memcpy_2d_round_trip(rows, row_elems, hpitch_elems, dpitch_elems):
     assert np.all(back[:, :2] == 7.0) and np.all(back[:, 2 + row_elems:] == 7.0)
     with pytest.raises(Exception):
         _lib.check(_lib.SDB.lib.sdb_memcpy_2d(ct.c_void_p(back.ctypes.data), 4, dev, 8, 16, 2, 2), "sdb_memcpy_2d")
+
+
+# ===================================================== SpMV with 16-byte loads of A (spmv_wide_kernel)
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ALL4)
+@pytest.mark.parametrize("mean", [8, 15, 30, 60, 130])
+def test_spmv_wide_kernel_ragged_rows(dtype, mean):
+    """Every lanes-per-row specialisation of the 16-byte-load SpMV on rows of ragged length (empty rows, rows
+    shorter than a pack, rows starting at every position modulo 4), against float64 numpy and against the scalar
+    kernel (option spmv_wide = 1); conjugate transpose through the cached companion as well."""
+    rng = np.random.default_rng(mean)
+    rows, cols = 3001, 2500
+    lens = rng.integers(0, 2 * mean + 1, size=rows)
+    lens[::17] = 0
+    lens[5::31] = 1
+    indptr = np.zeros(rows + 1, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    indices = np.concatenate([np.sort(rng.choice(cols, size=k, replace=False)) for k in lens]).astype(np.int32)
+    data = rng.random(indptr[-1]) + 0.5
+    if np.dtype(dtype).kind == "c":
+        data = data + 1j * (rng.random(indptr[-1]) - 0.5)
+    a = sp.csr_matrix((data.astype(dtype), indices, indptr), shape=(rows, cols))
+    v = rng.random(cols).astype(dtype)
+    if np.dtype(dtype).kind == "c":
+        v = (v + 1j * rng.random(cols)).astype(dtype)
+    want = a.astype(np.complex128) @ v.astype(np.complex128)
+    tol = cs.TOL[np.dtype(dtype)]
+    try:
+        got = {}
+        for opt in (0, 1):
+            _lib.set_option("spmv_wide", opt)
+            got[opt] = sdb.dot_product_mkl(a, v)
+            assert np.abs(got[opt] - want).max() <= tol * np.abs(want).max()
+        assert np.abs(got[0] - got[1]).max() <= tol * np.abs(want).max()
+        _lib.set_option("spmv_wide", 0)
+        w = rng.random(rows).astype(dtype)
+        got_t = sdb.dot_product_mkl(w, a)
+        want_t = w.astype(np.complex128) @ a.astype(np.complex128)
+        assert np.abs(got_t - want_t).max() <= tol * np.abs(want_t).max()
+    finally:
+        _lib.set_option("spmv_wide", 0)
