@@ -325,6 +325,8 @@ SDB_API int        sdb_last_error(char* buf, int len);
  *   "slab_keep"     SDB_SLAB_KEEP      streaming SpMM: gathers of X rows carry an L2 evict_last policy (0 / 1)
  *   "spgemm_sorted_cta" SDB_SPGEMM_SORTED_CTA  sorted SpGEMM: 1 keeps rows of 1025..4096 entries in the CTA hash bin (0: bitmap bin)
  *   "spmv_wide"     SDB_SPMV_WIDE      SpMV: 0 automatic (16-byte loads of A, four entries per lane and step), 1 scalar loads
+ *   "spmv_tile"     SDB_SPMV_TILE      SpMV with x staged slab by slab in shared memory (inspector + executor, cached on the
+ *                                      handle): 0 automatic (from the second product of a large matrix with a vector), 1 never, 2 always
  * Unknown names return SDB_STATUS_INVALID_VALUE.  No reference counterpart (tuning aid for tests and sweeps). */
 SDB_API sdb_status sdb_set_option(const char* name, int value);
 

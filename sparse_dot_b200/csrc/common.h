@@ -69,6 +69,7 @@ enum Option {
     kOptSpgemmSortedCta,  // "spgemm_sorted_cta" SDB_SPGEMM_SORTED_CTA  sorted SpGEMM: 1 keeps 1025..4096-entry rows in the CTA hash bin
     kOptSlabKeep,       // "slab_keep"     SDB_SLAB_KEEP      streaming SpMM gathers with an L2 evict_last policy (0 / 1)
     kOptSpmvWide,       // "spmv_wide"     SDB_SPMV_WIDE      SpMV: 0 auto (16-byte loads of A when rows are long enough), 1 scalar loads
+    kOptSpmvTile,       // "spmv_tile"     SDB_SPMV_TILE      SpMV with x staged in shared memory: 0 auto (repeated products), 1 never, 2 always
     kOptCount
 };
 int get_option(Option o);
@@ -224,6 +225,16 @@ struct sdb_mat {
     int slab_rpw;
     int64_t slab_width;
     int spmm_calls;  // multiplications seen so far (inspector policy)
+    // Optional tile-ordered copy for the shared-memory SpMV (spmv_tile.cu, built on the second product with a
+    // vector): entries grouped by (row block, column slab), vt_rc[p] = local row << 15 | local column, vt_ptr the
+    // tile offsets.  vt_state: 0 not built, 1 built, -1 the inspector found the matrix too skewed.
+    void* vt_rc;
+    void* vt_val;
+    int64_t* vt_ptr;
+    int64_t vt_rb_rows;
+    int64_t vt_entries;
+    int vt_state;
+    int spmv_calls;
 };
 
 namespace sdb {
@@ -259,6 +270,11 @@ struct CsrView {
     int64_t sub_rows = -1;
 };
 sdb_status csr_view(Context* ctx, const sdb_mat* m, bool transpose, CsrView* v, bool want_pos = false);
+// shared-memory SpMV (spmv_tile.cu): policy, executor (+ inspector on first use), and release of the cached tiles
+bool spmv_tile_wanted(const CsrView& a, int dtype, int64_t incx, int64_t incy);
+sdb_status spmv_tile_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype, const double* alpha,
+                            const double* beta, const void* dX, void* dY);
+void drop_spmv_tiles(sdb_mat* m, cudaStream_t s);
 sdb_status sort_rows(Context* ctx, int dtype, int64_t rows, const int64_t* indptr, int32_t* indices,
                      void* values, int64_t elems_per_entry, int32_t* extra = nullptr);
 sdb_status expand_bsr(Context* ctx, const sdb_mat* bsr, sdb_mat** out_csr);

@@ -696,6 +696,7 @@ sdb_status sdb_order(sdb_mat* m) {
     if (m->slab_rc) cudaFreeAsync(m->slab_rc, ctx->stream);
     if (m->slab_val) cudaFreeAsync(m->slab_val, ctx->stream);
     m->slab_rc = m->slab_val = nullptr;
+    drop_spmv_tiles(m, ctx->stream);
     m->strict_sorted = 0;
     SDB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SDB_STATUS_SUCCESS;
@@ -715,6 +716,7 @@ sdb_status sdb_invalidate(sdb_mat* m) {
     if (m->slab_val) cudaFreeAsync(m->slab_val, ctx->stream);
     m->pos = nullptr;
     m->slab_rc = m->slab_val = nullptr;
+    drop_spmv_tiles(m, ctx->stream);
     m->strict_sorted = 0;
     m->spmm_calls = 0;
     SDB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -63,12 +63,13 @@ void free_handle(sdb_mat* m) {
         if (m->indices) cudaFreeAsync(m->indices, s);
         if (m->values) cudaFreeAsync(m->values, s);
     }
-    if (m->pos || m->slab_rc || m->slab_val) {
+    if (m->pos || m->slab_rc || m->slab_val || m->vt_ptr) {
         Context* ctx = nullptr;
         cudaStream_t fs = get_context(&ctx) == SDB_STATUS_SUCCESS ? ctx->stream : nullptr;
         if (m->pos) cudaFreeAsync(m->pos, fs);
         if (m->slab_rc) cudaFreeAsync(m->slab_rc, fs);
         if (m->slab_val) cudaFreeAsync(m->slab_val, fs);
+        drop_spmv_tiles(m, fs);
     }
     m->magic = 0;
     free(m);

@@ -82,6 +82,7 @@ OptionSlot g_options[kOptCount] = {
     {"spgemm_sorted_cta", "SDB_SPGEMM_SORTED_CTA", 0, {0}, {false}},
     {"slab_keep", "SDB_SLAB_KEEP", 0, {0}, {false}},
     {"spmv_wide", "SDB_SPMV_WIDE", 0, {0}, {false}},
+    {"spmv_tile", "SDB_SPMV_TILE", 0, {0}, {false}},
 };
 }  // namespace
 

@@ -364,6 +364,7 @@ static sdb_status spmv(cudaStream_t s, const CsrView& a, bool conj_a, const doub
         SDB_LAUNCH((spmv_wide_kernel<T, L>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices,         \
                    static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,      \
                    static_cast<T*>(dY), incy);                                                                 \
+        note_spmm_kernel("spmv_wide_kernel<%s,%d>", dtype_cname(Num<T>::dtype), L);                            \
         return SDB_STATUS_SUCCESS;                                                                             \
     } while (0)
         if (mean > 96) SDB_SPMV_WIDE(32);
@@ -380,6 +381,7 @@ static sdb_status spmv(cudaStream_t s, const CsrView& a, bool conj_a, const doub
         SDB_LAUNCH((spmv_kernel<T, L>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices,              \
                    static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,      \
                    static_cast<T*>(dY), incy);                                                                 \
+        note_spmm_kernel("spmv_kernel<%s,%d>", dtype_cname(Num<T>::dtype), L);                                 \
         return SDB_STATUS_SUCCESS;                                                                             \
     } while (0)
     if (mean > 48) SDB_SPMV(32);
@@ -425,6 +427,11 @@ sdb_status spmm_device(Context* ctx, cudaStream_t s, const CsrView& a, int dtype
     if (n == 1 && n_peers == 1 && row0 == 0 && a.sub_rows < 0) {
         // one column: the panel layout only decides the element strides
         const bool rm = layout == SDB_LAYOUT_ROW_MAJOR;
+        // repeated products with a vector: x staged in shared memory (spmv_tile.cu) unless the inspector declines
+        if (!conj_a && spmv_tile_wanted(a, dtype, rm ? ldx : 1, rm ? ldy : 1)) {
+            const sdb_status st = spmv_tile_device(ctx, s, a, dtype, alpha, beta, dX, dY_peers[0]);
+            if (st != SDB_STATUS_NOT_SUPPORTED) return st;
+        }
         return SDB_DISPATCH_DTYPE(dtype, T, [&]() -> sdb_status {
             return spmv<T>(s, a, conj_a, alpha, beta, dX, rm ? ldx : 1, dY_peers[0], rm ? ldy : 1);
         });

@@ -371,3 +371,88 @@ def test_spmv_wide_kernel_ragged_rows(dtype, mean):
         assert np.abs(got_t - want_t).max() <= tol * np.abs(want_t).max()
     finally:
         _lib.set_option("spmv_wide", 0)
+
+
+# ===================================================== SpMV with x staged in shared memory (spmv_tile.cu)
+def _ragged_csr(rows, cols, mean, dtype, seed, banded=False):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(0, 2 * mean + 1, size=rows)
+    lens[::17] = 0
+    indptr = np.zeros(rows + 1, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    if banded:  # columns next to the diagonal: whole rows fall into one column slab
+        start = (np.arange(rows) * (cols - 2 * mean - 1) // max(rows - 1, 1)).astype(np.int64)
+        indices = np.concatenate([start[i] + np.arange(k) for i, k in enumerate(lens)]).astype(np.int32)
+    else:
+        indices = np.concatenate([np.sort(rng.choice(cols, size=k, replace=False)) for k in lens]).astype(np.int32)
+    data = (rng.random(indptr[-1]) + 0.5).astype(dtype)
+    return sp.csr_matrix((data, indices, indptr), shape=(rows, cols))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(3001, 2500, 12, False), (40_000, 70_000, 9, False), (20_000, 50_000, 40, True),
+                                   (5, 40_000, 3, False)])
+def test_spmv_tile_kernel_forced(dtype, shape):
+    """Option spmv_tile = 2: the shared-memory SpMV on one-shot calls, several column slabs and row blocks, ragged
+    and empty rows, banded rows (every entry of a row in one slab), out= with beta 0 / 0.5 / 1, and the transposed
+    product through the cached companion; against float64 numpy."""
+    rows, cols, mean, banded = shape
+    a = _ragged_csr(rows, cols, mean, dtype, seed=rows + mean, banded=banded)
+    rng = np.random.default_rng(3)
+    v = rng.random(cols).astype(dtype)
+    want = a.astype(np.float64) @ v.astype(np.float64)
+    tol = cs.TOL[np.dtype(dtype)]
+    scale = max(np.abs(want).max(), 1e-30)
+    try:
+        _lib.set_option("spmv_tile", 2)
+        got = sdb.dot_product_mkl(a, v)
+        assert sdb.last_spmm_kernel().startswith("spmv_tile_kernel")
+        assert np.abs(got - want).max() <= tol * scale
+        for beta in (0.0, 0.5, 1.0):
+            out = np.full((rows, 1), np.nan if beta == 0.0 else 2.0, dtype=dtype)
+            got = sdb.dot_product_mkl(a, v.reshape(-1, 1), out=out, out_scalar=beta)
+            assert got is out
+            assert np.abs(got.ravel() - (want + 2.0 * beta)).max() <= tol * (scale + 2.0)
+        w = rng.random(rows).astype(dtype)
+        got_t = sdb.dot_product_mkl(w, a)
+        want_t = w.astype(np.float64) @ a.astype(np.float64)
+        assert np.abs(got_t - want_t).max() <= tol * max(np.abs(want_t).max(), 1e-30)
+    finally:
+        _lib.set_option("spmv_tile", 0)
+
+
+@pytest.mark.gpu
+def test_spmv_tile_kernel_is_picked_for_repeated_products():
+    """Automatic policy: a resident matrix large enough (4.5 M entries, x of 1.2 MB) runs the gather kernel on
+    its first product with a vector and the shared-memory kernel from the second on; sdb_invalidate (the values
+    changed) drops the cached tiles; a skewed matrix is declined by the inspector and stays on the gather kernel."""
+    a = cs.uniform_rows_csr(150_000, 300_000, 30, np.float32, seed=9)
+    x = np.random.default_rng(1).random((300_000, 1)).astype(np.float32)
+    want = a.astype(np.float64) @ x.astype(np.float64)
+    with sdb.optimize(a) as h:
+        names = []
+        for _ in range(3):
+            got = h.dot(x)
+            names.append(sdb.last_spmm_kernel())
+            assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+        assert not names[0].startswith("spmv_tile_kernel")
+        assert names[1].startswith("spmv_tile_kernel") and names[2].startswith("spmv_tile_kernel")
+        _lib.check(_lib.SDB.lib.sdb_invalidate(h.handle.ref), "sdb_invalidate")
+        h.dot(x)
+        assert not sdb.last_spmm_kernel().startswith("spmv_tile_kernel")
+    # half of the entries in the first 2 % of the rows: one row block would hold most of the work
+    rng = np.random.default_rng(2)
+    lens = np.full(150_000, 15)
+    lens[:3000] = 800
+    indptr = np.zeros(150_001, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    indices = rng.integers(0, 300_000, size=indptr[-1]).astype(np.int32)
+    skew = sp.csr_matrix((rng.random(indptr[-1]).astype(np.float32) + 0.5, indices, indptr), shape=(150_000, 300_000))
+    skew.sum_duplicates()
+    want = skew.astype(np.float64) @ x.astype(np.float64)
+    with sdb.optimize(skew) as h:
+        for _ in range(3):
+            got = h.dot(x)
+            assert not sdb.last_spmm_kernel().startswith("spmv_tile_kernel")
+            assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
