@@ -31,6 +31,7 @@ FAMILIES = {
     "spmm_rowmajor_kernel": "spmm_rowmajor_kernel",
     "spmm_bsr_kernel": "spmm_bsr_kernel",
     "spmv_wide_kernel": "spmv_wide_kernel",
+    "spmv_tile_kernel": "spmv_tile_kernel",
     "spmm_bsr_mma_kernel": "spmm_bsr_mma_kernel",
     "spgemm_dense_red_kernel": "spgemm_dense_red_kernel",
     "spgemm_": "spgemm_",
@@ -44,6 +45,7 @@ MATCH = {
     "spmm_bsr_mma_kernel<float,16,256,0,2>": "spmm_bsr_mma_kernelIfLi16ELi256ELb0ELi2E",
     "spmm_stream_half_kernel<float,6,16,4>": "spmm_stream_half_kernelIfLi6ELi16ELi4E",
     "spmv_wide_kernel<float,16>": "spmv_wide_kernelIfLi16E",
+    "spmv_tile_kernel<float>": "spmv_tile_kernelIfE",
 }
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 TSCALE = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "second": 1.0, "msecond": 1e-3, "usecond": 1e-6,
