@@ -72,6 +72,14 @@ class ResidentCSR:
         """op(A) @ x for a host array ``x`` (C or F ordered); same ``out`` / ``out_scalar`` rules as
         dot_product_mkl.  Only x (and ``out`` when it is accumulated into) is uploaded."""
         x = np.asarray(x)
+        if x.ndim == 1:
+            # a vector (what a CG / FGMRES loop passes): one column, the result comes back 1-D as well; from the
+            # second product on a large matrix runs the shared-memory SpMV (csrc/spmv_tile.cu)
+            if out is not None and out.ndim != 1:
+                raise ValueError("out must be a vector when x is one")
+            res = self.dot(x.reshape(-1, 1), out=None if out is None else out.reshape(-1, 1), out_scalar=out_scalar,
+                           transpose=transpose)
+            return out if out is not None else res.ravel()
         if x.ndim != 2 or x.shape[0] != self.shape[0 if transpose else 1]:
             raise ValueError(f"Matrix alignment error: {self.shape} * {x.shape} is not valid")
         if x.dtype != self.dtype:

@@ -456,3 +456,25 @@ def test_spmv_tile_kernel_is_picked_for_repeated_products():
             got = h.dot(x)
             assert not sdb.last_spmm_kernel().startswith("spmv_tile_kernel")
             assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.gpu
+def test_resident_matrix_times_vector_in_a_loop():
+    """What a CG / power-iteration caller does: y = A x with a resident A and 1-D vectors, again and again,
+    out= / out_scalar= included; the iterates match scipy's to fp32 tolerance."""
+    a = cs.uniform_rows_csr(4000, 4000, 12, np.float32, seed=3)
+    x = np.random.default_rng(4).random(4000).astype(np.float32)
+    with sdb.optimize(a) as h:
+        v, ref = x.copy(), x.astype(np.float64)
+        for _ in range(4):
+            v = sdb.dot_product_mkl(h, v)
+            v /= np.abs(v).max()
+            ref = a.astype(np.float64) @ ref
+            ref /= np.abs(ref).max()
+            assert v.ndim == 1 and np.abs(v - ref).max() <= 1e-5
+        out = np.ones(4000, dtype=np.float32)
+        got = h.dot(x, out=out, out_scalar=2.0)
+        assert got is out
+        assert np.abs(out - (a.astype(np.float64) @ x.astype(np.float64) + 2.0)).max() <= 1e-4
+        with pytest.raises(ValueError):
+            h.dot(x[:-1])
