@@ -804,7 +804,7 @@ def run_legs(args, peak):
                               "x dense(1M x 256)"
             elif name == "spmv":
                 r = rc.run_spmv(1_000_000, 1_000_000, 50)
-                r["roofline"] = roof(name, r["algorithmic_bytes"] / 1e9, r["spmv_ms"], r.get("kernel", "spmv_wide_kernel<float,16>"))
+                r["roofline"] = roof(name, r["algorithmic_bytes"] / 1e9, r["spmv_ms"], r.get("kernel", "spmv_wide_kernel<float,16,0>"))
                 r["config"] = "SURVEY 8f rank 2 (mkl_sparse_?_mv): the configs[1] matrix x one dense column, fp32, " \
                               "beta = 0.5, operands in HBM"
             else:

@@ -44,7 +44,7 @@ MATCH = {
     "spmm_rowmajor_kernel<float,4,32,2,8>": "spmm_rowmajor_kernelIfLi4ELi32ELi2ELi8E",
     "spmm_bsr_mma_kernel<float,16,256,0,2>": "spmm_bsr_mma_kernelIfLi16ELi256ELb0ELi2E",
     "spmm_stream_half_kernel<float,6,16,4>": "spmm_stream_half_kernelIfLi6ELi16ELi4E",
-    "spmv_wide_kernel<float,16>": "spmv_wide_kernelIfLi16E",
+    "spmv_wide_kernel<float,16,0>": "spmv_wide_kernelIfLi16ELb0E",
     "spmv_tile_kernel<float>": "spmv_tile_kernelIfE",
 }
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}

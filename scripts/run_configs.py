@@ -353,10 +353,11 @@ def run_c5bsr(block_rows, blocks_per_row, b, n):
     return res
 
 
-def run_spmv(rows, cols, per_row, dtype=np.float32):
+def run_spmv(rows, cols, per_row, dtype=np.float32, matrix=None):
     """y = beta*y + A x on the configs[1] matrix (one dense column), operands in HBM; the
     16-byte-load kernel and the scalar one ("spmv_wide" 0 / 1), every row checked against float64 numpy."""
-    a = cs.uniform_rows_csr(rows, cols, per_row, dtype, seed=2)
+    a = matrix if matrix is not None else cs.uniform_rows_csr(rows, cols, per_row, dtype, seed=2)
+    rows, cols = a.shape
     rng = np.random.default_rng(7)
     x = rng.random(cols).astype(dtype)
     y0 = rng.random(rows).astype(dtype)
@@ -378,6 +379,7 @@ def run_spmv(rows, cols, per_row, dtype=np.float32):
             for label, wide, tile in (("scalar", 1, 1), ("wide", 0, 1), ("tile", 0, 2), ("auto", 0, 0)):
                 _lib.set_option("spmv_wide", wide)
                 _lib.set_option("spmv_tile", tile)
+                _lib.check(lib.sdb_invalidate(ha.ref), "sdb_invalidate")  # every variant starts from a fresh handle state
                 _lib.check(lib.sdb_memcpy(d_y, y0.ctypes.data_as(C.c_void_p), y0.nbytes, 1), "memcpy")
                 t0 = time.perf_counter()
                 call()
@@ -430,6 +432,9 @@ def main():
             r = run_spmv(1_000_000, 1_000_000, 50)
         elif w == "spmv64":
             r = run_spmv(1_000_000, 1_000_000, 50, np.float64)
+        elif w == "spmv_rmat":  # power-law rows and columns: BASELINE configs[2]'s operand times a vector
+            r = run_spmv(0, 0, 0, matrix=cs.rmat_csr(args.scale, args.ef, np.float32, seed=1))
+            r["config"] = f"spmv_rmat scale {args.scale} ef {args.ef}"
         else:
             raise SystemExit(f"unknown config {w}")
         r["wall_s"] = time.perf_counter() - t0

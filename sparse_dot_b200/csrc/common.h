@@ -226,13 +226,15 @@ struct sdb_mat {
     int64_t slab_width;
     int spmm_calls;  // multiplications seen so far (inspector policy)
     // Optional tile-ordered copy for the shared-memory SpMV (spmv_tile.cu, built on the second product with a
-    // vector): entries grouped by (row block, column slab), vt_rc[p] = local row << 15 | local column, vt_ptr the
-    // tile offsets.  vt_state: 0 not built, 1 built, -1 the inspector found the matrix too skewed.
-    void* vt_rc;
-    void* vt_val;
-    int64_t* vt_ptr;
-    int64_t vt_rb_rows;
-    int64_t vt_entries;
+    // vector): entries grouped by (row block, column slab).  vt_state: 0 not built, 1 built, -1 the inspector
+    // could not balance the matrix (stays on the gather kernel).
+    // Rows longer than long_threshold entries (SpMV reduces those with one CTA each; spmm.cu): built on the first
+    // product with a vector, dropped with the other caches.  long_state: 0 unknown, 1 built (n_long may be 0).
+    int32_t* long_rows;
+    int32_t n_long;
+    int64_t long_threshold;
+    int long_state;
+    void* vt_cache;  // spmv_tile.cu's TileCache (host object owning the device arrays)
     int vt_state;
     int spmv_calls;
 };

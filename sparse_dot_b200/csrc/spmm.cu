@@ -21,6 +21,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <mutex>
+
 #include "common.h"
 #include "prims.h"
 #include "types.cuh"
@@ -251,15 +253,18 @@ static sdb_status pick_lanes(cudaStream_t s, const CsrView& a, bool conj_a, cons
 // mkl_sparse_?_mv (_sparse_vector.py:20-25,84-92): y = alpha * op(A) * x + beta * y.
 // A group of LANES lanes reduces one row: lanes stride the row's entries (coalesced index / value
 // loads, gathered x), then a shuffle tree adds the partial sums.  LANES follows the mean row length.
-template <typename T, int LANES>
+template <typename T, int LANES, bool LONG>
 __global__ void __launch_bounds__(256) spmv_kernel(int64_t rows, const int64_t* __restrict__ indptr,
                                                    const int32_t* __restrict__ indices,
                                                    const T* __restrict__ values, bool conj_a,
                                                    const T* __restrict__ x, int64_t incx, T alpha, T beta,
-                                                   T* __restrict__ y, int64_t incy) {
+                                                   T* __restrict__ y, int64_t incy, int64_t long_row) {
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES;
-    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / LANES;
+    int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / LANES;
+    // LONG: rows longer than long_row belong to spmv_long_rows_kernel (a separate instantiation: the check costs
+    // registers, and with them occupancy, that matrices without such rows should not pay)
+    if (LONG && row < rows && indptr[row + 1] - indptr[row] > long_row) row = rows;
     T acc = Num<T>::zero();
     if (row < rows) {
         const int64_t e = indptr[row + 1];
@@ -303,15 +308,16 @@ __device__ __forceinline__ void load4(const cf64* p, cf64 (&v)[4]) {
 // indices, 16-64 bytes of values), so a warp has 4x the bytes in flight of spmv_kernel for the same occupancy — what
 // an HBM-bound stream of A wants.  Rows start anywhere: the entries before the first multiple-of-4 position and
 // after the last whole pack (at most 3 + 3) are taken one per lane.
-template <typename T, int LANES>
+template <typename T, int LANES, bool LONG>
 __global__ void __launch_bounds__(256) spmv_wide_kernel(int64_t rows, const int64_t* __restrict__ indptr,
                                                         const int32_t* __restrict__ indices,
                                                         const T* __restrict__ values, bool conj_a,
                                                         const T* __restrict__ x, int64_t incx, T alpha, T beta,
-                                                        T* __restrict__ y, int64_t incy) {
+                                                        T* __restrict__ y, int64_t incy, int64_t long_row) {
     const int lane = threadIdx.x & 31;
     const int sub = lane % LANES;
-    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / LANES;
+    int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) / LANES;
+    if (LONG && row < rows && indptr[row + 1] - indptr[row] > long_row) row = rows;
     T acc = Num<T>::zero();
     if (row < rows) {
         const int64_t b = indptr[row], e = indptr[row + 1];
@@ -349,6 +355,116 @@ __global__ void __launch_bounds__(256) spmv_wide_kernel(int64_t rows, const int6
     }
 }
 
+// ---- rows far longer than the rest (power-law matrices: R-MAT scale 22 has rows of 10^5 entries next to a mean of 4)
+// A group of 2-32 lanes would walk such a row alone while the rest of the machine idles (measured: 1.89 ms for 16.6 M
+// entries).  They are listed once per handle and reduced by one CTA each; the group kernels skip them.
+constexpr int kLongThreads = 1024;
+
+__global__ void find_long_rows_kernel(int64_t rows, const int64_t* __restrict__ indptr, int64_t long_row,
+                                      int32_t capacity, int32_t* __restrict__ count, int32_t* __restrict__ list) {
+    const int64_t r = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r < rows && indptr[r + 1] - indptr[r] > long_row) {
+        const int32_t at = atomicAdd(count, 1);
+        if (at < capacity) list[at] = int32_t(r);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLongThreads) spmv_long_rows_kernel(const int32_t* __restrict__ list, int32_t n_long,
+                                                                    const int64_t* __restrict__ indptr,
+                                                                    const int32_t* __restrict__ indices,
+                                                                    const T* __restrict__ values, bool conj_a,
+                                                                    const T* __restrict__ x, int64_t incx, T alpha,
+                                                                    T beta, T* __restrict__ y, int64_t incy) {
+    __shared__ T part[kLongThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int32_t i = blockIdx.x; i < n_long; i += gridDim.x) {
+        const int64_t row = list[i];
+        const int64_t b = indptr[row], e = indptr[row + 1];
+        T acc0 = Num<T>::zero(), acc1 = Num<T>::zero();
+        int64_t p = b + threadIdx.x;
+        for (; p + kLongThreads < e; p += 2 * kLongThreads) {  // two independent chains per thread
+            T v0 = ldg(values + p), v1 = ldg(values + p + kLongThreads);
+            if (conj_a) v0 = conj_(v0), v1 = conj_(v1);
+            acc0 = madd(v0, ldg(x + int64_t(__ldg(indices + p)) * incx), acc0);
+            acc1 = madd(v1, ldg(x + int64_t(__ldg(indices + p + kLongThreads)) * incx), acc1);
+        }
+        if (p < e) {
+            T v = ldg(values + p);
+            if (conj_a) v = conj_(v);
+            acc0 = madd(v, ldg(x + int64_t(__ldg(indices + p)) * incx), acc0);
+        }
+        T acc = add(acc0, acc1);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc = add(acc, shfl(0xffffffffu, acc, lane ^ d, 32));
+        if (lane == 0) part[warp] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            acc = part[lane];  // kLongThreads / 32 == 32 partial sums
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc = add(acc, shfl(0xffffffffu, acc, lane ^ d, 32));
+            if (lane == 0) {
+                T* out = y + row * incy;
+                *out = Num<T>::is_zero(beta) ? mul(alpha, acc) : madd(alpha, acc, mul(beta, *out));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// The handle's list of rows longer than `long_row` (built on the first product with a vector; dropped with the
+// other per-handle caches).  Returns the count, 0 when there is none or the view has no owning handle.
+static sdb_status long_rows_of(cudaStream_t s, const CsrView& a, int64_t long_row, const int32_t** list, int32_t* n) {
+    *list = nullptr;
+    *n = 0;
+    sdb_mat* m = a.owner;
+    if (m == nullptr || !m->owns || a.sub_rows >= 0 || a.rows >= (int64_t(1) << 31)) return SDB_STATUS_SUCCESS;
+    std::lock_guard<std::mutex> cache_lock(g_companion_mutex);
+    if (m->long_state != 1 || m->long_threshold != long_row) {
+        if (m->long_rows) cudaFreeAsync(m->long_rows, s);
+        m->long_rows = nullptr;
+        m->n_long = 0;
+        const int64_t capacity = std::min<int64_t>(a.nnz / (long_row + 1) + 1, int64_t(1) << 30);
+        DevBuf count;
+        SDB_TRY(count.alloc(4, s));
+        SDB_CUDA(cudaMemsetAsync(count.p, 0, 4, s));
+        int32_t* d_list = nullptr;
+        SDB_TRY(dev_alloc(reinterpret_cast<void**>(&d_list), size_t(capacity) * 4, s));
+        SDB_LAUNCH(find_long_rows_kernel, unsigned((a.rows + 255) / 256), 256, 0, s, a.rows, a.indptr, long_row,
+                   int32_t(capacity), count.as<int32_t>(), d_list);
+        int32_t found = 0;
+        if (cudaMemcpyAsync(&found, count.p, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) {
+            cudaFreeAsync(d_list, s);
+            set_error("spmv: reading the long-row count failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return SDB_STATUS_EXECUTION_FAILED;
+        }
+        if (found == 0) {
+            cudaFreeAsync(d_list, s);
+            d_list = nullptr;
+        }
+        m->long_rows = d_list;
+        m->n_long = int32_t(std::min<int64_t>(found, capacity));
+        m->long_threshold = long_row;
+        m->long_state = 1;
+    }
+    *list = m->long_rows;
+    *n = m->n_long;
+    return SDB_STATUS_SUCCESS;
+}
+
+constexpr int kLongPerLane = 512;  // a row is "long" beyond this many entries per lane of its group
+
+template <typename T>
+static sdb_status long_rows_launch(cudaStream_t s, const CsrView& a, const int32_t* list, int32_t n_long, bool conj_a,
+                                   const void* dX, int64_t incx, T alpha, T beta, void* dY, int64_t incy) {
+    if (n_long <= 0) return SDB_STATUS_SUCCESS;
+    SDB_LAUNCH((spmv_long_rows_kernel<T>), unsigned(std::min<int32_t>(n_long, 1024)), kLongThreads, 0, s, list, n_long,
+               a.indptr, a.indices, static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha,
+               beta, static_cast<T*>(dY), incy);
+    return SDB_STATUS_SUCCESS;
+}
+
 template <typename T>
 static sdb_status spmv(cudaStream_t s, const CsrView& a, bool conj_a, const double* alpha_d, const double* beta_d,
                        const void* dX, int64_t incx, void* dY, int64_t incy) {
@@ -361,11 +477,20 @@ static sdb_status spmv(cudaStream_t s, const CsrView& a, bool conj_a, const doub
     do {                                                                                                       \
         const int64_t blocks = (a.rows * L + 255) / 256;                                                       \
         SDB_REQUIRE(blocks < (int64_t(1) << 31), SDB_STATUS_NOT_SUPPORTED, "spmv: grid too large");             \
-        SDB_LAUNCH((spmv_wide_kernel<T, L>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices,         \
-                   static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,      \
-                   static_cast<T*>(dY), incy);                                                                 \
-        note_spmm_kernel("spmv_wide_kernel<%s,%d>", dtype_cname(Num<T>::dtype), L);                            \
-        return SDB_STATUS_SUCCESS;                                                                             \
+        const int64_t long_row = int64_t(kLongPerLane) * L;                                                    \
+        const int32_t* long_list = nullptr;                                                                    \
+        int32_t n_long = 0;                                                                                    \
+        SDB_TRY(long_rows_of(s, a, long_row, &long_list, &n_long));                                            \
+        if (n_long > 0)                                                                                        \
+            SDB_LAUNCH((spmv_wide_kernel<T, L, true>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices, \
+                       static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,  \
+                       static_cast<T*>(dY), incy, long_row);                                                   \
+        else                                                                                                   \
+            SDB_LAUNCH((spmv_wide_kernel<T, L, false>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices, \
+                       static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,  \
+                       static_cast<T*>(dY), incy, 0);                                                          \
+        note_spmm_kernel("spmv_wide_kernel<%s,%d,%d>", dtype_cname(Num<T>::dtype), L, n_long > 0 ? 1 : 0);     \
+        return long_rows_launch<T>(s, a, long_list, n_long, conj_a, dX, incx, alpha, beta, dY, incy);                                                                             \
     } while (0)
         if (mean > 96) SDB_SPMV_WIDE(32);
         if (mean > 48) SDB_SPMV_WIDE(16);
@@ -378,11 +503,20 @@ static sdb_status spmv(cudaStream_t s, const CsrView& a, bool conj_a, const doub
     do {                                                                                                       \
         const int64_t blocks = (a.rows * L + 255) / 256;                                                       \
         SDB_REQUIRE(blocks < (int64_t(1) << 31), SDB_STATUS_NOT_SUPPORTED, "spmv: grid too large");             \
-        SDB_LAUNCH((spmv_kernel<T, L>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices,              \
-                   static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,      \
-                   static_cast<T*>(dY), incy);                                                                 \
-        note_spmm_kernel("spmv_kernel<%s,%d>", dtype_cname(Num<T>::dtype), L);                                 \
-        return SDB_STATUS_SUCCESS;                                                                             \
+        const int64_t long_row = int64_t(kLongPerLane) * L;                                                    \
+        const int32_t* long_list = nullptr;                                                                    \
+        int32_t n_long = 0;                                                                                    \
+        SDB_TRY(long_rows_of(s, a, long_row, &long_list, &n_long));                                            \
+        if (n_long > 0)                                                                                        \
+            SDB_LAUNCH((spmv_kernel<T, L, true>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices,    \
+                       static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,  \
+                       static_cast<T*>(dY), incy, long_row);                                                   \
+        else                                                                                                   \
+            SDB_LAUNCH((spmv_kernel<T, L, false>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices,   \
+                       static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,  \
+                       static_cast<T*>(dY), incy, 0);                                                          \
+        note_spmm_kernel("spmv_kernel<%s,%d,%d>", dtype_cname(Num<T>::dtype), L, n_long > 0 ? 1 : 0);          \
+        return long_rows_launch<T>(s, a, long_list, n_long, conj_a, dX, incx, alpha, beta, dY, incy);                                                                             \
     } while (0)
     if (mean > 48) SDB_SPMV(32);
     if (mean > 24) SDB_SPMV(16);

@@ -424,10 +424,11 @@ def test_spmv_tile_kernel_forced(dtype, shape):
 
 @pytest.mark.gpu
 def test_spmv_tile_kernel_is_picked_for_repeated_products():
-    """Automatic policy: a resident matrix large enough (4.5 M entries, x of 1.2 MB) runs the gather kernel on
+    """Automatic policy: a resident matrix large enough (6 M entries, x of 1.2 MB) runs the gather kernel on
     its first product with a vector and the shared-memory kernel from the second on; sdb_invalidate (the values
-    changed) drops the cached tiles; a skewed matrix is declined by the inspector and stays on the gather kernel."""
-    a = cs.uniform_rows_csr(150_000, 300_000, 30, np.float32, seed=9)
+    changed) drops the cached tiles; a skewed matrix is balanced by work; one with too few entries per tile is
+    declined by the inspector and stays on the gather kernel."""
+    a = cs.uniform_rows_csr(150_000, 300_000, 40, np.float32, seed=9)
     x = np.random.default_rng(1).random((300_000, 1)).astype(np.float32)
     want = a.astype(np.float64) @ x.astype(np.float64)
     with sdb.optimize(a) as h:
@@ -441,9 +442,9 @@ def test_spmv_tile_kernel_is_picked_for_repeated_products():
         _lib.check(_lib.SDB.lib.sdb_invalidate(h.handle.ref), "sdb_invalidate")
         h.dot(x)
         assert not sdb.last_spmm_kernel().startswith("spmv_tile_kernel")
-    # half of the entries in the first 2 % of the rows: one row block would hold most of the work
+    # half of the entries in the first 2 % of the rows: row blocks of equal work (not equal height) still balance it
     rng = np.random.default_rng(2)
-    lens = np.full(150_000, 15)
+    lens = np.full(150_000, 25)
     lens[:3000] = 800
     indptr = np.zeros(150_001, dtype=np.int64)
     np.cumsum(lens, out=indptr[1:])
@@ -452,10 +453,42 @@ def test_spmv_tile_kernel_is_picked_for_repeated_products():
     skew.sum_duplicates()
     want = skew.astype(np.float64) @ x.astype(np.float64)
     with sdb.optimize(skew) as h:
-        for _ in range(3):
+        for i in range(3):
             got = h.dot(x)
+            assert sdb.last_spmm_kernel().startswith("spmv_tile_kernel") == (i >= 1)
+            assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    # too few entries per tile (12 per row over 2 M columns: every row block would stream 8 MB of x through shared
+    # memory for 130 k entries): declined by the inspector, the gather kernel keeps serving it
+    thin = cs.uniform_rows_csr(400_000, 2_000_000, 12, np.float32, seed=11)
+    xt = np.random.default_rng(5).random((2_000_000, 1)).astype(np.float32)
+    want = thin.astype(np.float64) @ xt.astype(np.float64)
+    with sdb.optimize(thin) as h:
+        for _ in range(3):
+            got = h.dot(xt)
             assert not sdb.last_spmm_kernel().startswith("spmv_tile_kernel")
             assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_spmv_tile_kernel_on_a_power_law_matrix(dtype):
+    """R-MAT rows and columns (BASELINE configs[2]'s generator): a few rows and columns hold most of the entries;
+    forced shared-memory SpMV against float64 numpy, both directions."""
+    a = cs.rmat_csr(16, 8, dtype, seed=5)
+    rng = np.random.default_rng(6)
+    v = rng.random(a.shape[1]).astype(dtype)
+    want = a.astype(np.float64) @ v.astype(np.float64)
+    tol = cs.TOL[np.dtype(dtype)]
+    try:
+        _lib.set_option("spmv_tile", 2)
+        got = sdb.dot_product_mkl(a, v)
+        assert sdb.last_spmm_kernel().startswith("spmv_tile_kernel")
+        assert np.abs(got - want).max() <= tol * np.abs(want).max()
+        got_t = sdb.dot_product_mkl(v, a)
+        want_t = v.astype(np.float64) @ a.astype(np.float64)
+        assert np.abs(got_t - want_t).max() <= tol * np.abs(want_t).max()
+    finally:
+        _lib.set_option("spmv_tile", 0)
 
 
 @pytest.mark.gpu
@@ -478,3 +511,49 @@ def test_resident_matrix_times_vector_in_a_loop():
         assert np.abs(out - (a.astype(np.float64) @ x.astype(np.float64) + 2.0)).max() <= 1e-4
         with pytest.raises(ValueError):
             h.dot(x[:-1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ALL4)
+def test_spmv_rows_far_longer_than_the_rest(dtype):
+    """Power-law rows: a mean of ~6 entries per row selects 2-4 lanes per row, and the rows beyond 512 entries per
+    lane (here 2 600 and 2 999 entries, and an R-MAT matrix's head rows) are reduced by one CTA each
+    (spmv_long_rows_kernel); both directions, out= with a scalar, against float64 numpy."""
+    rng = np.random.default_rng(12)
+    rows, cols = 20_000, 3000
+    lens = rng.integers(0, 13, size=rows)
+    lens[5], lens[777], lens[rows - 1] = 2600, 2999, 2100
+    indptr = np.zeros(rows + 1, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    indices = np.concatenate([np.sort(rng.choice(cols, size=k, replace=False)) for k in lens]).astype(np.int32)
+    data = rng.random(indptr[-1]) + 0.5
+    v = rng.random(cols)
+    if np.dtype(dtype).kind == "c":
+        data = data + 1j * (rng.random(indptr[-1]) - 0.5)
+        v = v + 1j * rng.random(cols)
+    a = sp.csr_matrix((data.astype(dtype), indices, indptr), shape=(rows, cols))
+    v = v.astype(dtype)
+    tol = cs.TOL[np.dtype(dtype)]
+    want = a.astype(np.complex128) @ v.astype(np.complex128)
+    for wide in (0, 1):
+        try:
+            _lib.set_option("spmv_wide", wide)
+            got = sdb.dot_product_mkl(a, v)
+            assert np.abs(got - want).max() <= tol * np.abs(want).max()
+            out = np.ones(rows, dtype=dtype)
+            got = sdb.dot_product_mkl(a, v, out=out, out_scalar=0.5)
+            assert got is out and np.abs(out - (want + 0.5)).max() <= tol * np.abs(want).max()
+        finally:
+            _lib.set_option("spmv_wide", 0)
+    w = rng.random(rows).astype(dtype)
+    got_t = sdb.dot_product_mkl(w, a)
+    want_t = w.astype(np.complex128) @ a.astype(np.complex128)
+    assert np.abs(got_t - want_t).max() <= tol * np.abs(want_t).max()
+    if np.dtype(dtype).kind != "c":
+        g = cs.rmat_csr(17, 8, dtype, seed=3)
+        x = rng.random(g.shape[1]).astype(dtype)
+        with sdb.optimize(g) as h:
+            for _ in range(2):
+                got = h.dot(x)
+                want = g.astype(np.float64) @ x.astype(np.float64)
+                assert np.abs(got - want).max() <= tol * np.abs(want).max()
