@@ -41,7 +41,7 @@ MATCH = {
     "spmm_stream_kernel<float,6,32,2,2>": "spmm_stream_kernelIfLi6ELi32ELi2ELi2ELb0",
     "spmm_bsr_kernel<float,16,256,0,2>": "spmm_bsr_kernelIfLi16ELi256ELb0ELi2E",
     "spgemm_dense_red_kernel<float>": "spgemm_dense_red_kernelIf",
-    "spmm_rowmajor_kernel<float,4,32,2,8>": "spmm_rowmajor_kernelIfLi4ELi32ELi2ELi8E",
+    "spmm_rowmajor_kernel<float,4,32,2,8>": "spmm_rowmajor_kernelIfLi4ELi32ELi2ELi8ELb0E",
     "spmm_bsr_mma_kernel<float,16,256,0,2>": "spmm_bsr_mma_kernelIfLi16ELi256ELb0ELi2E",
     "spmm_stream_half_kernel<float,6,16,4>": "spmm_stream_half_kernelIfLi6ELi16ELi4E",
     "spmv_wide_kernel<float,16,0>": "spmv_wide_kernelIfLi16ELb0E",

@@ -228,12 +228,12 @@ struct sdb_mat {
     // Optional tile-ordered copy for the shared-memory SpMV (spmv_tile.cu, built on the second product with a
     // vector): entries grouped by (row block, column slab).  vt_state: 0 not built, 1 built, -1 the inspector
     // could not balance the matrix (stays on the gather kernel).
-    // Rows longer than long_threshold entries (SpMV reduces those with one CTA each; spmm.cu): built on the first
-    // product with a vector, dropped with the other caches.  long_state: 0 unknown, 1 built (n_long may be 0).
-    int32_t* long_rows;
-    int32_t n_long;
-    int64_t long_threshold;
-    int long_state;
+    // Rows longer than long_threshold entries (SpMV / SpMM give those one CTA each; spmm.cu): built on the first
+    // product, dropped with the other caches.  long_state: 0 unknown, 1 built (n_long may be 0).
+    int32_t* long_rows[2];  // slot 0: the SpMV kernels' threshold, slot 1: the SpMM kernel's
+    int32_t n_long[2];
+    int64_t long_threshold[2];
+    int long_state[2];
     void* vt_cache;  // spmv_tile.cu's TileCache (host object owning the device arrays)
     int vt_state;
     int spmv_calls;

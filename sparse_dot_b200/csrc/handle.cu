@@ -63,7 +63,7 @@ void free_handle(sdb_mat* m) {
         if (m->indices) cudaFreeAsync(m->indices, s);
         if (m->values) cudaFreeAsync(m->values, s);
     }
-    if (m->pos || m->slab_rc || m->slab_val || m->vt_cache || m->long_rows) {
+    if (m->pos || m->slab_rc || m->slab_val || m->vt_cache || m->long_rows[0] || m->long_rows[1]) {
         Context* ctx = nullptr;
         cudaStream_t fs = get_context(&ctx) == SDB_STATUS_SUCCESS ? ctx->stream : nullptr;
         if (m->pos) cudaFreeAsync(m->pos, fs);

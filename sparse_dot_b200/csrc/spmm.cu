@@ -95,12 +95,12 @@ template <typename T, int VEC> __device__ __forceinline__ void store_pack(T* p, 
     }
 }
 
-template <typename T, int VEC, int LANES, int UNROLL = kUnroll, int MINB = 1>
+template <typename T, int VEC, int LANES, int UNROLL = kUnroll, int MINB = 1, bool LONG = false>
 __global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
     spmm_rowmajor_kernel(int64_t rows, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                          const T* __restrict__ values, bool conj_a, const T* __restrict__ X, int64_t ldx, int64_t n,
                          T alpha, T beta, T* __restrict__ y_self, PeerPanels<T> out, int n_peers, int self, int64_t row0,
-                         int64_t ldy) {
+                         int64_t ldy, int long_row) {
     constexpr int kRowsPerWarp = 32 / LANES;
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int kU = LANES < UNROLL ? LANES : UNROLL;  // gathers in flight per lane
@@ -122,6 +122,10 @@ __global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
         ci += start;
         cv += start;
     }
+    // LONG (a separate instantiation: the default one keeps its schedule): rows longer than long_row are left to
+    // spmm_long_rows_kernel, which spreads their entries over a whole CTA
+    const bool skipped = LONG && len > long_row;
+    if (LONG && skipped) len = 0;
     // the warp iterates together: shuffles need every lane, groups may differ in length
     int maxlen = len;
     if (LANES < 32) {
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
     }
 
     if (!(row_ok && col_ok)) return;
+    if (LONG && skipped) return;
     const int64_t off = (row0 + row) * ldy + col0;
     Pack<T, VEC> y;
     if (Num<T>::is_zero(beta)) {
@@ -188,11 +193,24 @@ __global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
     }
 }
 
+// rows far longer than the rest (defined next to the SpMV kernels below)
+constexpr int kSpmmLongRow = 1024;
+static sdb_status long_rows_of(cudaStream_t s, const CsrView& a, int slot, int64_t long_row, const int32_t** list,
+                               int32_t* n);
+template <typename T>
+static sdb_status spmm_long_rows_launch(cudaStream_t s, const CsrView& a, const int32_t* list, int32_t n_long,
+                                        bool conj_a, const T* X, int64_t ldx, int64_t n, T alpha, T beta, T* Y,
+                                        int64_t row0, int64_t ldy);
+
 template <typename T, int VEC, int LANES>
 static sdb_status launch_rowmajor(cudaStream_t s, const CsrView& a, bool conj_a, const T* X, int64_t ldx, int64_t n,
                                   T alpha, T beta, const PeerPanels<T>& out, int n_peers, int self, int64_t row0,
                                   int64_t ldy) {
     constexpr int kRowsPerCta = kSpmmWarps * (32 / LANES);
+    // single-GPU whole-matrix products: rows beyond kSpmmLongRow entries (power-law matrices) go to their own kernel
+    const int32_t* long_list = nullptr;
+    int32_t n_long = 0;
+    if (n_peers == 1 && a.sub_rows < 0) SDB_TRY(long_rows_of(s, a, 1, kSpmmLongRow, &long_list, &n_long));
     const int64_t sub_rows = a.sub_rows < 0 ? a.rows : a.sub_rows;  // row sub-range of the view (default: all)
     const int64_t* sub_indptr = a.indptr + a.sub_begin;
     row0 += a.sub_begin;
@@ -203,7 +221,13 @@ static sdb_status launch_rowmajor(cudaStream_t s, const CsrView& a, bool conj_a,
     note_spmm_kernel("spmm_rowmajor_kernel<%s,%d,%d,%d,%d>", dtype_cname(Num<T>::dtype), VEC, LANES, U, MB);                    \
     SDB_LAUNCH((spmm_rowmajor_kernel<T, VEC, LANES, U, MB>), dim3(unsigned(gx), unsigned(gy)), kSpmmWarps * 32, 0, s, \
                sub_rows, sub_indptr, a.indices, static_cast<const T*>(a.values), conj_a, X, ldx, n, alpha, beta,    \
-               out.y[self], out, n_peers, self, row0, ldy)
+               out.y[self], out, n_peers, self, row0, ldy, 0)
+#define SDB_SPMM_LAUNCH_LONG(U, MB)                                                                             \
+    note_spmm_kernel("spmm_rowmajor_kernel<%s,%d,%d,%d,%d,long>", dtype_cname(Num<T>::dtype), VEC, LANES, U, MB);   \
+    SDB_LAUNCH((spmm_rowmajor_kernel<T, VEC, LANES, U, MB, true>), dim3(unsigned(gx), unsigned(gy)), kSpmmWarps * 32, \
+               0, s, sub_rows, sub_indptr, a.indices, static_cast<const T*>(a.values), conj_a, X, ldx, n, alpha,    \
+               beta, out.y[self], out, n_peers, self, row0, ldy, kSpmmLongRow);                                     \
+    return spmm_long_rows_launch<T>(s, a, long_list, n_long, conj_a, X, ldx, n, alpha, beta, out.y[self], row0, ldy)
     if (LANES == 32 && VEC * sizeof(T) == 16) {
         // full-warp rows (the headline shape): tuning variants selectable for experiments
         static const int tune = [] {
@@ -224,13 +248,20 @@ static sdb_status launch_rowmajor(cudaStream_t s, const CsrView& a, bool conj_a,
             case 11: SDB_SPMM_LAUNCH(kUnroll, 1); return SDB_STATUS_SUCCESS;
             default: break;
         }
+        if (n_long > 0) {
+            SDB_SPMM_LAUNCH_LONG(2, 8);
+        }
         // measured on B200 (profiles/README.md, round 1): full occupancy (32 registers, 8 CTAs x 8 warps per
         // SM) with 2 gathers in flight per lane beats deeper unrolling at 3 CTAs/SM by 22 %
         SDB_SPMM_LAUNCH(2, 8);
         return SDB_STATUS_SUCCESS;
     }
+    if (n_long > 0) {
+        SDB_SPMM_LAUNCH_LONG(kUnroll, 1);
+    }
     SDB_SPMM_LAUNCH(kUnroll, 1);
 #undef SDB_SPMM_LAUNCH
+#undef SDB_SPMM_LAUNCH_LONG
     return SDB_STATUS_SUCCESS;
 }
 
@@ -414,16 +445,18 @@ __global__ void __launch_bounds__(kLongThreads) spmv_long_rows_kernel(const int3
 
 // The handle's list of rows longer than `long_row` (built on the first product with a vector; dropped with the
 // other per-handle caches).  Returns the count, 0 when there is none or the view has no owning handle.
-static sdb_status long_rows_of(cudaStream_t s, const CsrView& a, int64_t long_row, const int32_t** list, int32_t* n) {
+// slot 0: the SpMV kernels' threshold, slot 1: the SpMM kernel's
+static sdb_status long_rows_of(cudaStream_t s, const CsrView& a, int slot, int64_t long_row, const int32_t** list,
+                               int32_t* n) {
     *list = nullptr;
     *n = 0;
     sdb_mat* m = a.owner;
     if (m == nullptr || !m->owns || a.sub_rows >= 0 || a.rows >= (int64_t(1) << 31)) return SDB_STATUS_SUCCESS;
     std::lock_guard<std::mutex> cache_lock(g_companion_mutex);
-    if (m->long_state != 1 || m->long_threshold != long_row) {
-        if (m->long_rows) cudaFreeAsync(m->long_rows, s);
-        m->long_rows = nullptr;
-        m->n_long = 0;
+    if (m->long_state[slot] != 1 || m->long_threshold[slot] != long_row) {
+        if (m->long_rows[slot]) cudaFreeAsync(m->long_rows[slot], s);
+        m->long_rows[slot] = nullptr;
+        m->n_long[slot] = 0;
         const int64_t capacity = std::min<int64_t>(a.nnz / (long_row + 1) + 1, int64_t(1) << 30);
         DevBuf count;
         SDB_TRY(count.alloc(4, s));
@@ -443,13 +476,74 @@ static sdb_status long_rows_of(cudaStream_t s, const CsrView& a, int64_t long_ro
             cudaFreeAsync(d_list, s);
             d_list = nullptr;
         }
-        m->long_rows = d_list;
-        m->n_long = int32_t(std::min<int64_t>(found, capacity));
-        m->long_threshold = long_row;
-        m->long_state = 1;
+        m->long_rows[slot] = d_list;
+        m->n_long[slot] = int32_t(std::min<int64_t>(found, capacity));
+        m->long_threshold[slot] = long_row;
+        m->long_state[slot] = 1;
     }
-    *list = m->long_rows;
-    *n = m->n_long;
+    *list = m->long_rows[slot];
+    *n = m->n_long[slot];
+    return SDB_STATUS_SUCCESS;
+}
+
+// SpMM on a long row: the CTA's threads form G groups of cw columns; group g takes entries g, g + G, ... of the row
+// (four gathers in flight per thread, X rows read coalesced across the group), the partial rows are added up in
+// shared memory.  Panels wider than cw columns are swept in chunks.
+template <typename T>
+__global__ void __launch_bounds__(kLongThreads) spmm_long_rows_kernel(const int32_t* __restrict__ list, int32_t n_long,
+                                                                    const int64_t* __restrict__ indptr,
+                                                                    const int32_t* __restrict__ indices,
+                                                                    const T* __restrict__ values, bool conj_a,
+                                                                    const T* __restrict__ X, int64_t ldx, int64_t n,
+                                                                    int cw, T alpha, T beta, T* __restrict__ Y,
+                                                                    int64_t row0, int64_t ldy) {
+    __shared__ T partial[kLongThreads];
+    const int groups = kLongThreads / cw;
+    const int c = threadIdx.x % cw, g = threadIdx.x / cw;
+    for (int32_t i = blockIdx.x; i < n_long; i += gridDim.x) {
+        const int64_t row = list[i];
+        const int64_t b = indptr[row], e = indptr[row + 1];
+        for (int64_t cb = 0; cb < n; cb += cw) {
+            const int64_t col = cb + c;
+            const bool live = col < n && g < groups;
+            T acc[4] = {Num<T>::zero(), Num<T>::zero(), Num<T>::zero(), Num<T>::zero()};
+            if (live) {
+                int64_t p = b + g;
+                for (; p + 3 * int64_t(groups) < e; p += 4 * int64_t(groups)) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        T v = ldg(values + p + u * int64_t(groups));
+                        if (conj_a) v = conj_(v);
+                        acc[u] = madd(v, ldg(X + int64_t(__ldg(indices + p + u * int64_t(groups))) * ldx + col), acc[u]);
+                    }
+                }
+                for (; p < e; p += groups) {
+                    T v = ldg(values + p);
+                    if (conj_a) v = conj_(v);
+                    acc[0] = madd(v, ldg(X + int64_t(__ldg(indices + p)) * ldx + col), acc[0]);
+                }
+            }
+            partial[threadIdx.x] = add(add(acc[0], acc[1]), add(acc[2], acc[3]));
+            __syncthreads();
+            if (g == 0 && col < n) {
+                T sum = partial[c];
+                for (int k = 1; k < groups; ++k) sum = add(sum, partial[k * cw + c]);
+                T* out = Y + (row0 + row) * ldy + col;
+                *out = Num<T>::is_zero(beta) ? mul(alpha, sum) : madd(alpha, sum, mul(beta, *out));
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <typename T>
+static sdb_status spmm_long_rows_launch(cudaStream_t s, const CsrView& a, const int32_t* list, int32_t n_long,
+                                        bool conj_a, const T* X, int64_t ldx, int64_t n, T alpha, T beta, T* Y,
+                                        int64_t row0, int64_t ldy) {
+    if (n_long <= 0) return SDB_STATUS_SUCCESS;
+    const int cw = int(std::min<int64_t>(128, (n + 31) / 32 * 32));
+    SDB_LAUNCH((spmm_long_rows_kernel<T>), unsigned(std::min<int32_t>(n_long, 1024)), kLongThreads, 0, s, list, n_long,
+               a.indptr, a.indices, static_cast<const T*>(a.values), conj_a, X, ldx, n, cw, alpha, beta, Y, row0, ldy);
     return SDB_STATUS_SUCCESS;
 }
 
@@ -480,7 +574,7 @@ static sdb_status spmv(cudaStream_t s, const CsrView& a, bool conj_a, const doub
         const int64_t long_row = int64_t(kLongPerLane) * L;                                                    \
         const int32_t* long_list = nullptr;                                                                    \
         int32_t n_long = 0;                                                                                    \
-        SDB_TRY(long_rows_of(s, a, long_row, &long_list, &n_long));                                            \
+        SDB_TRY(long_rows_of(s, a, 0, long_row, &long_list, &n_long));                                            \
         if (n_long > 0)                                                                                        \
             SDB_LAUNCH((spmv_wide_kernel<T, L, true>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices, \
                        static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,  \
@@ -506,7 +600,7 @@ static sdb_status spmv(cudaStream_t s, const CsrView& a, bool conj_a, const doub
         const int64_t long_row = int64_t(kLongPerLane) * L;                                                    \
         const int32_t* long_list = nullptr;                                                                    \
         int32_t n_long = 0;                                                                                    \
-        SDB_TRY(long_rows_of(s, a, long_row, &long_list, &n_long));                                            \
+        SDB_TRY(long_rows_of(s, a, 0, long_row, &long_list, &n_long));                                            \
         if (n_long > 0)                                                                                        \
             SDB_LAUNCH((spmv_kernel<T, L, true>), unsigned(blocks), 256, 0, s, a.rows, a.indptr, a.indices,    \
                        static_cast<const T*>(a.values), conj_a, static_cast<const T*>(dX), incx, alpha, beta,  \

@@ -352,10 +352,12 @@ void drop_spmv_tiles(sdb_mat* m, cudaStream_t s) {
     m->vt_state = 0;
     m->spmv_calls = 0;
     // the long-row list of the gather SpMV (spmm.cu) depends on the same structure
-    if (m->long_rows) cudaFreeAsync(m->long_rows, s);
-    m->long_rows = nullptr;
-    m->n_long = 0;
-    m->long_state = 0;
+    for (int slot = 0; slot < 2; ++slot) {
+        if (m->long_rows[slot]) cudaFreeAsync(m->long_rows[slot], s);
+        m->long_rows[slot] = nullptr;
+        m->n_long[slot] = 0;
+        m->long_state[slot] = 0;
+    }
 }
 
 // Policy ("spmv_tile": 0 automatic, 1 never, 2 whenever the shape allows).  Automatic: the handle has been

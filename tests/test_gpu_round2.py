@@ -557,3 +557,58 @@ def test_spmv_rows_far_longer_than_the_rest(dtype):
                 got = h.dot(x)
                 want = g.astype(np.float64) @ x.astype(np.float64)
                 assert np.abs(got - want).max() <= tol * np.abs(want).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ALL4)
+@pytest.mark.parametrize("n", [3, 32, 100, 128, 200])
+def test_spmm_rows_far_longer_than_the_rest(dtype, n):
+    """Power-law rows in sparse x dense: rows beyond 1024 entries (here 2 600, 2 999 and 1 025, next to a mean of 6)
+    go to spmm_long_rows_kernel, the others stay in the row-gather kernel's 'long' instantiation; C and F ordered
+    panels, out= with a scalar, the transposed product; against complex128 numpy."""
+    rng = np.random.default_rng(n)
+    rows, cols = 6000, 3000
+    lens = rng.integers(0, 13, size=rows)
+    lens[5], lens[777], lens[rows - 1], lens[4000] = 2600, 2999, 1025, 1024
+    indptr = np.zeros(rows + 1, dtype=np.int64)
+    np.cumsum(lens, out=indptr[1:])
+    indices = np.concatenate([np.sort(rng.choice(cols, size=k, replace=False)) for k in lens]).astype(np.int32)
+    data = rng.random(indptr[-1]) + 0.5
+    x = rng.random((cols, n))
+    if np.dtype(dtype).kind == "c":
+        data = data + 1j * (rng.random(indptr[-1]) - 0.5)
+        x = x + 1j * rng.random((cols, n))
+    a = sp.csr_matrix((data.astype(dtype), indices, indptr), shape=(rows, cols))
+    x = x.astype(dtype)
+    tol = cs.TOL[np.dtype(dtype)]
+    want = a.astype(np.complex128) @ x.astype(np.complex128)
+    scale = np.abs(want).max()
+    got = sdb.dot_product_mkl(a, x)
+    assert np.abs(got - want).max() <= tol * scale
+    with sdb.optimize(a) as h:  # (large panels go through the row-chunk pipeline, whose chunks carry no handle)
+        got = h.dot(x)
+        assert "long" in sdb.last_spmm_kernel()
+        assert np.abs(got - want).max() <= tol * scale
+    got_f = sdb.dot_product_mkl(a, np.asfortranarray(x))
+    assert np.abs(got_f - want).max() <= tol * scale
+    out = np.ones((rows, n), dtype=dtype)
+    got = sdb.dot_product_mkl(a, x, out=out, out_scalar=0.5)
+    assert got is out and np.abs(out - (want + 0.5)).max() <= tol * scale
+    w = rng.random((n, rows)).astype(dtype)
+    got_t = sdb.dot_product_mkl(w, a)  # dense x sparse: the transposed companion has long rows of its own or none
+    want_t = w.astype(np.complex128) @ a.astype(np.complex128)
+    assert np.abs(got_t - want_t).max() <= tol * np.abs(want_t).max()
+
+
+@pytest.mark.gpu
+def test_spmm_on_a_power_law_matrix_keeps_its_results_when_repeated():
+    """R-MAT scale 17 x dense 64 with a resident handle: the long-row list is built once and reused; csc input too."""
+    g = cs.rmat_csr(17, 16, np.float32, seed=4)
+    x = np.random.default_rng(1).random((g.shape[1], 64)).astype(np.float32)
+    want = g.astype(np.float64) @ x.astype(np.float64)
+    with sdb.optimize(g) as h:
+        for _ in range(3):
+            got = h.dot(x)
+            assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    got = sdb.dot_product_mkl(g.tocsc(), x)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
