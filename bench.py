@@ -138,34 +138,53 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- ncu traffic, tied to the SASS
-def sass_sha(kernel_substr):
-    """sha1 of the instruction text of every function of libsdb200's objects whose mangled name contains
-    `kernel_substr` (addresses, comments and the names themselves left out), or None when cuobjdump / the
-    objects are not there.  The ncu DRAM bytes in profiles/kernel_traffic.json are only quoted for the SASS they
-    were captured from."""
+_SASS_FUNCS = None  # [(mangled name, instruction text)] of every function of libsdb200's objects, read once
+
+
+def _sass_functions():
+    global _SASS_FUNCS
+    if _SASS_FUNCS is not None:
+        return _SASS_FUNCS or None
     obj_dir = os.path.join(ROOT, "sparse_dot_b200", "csrc", "_obj")
+    funcs = []
     try:
         objs = sorted(f for f in os.listdir(obj_dir) if f.endswith(".o"))
-    except OSError:
+        for o in objs:
+            out = subprocess.run(["cuobjdump", "-sass", os.path.join(obj_dir, o)], capture_output=True, text=True,
+                                 timeout=300).stdout
+            name, text = None, []
+            for line in out.splitlines():
+                m = re.match(r"\s*Function : (\S+)", line)
+                if m:
+                    if name is not None:
+                        funcs.append((name, "".join(text)))
+                    name, text = m.group(1), []
+                    continue
+                if name is not None:
+                    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
+                    if m:
+                        text.append(m.group(1))
+            if name is not None:
+                funcs.append((name, "".join(text)))
+    except (OSError, subprocess.TimeoutExpired):
+        funcs = []
+    _SASS_FUNCS = funcs
+    return funcs or None
+
+
+def sass_sha(kernel_substr):
+    """sha1 of the instruction text of every function of libsdb200's objects whose mangled name contains
+    `kernel_substr` (addresses, comments and the names themselves left out; objects in name order, functions in file
+    order), or None when cuobjdump / the objects are not there or nothing matches.  The ncu DRAM bytes in
+    profiles/kernel_traffic.json are only quoted for the SASS they were captured from."""
+    funcs = _sass_functions()
+    if funcs is None:
         return None
     h, found = hashlib.sha1(), False
-    for o in objs:
-        try:
-            out = subprocess.run(["cuobjdump", "-sass", os.path.join(obj_dir, o)], capture_output=True, text=True,
-                                 timeout=120).stdout
-        except (OSError, subprocess.TimeoutExpired):
-            return None
-        keep = False
-        for line in out.splitlines():
-            m = re.match(r"\s*Function : (\S+)", line)
-            if m:
-                keep = kernel_substr in m.group(1)
-                found = found or keep
-                continue  # names are not hashed: only the instruction text of the matching functions, in file order
-            if keep:
-                m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
-                if m:
-                    h.update(m.group(1).encode())
+    for name, text in funcs:
+        if kernel_substr in name:
+            found = True
+            h.update(text.encode())
     return h.hexdigest() if found else None
 
 

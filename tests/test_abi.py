@@ -109,6 +109,24 @@ def test_bench_helpers():
     assert abs(bench.algorithmic_bytes(1_000_000, 50_000_000, 128) - 27.032e9) < 1e7
 
 
+def test_traffic_table_entries_name_kernels_of_the_build():
+    """profiles/kernel_traffic.json: every entry's match string must resolve to a kernel of the built objects (else
+    bench.py could never quote it), and its fields must be the ones bench.py reads."""
+    import importlib.util
+    import json
+
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    table = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))["kernels"]
+    assert "spmm_stream_kernel<float,6,32,2,2>" in table
+    if bench.sass_sha("spmm_stream_kernel") is None:
+        pytest.skip("cuobjdump or the objects are not available here")
+    for name, entry in table.items():
+        assert entry["dram_bytes_per_launch"] > 0 and len(entry["sass_sha1"]) == 40, name
+        assert bench.sass_sha(entry["sass_match"]) is not None, f"{name}: no kernel matches {entry['sass_match']}"
+
+
 def test_host_copy_pool_copies_correctly_and_reports_a_rate():
     """kind 3 of sdb_probe_bandwidth runs without a GPU: the pageable -> staging copies of the host pipeline
     (worker threads, non-temporal stores), verified byte for byte inside the probe."""
